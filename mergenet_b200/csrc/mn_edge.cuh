@@ -1,0 +1,291 @@
+// mn_edge.cuh -- edge construction for the merge segmenter (sm_100a).
+//
+// Kernel 1  mn_edge_pass_kernel   (HBM-bound streaming pass; THE roofline kernel)
+//   reference: Object ctor cc:5-21 (+ h:295-297) and the (pixel,offset) AdjacencyRecord ctor
+//   cc:24-36, i.e. per pixel  clp[c] = logf(class[c,p]), cls = first argmax, and per pixel x offset
+//   same = logf(s), diff = (float)log(1.0 - (double)s) with s read at the SOURCE pixel (h:301-303).
+//   A tile of TP consecutive pixels needs one contiguous TP*4-byte segment of each of the C+K input
+//   planes and nothing else (no halo: the neighbour contributes no probability), so each
+//   plane segment is brought to shared memory by ONE 1-D TMA bulk copy (cp.async.bulk + mbarrier),
+//   double buffered; every input byte is read exactly once for all K offsets, including the large
+//   occlusion offsets.  Results are staged in shared memory and leave as TMA bulk stores.
+//   Algorithmic bytes per pixel: 4*(C+K) read + 4*(C+2K) written (+4 for cls).
+//
+// Kernel 2  mn_record_init_kernel
+//   reference: cc:209-231 + SortAndUpdateHash cc:49-56 + UpdateMergePriority cc:145-150.
+//   Per record slot r = pixel*K + k: bounds test, endpoints (lo,hi), oml = same - diff, the initial
+//   merge priority (needs the neighbour's class / class vector -> separate pass after kernel 1),
+//   the (lo,hi)->record hash insert, the per-pixel live-record bit masks, and the 64-bit sort key
+//   of the initial queue entry (sentinel when mp < 0 or the slot does not exist, cc:225-227).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "mn_common.h"
+#include "mn_layout.h"
+
+// ---- PTX helpers: mbarrier + 1-D TMA bulk copies --------------------------------------------
+__device__ __forceinline__ uint32_t mn_smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mn_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mn_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mn_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mn_smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mn_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(mn_smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void mn_tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                               uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          mn_smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(mn_smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mn_tma_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"(mn_smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mn_tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void mn_tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void mn_fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// diff = (float)log(1.0 - (double)s)   (cc:34).  1.0 - s is exact in fp64 for s >= 2^-23.
+__device__ __forceinline__ float mn_log1m_exact(float s) { return (float)log(1.0 - (double)s); }
+
+// same_different_bias transform (cc:183-195), evaluated like the reference: logf + fp64 log,
+// rounded to float, expf, then 1/(1+e) in fp64 rounded to float.
+__device__ __forceinline__ float mn_bias_sameness(float s, float sdb, const MnLogfTab* tab) {
+  float logit = (float)(((double)mn_logf_exact(s, tab) - log(1.0 - (double)s)) + (double)sdb);
+  return (float)(1.0 / (1.0 + (double)expf(-logit)));
+}
+
+struct MnEdgeParams {
+  const float* class_pred;  // [B][C][N]
+  const float* adj_pred;    // [B][K][N]
+  float* adj_pred_rw;       // same buffer, written in place when sdb != 0 (cc:187-191), else null
+  float* clp;               // [B][N][C]
+  int* cls;                 // [B][N]
+  float* rec_same;          // [B][N*K]
+  float* rec_diff;          // [B][N*K]
+  int B, C, K, N;
+  int TP;                   // pixels per tile (multiple of 4)
+  int tiles_per_image;
+  int use_tma;              // N % 4 == 0 and 16-byte aligned bases
+  float sdb;
+};
+
+// dynamic smem layout: [bar0, bar1][pad to 128][in0][in1][out_clp][out_same][out_diff][logf tab]
+__global__ void __launch_bounds__(512, 1) mn_edge_pass_kernel(MnEdgeParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int C = P.C, K = P.K, TP = P.TP, NPL = C + K;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* in0 = reinterpret_cast<float*>(smem_raw + 128);
+  float* in1 = in0 + (size_t)NPL * TP;
+  float* out_clp = in1 + (size_t)NPL * TP;
+  float* out_same = out_clp + (size_t)C * TP;
+  float* out_diff = out_same + (size_t)K * TP;
+  MnLogfTab* tab = reinterpret_cast<MnLogfTab*>(out_diff + (size_t)K * TP);
+
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid < 16) {
+    const MnLogfTab t16[16] = {MN_LOGF_TABLE};
+    tab[tid] = t16[tid];
+  }
+  if (tid == 0) {
+    mn_mbar_init(&bars[0], 1);
+    mn_mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long total_tiles = (long long)P.B * P.tiles_per_image;
+  auto issue = [&](long long tile, int stage) {
+    // one elected thread: arm the barrier, then one bulk copy per input plane
+    int b = (int)(tile / P.tiles_per_image);
+    int start = (int)(tile % P.tiles_per_image) * TP;
+    int tl = min(TP, P.N - start);
+    float* dst = stage ? in1 : in0;
+    const float* cbase = P.class_pred + ((size_t)b * C) * P.N + start;
+    const float* abase = P.adj_pred + ((size_t)b * K) * P.N + start;
+    mn_mbar_expect_tx(&bars[stage], (uint32_t)(NPL * tl * 4));
+    for (int pl = 0; pl < C; pl++)
+      mn_tma_load_1d(dst + (size_t)pl * TP, cbase + (size_t)pl * P.N, tl * 4, &bars[stage]);
+    for (int pl = 0; pl < K; pl++)
+      mn_tma_load_1d(dst + (size_t)(C + pl) * TP, abase + (size_t)pl * P.N, tl * 4, &bars[stage]);
+  };
+
+  uint32_t phase[2] = {0, 0};
+  long long tile = blockIdx.x;
+  if (P.use_tma && tid == 0 && tile < total_tiles) issue(tile, 0);
+  int stage = 0;
+  for (; tile < total_tiles; tile += gridDim.x, stage ^= 1) {
+    const int b = (int)(tile / P.tiles_per_image);
+    const int start = (int)(tile % P.tiles_per_image) * TP;
+    const int tl = min(TP, P.N - start);
+    float* in = stage ? in1 : in0;
+    if (P.use_tma) {
+      // prefetch the next tile into the other stage (its previous readers passed the
+      // __syncthreads at the end of the last iteration)
+      long long nxt = tile + gridDim.x;
+      if (tid == 0 && nxt < total_tiles) {
+        mn_fence_proxy_async();
+        issue(nxt, stage ^ 1);
+      }
+      mn_mbar_wait(&bars[stage], phase[stage]);
+      phase[stage] ^= 1;
+    } else {
+      const float* cbase = P.class_pred + ((size_t)b * C) * P.N + start;
+      const float* abase = P.adj_pred + ((size_t)b * K) * P.N + start;
+      for (int i = tid; i < NPL * tl; i += nt) {
+        int pl = i / tl, px = i - pl * tl;
+        in[(size_t)pl * TP + px] =
+            pl < C ? cbase[(size_t)pl * P.N + px] : abase[(size_t)(pl - C) * P.N + px];
+      }
+      __syncthreads();
+    }
+    // previous tile's bulk stores must have finished READING the staging buffers
+    if (tid == 0) mn_tma_store_wait_read();
+    __syncthreads();
+
+    // ---- compute: one item per (plane, pixel); consecutive lanes -> consecutive pixels ----
+    const int items = NPL * tl;
+    for (int i = tid; i < items; i += nt) {
+      int pl = i / tl, px = i - pl * tl;
+      float v = in[(size_t)pl * TP + px];
+      if (pl < C) {
+        out_clp[px * C + pl] = MN_FADD(0.0f, mn_logf_exact(v, tab));  // cc:11-16
+      } else {
+        int k = pl - C;
+        if (P.sdb != 0.0f) {  // cc:183-195, in place on the caller's buffer
+          v = mn_bias_sameness(v, P.sdb, tab);
+          P.adj_pred_rw[((size_t)b * K + k) * P.N + start + px] = v;
+        }
+        out_same[px * K + k] = mn_logf_exact(v, tab);  // cc:35
+        out_diff[px * K + k] = mn_log1m_exact(v);      // cc:34
+      }
+    }
+    __syncthreads();
+    // ---- first-argmax class per pixel (cc:18-20) ----
+    for (int px = tid; px < tl; px += nt) {
+      const float* v = out_clp + px * C;
+      float best = v[0];
+      int bc = 0;
+      for (int c = 1; c < C; c++) {
+        float x = v[c];
+        if (x > best) {
+          best = x;
+          bc = c;
+        }
+      }
+      P.cls[(size_t)b * P.N + start + px] = bc;
+    }
+    // ---- results leave as bulk stores (contiguous in global: pixel-major tiles) ----
+    float* g_clp = P.clp + ((size_t)b * P.N + start) * C;
+    float* g_same = P.rec_same + ((size_t)b * P.N + start) * K;
+    float* g_diff = P.rec_diff + ((size_t)b * P.N + start) * K;
+    if (P.use_tma) {
+      mn_fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        mn_tma_store_1d(g_clp, out_clp, (uint32_t)(tl * C * 4));
+        mn_tma_store_1d(g_same, out_same, (uint32_t)(tl * K * 4));
+        mn_tma_store_1d(g_diff, out_diff, (uint32_t)(tl * K * 4));
+        mn_tma_store_commit();
+      }
+    } else {
+      __syncthreads();
+      for (int i = tid; i < tl * C; i += nt) g_clp[i] = out_clp[i];
+      for (int i = tid; i < tl * K; i += nt) {
+        g_same[i] = out_same[i];
+        g_diff[i] = out_diff[i];
+      }
+    }
+    __syncthreads();  // everyone is done with `in` before it is refilled
+  }
+  if (tid == 0) mn_tma_store_wait_read();
+}
+
+// ---------------------------------------------------------------------------------------------
+struct MnRecInitParams {
+  MnImage img0;  // image 0's pointers; image b = img0 advanced by b * stride (see mn_layout.h)
+  MnStrides st;
+  int B, H, W, C, K, N;
+  int off_r[MN_MAX_K], off_c[MN_MAX_K];
+  int rank_of_k[MN_MAX_K];  // rank of |linear delta| among the offsets (tie-break ordinal)
+  float omf, mlb;
+};
+
+__global__ void __launch_bounds__(256) mn_record_init_kernel(MnRecInitParams P) {
+  const long long E = (long long)P.N * P.K;
+  const long long total = E * P.B;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(g / E);
+    const int r = (int)(g - (long long)b * E);
+    MnImage im = mn_image_at(P.img0, P.st, b);
+    const int p = r / P.K, k = r - p * P.K;
+    const int row = p / P.W, col = p - row * P.W;
+    if (k == 0) {
+      // live-record masks: bit k = record (p,k) exists; bit 16+k = record (p - o_k, k) exists
+      uint32_t m = 0;
+      for (int kk = 0; kk < P.K; kk++) {
+        int r2 = row + P.off_r[kk], c2 = col + P.off_c[kk];
+        if (r2 >= 0 && r2 < P.H && c2 >= 0 && c2 < P.W) m |= 1u << kk;
+        r2 = row - P.off_r[kk];
+        c2 = col - P.off_c[kk];
+        if (r2 >= 0 && r2 < P.H && c2 >= 0 && c2 < P.W) m |= 1u << (16 + kk);
+      }
+      im.live_mask[p] = m;
+      im.parent[p] = p;
+      im.obj_nc[p] = mn_pack_nc(1, im.cls[p]);
+      im.obj_same[p] = 0.0f;
+      im.pl_head[p] = -1;
+      im.pl_tail[p] = -1;
+    }
+    const int r2 = row + P.off_r[k], c2 = col + P.off_c[k];
+    uint64_t key = ~0ull;
+    if (r2 >= 0 && r2 < P.H && c2 >= 0 && c2 < P.W) {
+      const int q = r2 * P.W + c2;
+      const int lo = p < q ? p : q, hi = p < q ? q : p;  // cc:49-56
+      const float same = im.rec_same[r], diff = im.rec_diff[r];
+      const float oml = MN_FSUB(same, diff);  // cc:36
+      const int cl = im.cls[lo], ch = im.cls[hi];
+      const float mp = mn_priority(oml, P.omf, P.mlb, P.C, 1, cl, im.clp + (size_t)lo * P.C, 1, ch,
+                                   im.clp + (size_t)hi * P.C, nullptr);  // cc:45
+      im.rec_lh[r] = make_int2(lo, hi);
+      im.rec_val[r] = make_float4(oml, same, diff, mp);
+      mn_hash_insert(im, lo, hi, r);
+      if (mp >= 0.0f) {  // cc:225-227
+        uint32_t ord = (uint32_t)lo * (uint32_t)P.K + (uint32_t)P.rank_of_k[k];
+        key = ((uint64_t)(~mn_f2u(mp)) << MN_ORD_BITS) | ord;
+      }
+    } else {
+      im.rec_lh[r] = make_int2(-1, -1);
+      im.rec_val[r] = make_float4(0.f, 0.f, 0.f, -1.0f);
+    }
+    im.init_keys[r] = key;
+  }
+}

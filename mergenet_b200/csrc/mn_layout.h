@@ -1,0 +1,236 @@
+// mn_layout.h -- per-image device workspace of the merge segmenter and the small data-structure
+// primitives every kernel shares (packed object word, (lo,hi)->record hash, SPMD/atomic shims).
+//
+// HBM layout per image (N = H*W pixels, E = N*K record slots, slot r = pixel*K + k):
+//   objects   clp[N*C] f32 | obj_nc[N] (npix | cls<<24) | obj_same[N] f32 | parent[N] | live_mask[N]
+//             | pl_head[N] pl_tail[N] + pixel-list chunk pool           (Object, h:85-137)
+//   records   rec_lh[E] int2 (lo,hi; lo=-1 = dead) | rec_val[E] float4 (oml,same,diff,mp)
+//             (AdjacencyRecord, h:175-232)
+//   hash      2-choice, 8-slot buckets of u32 (fingerprint<<26 | rec+1): (lo,hi) -> record
+//             (replaces the per-object unordered_map lookups of cc:685-688)
+//   queue     init_keys[E] u64, sorted: the initial priority-queue entries (cc:225-227);
+//             a radix tree of unsorted entry chunks for entries created later (cc:564,697,705);
+//             the entry pool aliases rec_same/rec_diff, which are dead after record init.
+#pragma once
+#include <stdint.h>
+
+#include "mn_common.h"
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#else
+struct int2 { int x, y; };
+struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r = {x, y, z, w}; return r; }
+struct float4 { float x, y, z, w; };
+static inline int2 make_int2(int x, int y) { int2 r = {x, y}; return r; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r = {x, y}; return r; }
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
+#endif
+
+// ---- SPMD shims: the scheduler is written as phases of `for (i = tid; i < n; i += nt)` loops
+// separated by block barriers, with all cross-thread traffic through shared/global arrays and
+// atomics.  Compiled for the host (tests/emul) it runs with one logical thread. -----------------
+#if defined(__CUDA_ARCH__)
+#define MN_SYNC() __syncthreads()
+#define MN_TID ((int)threadIdx.x)
+#define MN_NT ((int)blockDim.x)
+#define MN_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define MN_ATOMIC_SUB(p, v) atomicSub((p), (v))
+#define MN_ATOMIC_MIN(p, v) atomicMin((p), (v))
+#define MN_ATOMIC_MAX(p, v) atomicMax((p), (v))
+#define MN_ATOMIC_OR(p, v) atomicOr((p), (v))
+#define MN_ATOMIC_AND(p, v) atomicAnd((p), (v))
+#define MN_ATOMIC_CAS(p, c, v) atomicCAS((p), (c), (v))
+#else
+#define MN_SYNC() ((void)0)
+#define MN_TID 0
+#define MN_NT 1
+template <typename T> static inline T mn_h_add(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <typename T> static inline T mn_h_sub(T* p, T v) { T o = *p; *p = o - v; return o; }
+template <typename T> static inline T mn_h_min(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <typename T> static inline T mn_h_max(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <typename T> static inline T mn_h_or(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <typename T> static inline T mn_h_and(T* p, T v) { T o = *p; *p = o & v; return o; }
+template <typename T> static inline T mn_h_cas(T* p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
+#define MN_ATOMIC_ADD(p, v) mn_h_add((p), (v))
+#define MN_ATOMIC_SUB(p, v) mn_h_sub((p), (v))
+#define MN_ATOMIC_MIN(p, v) mn_h_min((p), (v))
+#define MN_ATOMIC_MAX(p, v) mn_h_max((p), (v))
+#define MN_ATOMIC_OR(p, v) mn_h_or((p), (v))
+#define MN_ATOMIC_AND(p, v) mn_h_and((p), (v))
+#define MN_ATOMIC_CAS(p, c, v) mn_h_cas((p), (c), (v))
+#endif
+
+#define MN_ORD_BITS 25       // initial-entry tie-break ordinal lo*K + rank  (N*K <= 2^25)
+#define MN_PLC 30            // pixels per pixel-list chunk (+ next, cnt = 32 words)
+#define MN_QCH 16            // queue entries per tree chunk (16 B each)
+#define MN_HASH_FP_SHIFT 26  // slot = fingerprint(6) << 26 | (rec + 1)
+#define MN_TREE_FANOUT 64    // children per split (6-bit digits)
+
+// queue tree roots: one per 2^12 float-bit patterns over [MN_ROOT_LO, MN_ROOT_HI)
+#define MN_ROOT_SHIFT 12
+#define MN_ROOT_LO_BITS 0x39800000u  // 2^-12
+#define MN_ROOT_HI_BITS 0x43800000u  // 2^8
+#define MN_NROOTS (((MN_ROOT_HI_BITS - MN_ROOT_LO_BITS) >> MN_ROOT_SHIFT) + 2)
+
+enum MnStatus {
+  MN_OK = 0,
+  MN_ERR_BAD_ARG = 1,
+  MN_ERR_PL_POOL = 2,     // pixel-list chunk pool exhausted
+  MN_ERR_Q_POOL = 3,      // queue entry pool exhausted
+  MN_ERR_TREE_POOL = 4,   // queue tree node pool exhausted
+  MN_ERR_HASH_FULL = 5,   // both hash buckets full and overflow area full
+  MN_ERR_INTERNAL = 6,    // an invariant failed (the reference would exit(1): cc:42,667,672)
+  MN_ERR_CUDA = 7,
+  MN_ERR_LIMIT = 8        // iteration guard tripped
+};
+
+// per-image control block (global memory)
+struct MnCtl {
+  int status;
+  int n_init;          // non-sentinel entries in init_keys
+  int static_cursor;
+  int plc_bump, plc_free_top;
+  int qc_bump, qc_free_top;
+  int tn_bump;
+  int hash_ovf_n;
+  int tree_entries;    // entries currently stored in the tree
+  int n_instances;     // output: labels 1..n
+  int fail_line;       // source line of the first failure (diagnostics)
+  // statistics (north star: per-round latency, round count, merges/s)
+  long long rounds, events, merges, restores, invalid_pops, solo_events;
+  long long refills, flushes, splits, pairs, cuts_conflict, cuts_cascade, cuts_capacity;
+  long long cycles_total;
+};
+
+struct MnImage {
+  // objects
+  float* clp;
+  int* cls;  // argmax class per pixel from the edge pass (consumed by record init)
+  uint32_t* obj_nc;
+  float* obj_same;
+  int* parent;
+  uint32_t* live_mask;
+  int* pl_head;
+  int* pl_tail;
+  int* plc_next;
+  int* plc_cnt;
+  int* plc_pix;
+  int* plc_free;
+  // records
+  int2* rec_lh;
+  float4* rec_val;
+  float* rec_same;  // edge-pass output; dead after record init, then aliased by q_ent
+  float* rec_diff;
+  // hash
+  uint32_t* hash;
+  uint32_t* hash_ovf;  // small linear overflow area of rec+1 values
+  uint32_t hash_nbuckets;
+  uint32_t hash_ovf_cap;
+  // queue
+  uint64_t* init_keys;
+  uint4* q_ent;  // [qc_cap * MN_QCH] (mp bits, rec, lo, hi): validated against the record on load
+  int* qc_next;
+  int* qc_cnt;
+  int* qc_free;
+  int* tn_head;
+  int* tn_tail;
+  int* tn_cnt;
+  int* tn_child;
+  int plc_cap, qc_cap, tn_cap;
+  // outputs
+  int* out_mask;
+  int* out_cls;
+  MnCtl* ctl;
+};
+
+MN_HD uint32_t mn_pack_nc(int npix, int cls) { return (uint32_t)npix | ((uint32_t)cls << 24); }
+MN_HD int mn_nc_npix(uint32_t nc) { return (int)(nc & 0xFFFFFFu); }
+MN_HD int mn_nc_cls(uint32_t nc) { return (int)(nc >> 24); }
+
+// ---- (lo,hi) -> record hash ---------------------------------------------------------------------
+MN_HD uint64_t mn_mix64(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return k;
+}
+struct MnHashPos {
+  uint32_t b1, b2, fp;
+};
+MN_HD MnHashPos mn_hash_pos(uint32_t nbuckets, int lo, int hi) {
+  uint64_t h = mn_mix64(((uint64_t)(uint32_t)lo << 32) | (uint32_t)hi);
+  MnHashPos p;
+  p.b1 = (uint32_t)(((h & 0xffffffffu) * (uint64_t)nbuckets) >> 32);
+  uint32_t d = (uint32_t)((((h >> 32) & 0x3ffffffu) * (uint64_t)(nbuckets - 1)) >> 26);
+  p.b2 = p.b1 + 1 + d;
+  if (p.b2 >= nbuckets) p.b2 -= nbuckets;
+  p.fp = (uint32_t)(h >> 58);
+  return p;
+}
+// returns record id or -1
+MN_HD int mn_hash_find(const MnImage& im, int lo, int hi) {
+  MnHashPos p = mn_hash_pos(im.hash_nbuckets, lo, hi);
+  for (int w = 0; w < 2; w++) {
+    const uint32_t* bk = im.hash + (size_t)(w ? p.b2 : p.b1) * 8;
+    for (int s = 0; s < 8; s++) {
+      uint32_t v = bk[s];
+      if (v != 0 && (v >> MN_HASH_FP_SHIFT) == p.fp) {
+        int r = (int)(v & ((1u << MN_HASH_FP_SHIFT) - 1)) - 1;
+        int2 lh = im.rec_lh[r];
+        if (lh.x == lo && lh.y == hi) return r;
+      }
+    }
+  }
+  int n = im.ctl->hash_ovf_n;
+  for (int i = 0; i < n; i++) {
+    uint32_t v = im.hash_ovf[i];
+    if (v != 0) {
+      int r = (int)v - 1;
+      int2 lh = im.rec_lh[r];
+      if (lh.x == lo && lh.y == hi) return r;
+    }
+  }
+  return -1;
+}
+// rec_lh[rec] must already hold (lo,hi).  Safe against concurrent inserts/erases of other keys.
+MN_HD void mn_hash_insert(const MnImage& im, int lo, int hi, int rec) {
+  MnHashPos p = mn_hash_pos(im.hash_nbuckets, lo, hi);
+  uint32_t val = (p.fp << MN_HASH_FP_SHIFT) | (uint32_t)(rec + 1);
+  for (int w = 0; w < 2; w++) {
+    uint32_t* bk = im.hash + (size_t)(w ? p.b2 : p.b1) * 8;
+    for (int s = 0; s < 8; s++) {
+      if (bk[s] == 0 && MN_ATOMIC_CAS(&bk[s], 0u, val) == 0u) return;
+    }
+  }
+  int i = MN_ATOMIC_ADD(&im.ctl->hash_ovf_n, 1);
+  if ((uint32_t)i < im.hash_ovf_cap) {
+    im.hash_ovf[i] = (uint32_t)(rec + 1);
+  } else {
+    im.ctl->status = MN_ERR_HASH_FULL;
+  }
+}
+MN_HD void mn_hash_erase(const MnImage& im, int lo, int hi, int rec) {
+  MnHashPos p = mn_hash_pos(im.hash_nbuckets, lo, hi);
+  uint32_t val = (p.fp << MN_HASH_FP_SHIFT) | (uint32_t)(rec + 1);
+  for (int w = 0; w < 2; w++) {
+    uint32_t* bk = im.hash + (size_t)(w ? p.b2 : p.b1) * 8;
+    for (int s = 0; s < 8; s++) {
+      if (bk[s] == val) {
+        bk[s] = 0;
+        return;
+      }
+    }
+  }
+  int n = im.ctl->hash_ovf_n;
+  for (int i = 0; i < n && (uint32_t)i < im.hash_ovf_cap; i++) {
+    if (im.hash_ovf[i] == (uint32_t)(rec + 1)) {
+      im.hash_ovf[i] = 0;
+      return;
+    }
+  }
+}

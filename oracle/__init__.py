@@ -31,7 +31,8 @@ EPS = float(np.finfo(np.float32).eps)
 class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_longlong) for n in (
         "pops", "valid_pops", "merges", "repushes", "pushes", "adj_visits", "folds",
-        "init_records", "init_pushes")] + [("final_objects", ctypes.c_int),
+        "init_records", "init_pushes", "sum_abs_npix", "max_abs_npix", "merges_abs_gt32",
+        "merges_abs_gt1024")] + [("final_objects", ctypes.c_int),
                                            ("final_instances", ctypes.c_int)]
 
     def as_dict(self):

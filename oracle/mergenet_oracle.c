@@ -39,6 +39,9 @@ typedef struct {
   long long folds;       /* this_arec folded into that_arec                (cc:685-698) */
   long long init_records;
   long long init_pushes;
+  long long sum_abs_npix; /* sum over merges of the absorbed object's pixel count */
+  long long max_abs_npix;
+  long long merges_abs_gt32, merges_abs_gt1024;
   int final_objects;     /* all surviving objects, incl. class 0 */
   int final_instances;   /* surviving objects with class != 0 */
 } mno_stats;
@@ -168,6 +171,16 @@ typedef struct {
   heap_ent* heap;
   long long hn, hcapacity;
   mno_stats st;
+  /* ---- schedule analysis (mno_analyze_rounds): greedy split of the sequential event order
+   * into rounds of mutually independent events that all existed at round start ---- */
+  int an_on;
+  long long an_cap, an_rounds, an_round_events, an_events;
+  long long an_cut_conflict, an_cut_cascade, an_cut_cap;
+  int an_cur;          /* current round id */
+  int* an_lastw;       /* per object: round id of last write */
+  int* an_lastr;       /* per object: round id of last read */
+  int* an_stored_round; /* per record: round id in which its stored priority was last written */
+  long long an_hist[16]; /* round-size histogram, bucket = floor(log2(size)) */
 } seg_t;
 
 static inline uint64_t hkey(int lo, int hi) { return ((uint64_t)(uint32_t)lo << 32) | (uint32_t)hi; }
@@ -401,6 +414,56 @@ static int seg_init(seg_t* s, float* class_pred, int class_dim, float* adj_pred,
   return 0;
 }
 
+static void an_close_round(seg_t* s) {
+  if (s->an_round_events > 0) {
+    int b = 0;
+    long long v = s->an_round_events;
+    while (v > 1 && b < 15) { v >>= 1; b++; }
+    s->an_hist[b]++;
+    s->an_rounds++;
+  }
+  s->an_round_events = 0;
+  s->an_cur++;
+}
+/* called before an event on record r executes; is_merge: o_abs is the absorbed object */
+static void an_event(seg_t* s, int r, int is_merge, int o_surv, int o_abs) {
+  int cut = 0;
+  if (s->an_stored_round[r] == s->an_cur) { cut = 1; s->an_cut_cascade++; }
+  else if (s->an_round_events >= s->an_cap) { cut = 1; s->an_cut_cap++; }
+  else {
+    int a = s->lo[r], b = s->hi[r], c = 0;
+    if (s->an_lastw[a] == s->an_cur || s->an_lastw[b] == s->an_cur) c = 1;
+    if (!c && is_merge) {
+      if (s->an_lastr[a] == s->an_cur || s->an_lastr[b] == s->an_cur) c = 1;
+      for (int t = s->adj_head[o_abs]; t >= 0 && !c; t = s->lnext[side_of(s, t, o_abs)][t]) {
+        int o3 = s->lo[t] == o_abs ? s->hi[t] : s->lo[t];
+        if (o3 != o_surv && s->an_lastw[o3] == s->an_cur) c = 1;
+      }
+    }
+    if (c) { cut = 1; s->an_cut_conflict++; }
+  }
+  if (cut) an_close_round(s);
+  s->an_round_events++;
+  s->an_events++;
+  int a = s->lo[r], b = s->hi[r];
+  if (is_merge) {
+    s->an_lastw[a] = s->an_cur; s->an_lastw[b] = s->an_cur;
+    for (int t = s->adj_head[o_abs]; t >= 0; t = s->lnext[side_of(s, t, o_abs)][t]) {
+      int o3 = s->lo[t] == o_abs ? s->hi[t] : s->lo[t];
+      s->an_lastr[o3] = s->an_cur;
+      s->an_stored_round[t] = s->an_cur; /* t (or the record it folds into) is re-stored */
+      if (o3 != o_surv) {
+        int nlo = o_surv < o3 ? o_surv : o3, nhi = o_surv < o3 ? o3 : o_surv;
+        int u = hash_find(s, nlo, nhi);
+        if (u >= 0) s->an_stored_round[u] = s->an_cur;
+      }
+    }
+  } else {
+    s->an_lastr[a] = s->an_cur; s->an_lastr[b] = s->an_cur;
+    s->an_stored_round[r] = s->an_cur;
+  }
+}
+
 /* cc:602-727 */
 static void seg_merge(seg_t* s, int rec, int merged_class, int* merge_log, long long log_cap) {
   int o1 = s->lo[rec], o2 = s->hi[rec];
@@ -412,6 +475,10 @@ static void seg_merge(seg_t* s, int rec, int merged_class, int* merge_log, long 
     merge_log[2 * s->st.merges + 1] = o2;
   }
   s->st.merges++;
+  s->st.sum_abs_npix += s->npix[o2];
+  if (s->npix[o2] > s->st.max_abs_npix) s->st.max_abs_npix = s->npix[o2];
+  if (s->npix[o2] > 32) s->st.merges_abs_gt32++;
+  if (s->npix[o2] > 1024) s->st.merges_abs_gt1024++;
   s->cls[o1] = merged_class;                 /* cc:635 */
   s->pix_next[s->pix_tail[o1]] = o2;         /* cc:636-639 (pixel-set union) */
   s->pix_tail[o1] = s->pix_tail[o2];
@@ -472,6 +539,12 @@ static void seg_run(seg_t* s, int* merge_log, long long log_cap) {
     int merged;
     float mp = compute_priority(s, r, &merged); /* cc:560 */
     s->mp[r] = mp;
+    if (s->an_on) {
+      int is_m = (mp == e.mp);
+      int a = s->lo[r], b = s->hi[r];
+      int surv = s->npix[a] < s->npix[b] ? b : a;
+      an_event(s, r, is_m, surv, surv == a ? b : a);
+    }
     if (mp == e.mp) { /* cc:561-562 */
       seg_merge(s, r, merged, merge_log, log_cap);
     } else if (mp >= 0) { /* cc:563-565 */
@@ -540,4 +613,185 @@ int mno_init_dump(float* class_pred, int class_dim, float* adj_pred, int offset_
   }
   seg_free(&s);
   return 0;
+}
+
+/* Schedule analysis (design aid, not part of the parity oracle): how many rounds does the
+ * sequential event order split into when a round may hold at most `cap` events that (a) all
+ * had their stored priority before the round began and (b) are pairwise independent
+ * (no object written by one is read or written by another)?
+ * out[0]=events out[1]=rounds out[2]=cuts by conflict out[3]=cuts by cascade out[4]=cuts by cap
+ * out[5..20]=histogram of round sizes by floor(log2). */
+int mno_analyze_rounds(float* class_pred, int class_dim, float* adj_pred, int offset_dim,
+                       int img_width, int img_height, int num_classes, const int* offset_list,
+                       float same_different_bias, float object_merge_factor,
+                       float merge_logprob_bias, long long cap, long long* out) {
+  seg_t s;
+  seg_init(&s, class_pred, class_dim, adj_pred, offset_dim, img_width, img_height, num_classes,
+           offset_list, same_different_bias, object_merge_factor, merge_logprob_bias, 1);
+  s.an_on = 1;
+  s.an_cap = cap;
+  s.an_cur = 1;
+  s.an_lastw = (int*)calloc(s.N, sizeof(int));
+  s.an_lastr = (int*)calloc(s.N, sizeof(int));
+  s.an_stored_round = (int*)calloc((size_t)s.E, sizeof(int));
+  seg_run(&s, NULL, 0);
+  an_close_round(&s);
+  out[0] = s.an_events; out[1] = s.an_rounds; out[2] = s.an_cut_conflict;
+  out[3] = s.an_cut_cascade; out[4] = s.an_cut_cap;
+  for (int i = 0; i < 16; i++) out[5 + i] = s.an_hist[i];
+  free(s.an_lastw); free(s.an_lastr); free(s.an_stored_round);
+  seg_free(&s);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Round-schedule model (design validation for the CUDA scheduler; still test infrastructure).
+ *
+ * A round takes the next `cap` valid queue entries in pop order, PLANS every one of them against
+ * the round-start state only (what a GPU worker could read before any commit), accepts the
+ * longest prefix whose members are pairwise independent and none of which is overtaken by a
+ * priority created by an earlier member, then COMMITS the accepted events one by one with the
+ * sequential code above and checks that what the sequential code stored equals the plan.
+ * A mismatch means the independence rule is wrong.  Result must equal mno_run_segmentation. */
+typedef struct { int t, u, x; float oml, same, diff, mp; int lo, hi; } plan_rec;
+typedef struct {
+  heap_ent e;
+  int kind; /* 1 = re-store, 2 = merge */
+  float newmp; int merged, surv, absd;
+  int nrec, roff;
+  int has_new; heap_ent maxnew;
+} plan_cand;
+
+static float prio_explicit(const seg_t* s, float oml, int n1, int cls1, const float* c1, int n2,
+                           int cls2, const float* c2, int* merged_out) {
+  float cdl; int merged;
+  if (cls1 == cls2) { cdl = 0.0f; merged = cls1; }
+  else {
+    float best = c1[0] + c2[0]; merged = 0;
+    for (int c = 1; c < s->C; c++) { float j = c1[c] + c2[c]; if (j > best) { best = j; merged = c; } }
+    cdl = best - c1[cls1]; cdl = cdl - c2[cls2];
+  }
+  if (merged_out) *merged_out = merged;
+  size_t den = (size_t)n1 + (size_t)n2;
+  float num = oml * s->omf; num = num + cdl;
+  float mp = num / (float)den; mp = mp + s->mlb;
+  return mp;
+}
+
+long long mno_model_mismatches;
+
+int mno_run_rounds_model(float* class_pred, int class_dim, float* adj_pred, int offset_dim,
+                         int img_width, int img_height, int num_classes, const int* offset_list,
+                         int* output, int* object_class, float same_different_bias,
+                         float object_merge_factor, float merge_logprob_bias, int cap,
+                         long long* out_rounds, long long* out_events) {
+  seg_t S; seg_t* s = &S;
+  seg_init(s, class_pred, class_dim, adj_pred, offset_dim, img_width, img_height, num_classes,
+           offset_list, same_different_bias, object_merge_factor, merge_logprob_bias, 1);
+  int C = s->C;
+  plan_cand* cand = (plan_cand*)malloc(sizeof(plan_cand) * cap);
+  size_t prcap = 1 << 16; plan_rec* pr = (plan_rec*)malloc(sizeof(plan_rec) * prcap);
+  float* tmpclp = (float*)malloc(sizeof(float) * C);
+  int* wstamp = (int*)calloc(s->N, sizeof(int)); /* round id in which an accepted event writes o */
+  int* rstamp = (int*)calloc(s->N, sizeof(int));
+  long long rounds = 0, events = 0; int rid = 0;
+  mno_model_mismatches = 0;
+  while (s->hn > 0) {
+    /* ---- select: next `cap` valid entries in pop order ---- */
+    int nc = 0;
+    while (nc < cap && s->hn > 0) {
+      heap_ent e = heap_pop(s); s->st.pops++;
+      int r = e.rec;
+      if (s->state[r] != 1 || e.mp != s->mp[r] || e.lo != s->lo[r] || e.hi != s->hi[r]) continue;
+      int dup = 0; for (int i = 0; i < nc; i++) if (cand[i].e.rec == r) dup = 1;
+      if (dup) continue;
+      cand[nc++].e = e;
+    }
+    if (nc == 0) break;
+    rid++; rounds++;
+    /* ---- plan (reads round-start state only) ---- */
+    size_t npr = 0;
+    for (int i = 0; i < nc; i++) {
+      plan_cand* c = &cand[i]; int r = c->e.rec;
+      c->has_new = 0; c->nrec = 0; c->roff = (int)npr;
+      c->newmp = compute_priority(s, r, &c->merged);
+      if (c->newmp != c->e.mp) {
+        c->kind = 1;
+        if (c->newmp >= 0) { c->has_new = 1; c->maxnew.mp = c->newmp; c->maxnew.lo = s->lo[r]; c->maxnew.hi = s->hi[r]; c->maxnew.rec = r; }
+        continue;
+      }
+      c->kind = 2;
+      int a = s->lo[r], b = s->hi[r];
+      if (s->npix[a] < s->npix[b]) { int t = a; a = b; b = t; }
+      c->surv = a; c->absd = b;
+      int na = s->npix[a] + s->npix[b];
+      for (int k = 0; k < C; k++) tmpclp[k] = s->clp[(size_t)a * C + k] + s->clp[(size_t)b * C + k];
+      for (int t = s->adj_head[b]; t >= 0; t = s->lnext[side_of(s, t, b)][t]) {
+        if (t == r) continue;
+        int x = s->lo[t] == b ? s->hi[t] : s->lo[t];
+        int nlo = a < x ? a : x, nhi = a < x ? x : a;
+        int u = hash_find(s, nlo, nhi);
+        if (npr == prcap) { prcap *= 2; pr = (plan_rec*)realloc(pr, sizeof(plan_rec) * prcap); }
+        plan_rec* q = &pr[npr++]; c->nrec++;
+        q->t = t; q->u = u; q->x = x; q->lo = nlo; q->hi = nhi;
+        if (u >= 0) { q->oml = s->oml[u] + s->oml[t]; q->diff = s->diff[u] + s->diff[t]; q->same = s->same[u] + s->same[t]; }
+        else { q->oml = s->oml[t]; q->diff = s->diff[t]; q->same = s->same[t]; }
+        const float* cx = s->clp + (size_t)x * C;
+        if (a < x) q->mp = prio_explicit(s, q->oml, na, c->merged, tmpclp, s->npix[x], s->cls[x], cx, NULL);
+        else q->mp = prio_explicit(s, q->oml, s->npix[x], s->cls[x], cx, na, c->merged, tmpclp, NULL);
+        if (q->mp >= 0) {
+          heap_ent ne = {q->mp, nlo, nhi, u >= 0 ? u : t};
+          if (!c->has_new || ent_before(&ne, &c->maxnew)) { c->has_new = 1; c->maxnew = ne; }
+        }
+      }
+    }
+    /* ---- accept the longest valid prefix ---- */
+    int nacc = 0; int have_max = 0; heap_ent runmax;
+    for (int i = 0; i < nc; i++) {
+      plan_cand* c = &cand[i]; int ok = 1;
+      if (have_max && ent_before(&runmax, &c->e)) ok = 0; /* a created entry pops first */
+      int a = s->lo[c->e.rec], b = s->hi[c->e.rec];
+      if (ok && (wstamp[a] == rid || wstamp[b] == rid)) ok = 0;
+      if (ok && c->kind == 2) {
+        if (rstamp[a] == rid || rstamp[b] == rid) ok = 0;
+        for (int k = 0; ok && k < c->nrec; k++) if (wstamp[pr[c->roff + k].x] == rid) ok = 0;
+      }
+      if (!ok) break;
+      nacc++;
+      if (c->kind == 2) {
+        wstamp[a] = rid; wstamp[b] = rid;
+        for (int k = 0; k < c->nrec; k++) rstamp[pr[c->roff + k].x] = rid;
+      } else { rstamp[a] = rid; rstamp[b] = rid; }
+      if (c->has_new && (!have_max || ent_before(&c->maxnew, &runmax))) { have_max = 1; runmax = c->maxnew; }
+    }
+    /* ---- push back the rest untouched ---- */
+    for (int i = nacc; i < nc; i++) { heap_push(s, cand[i].e.mp, cand[i].e.lo, cand[i].e.hi, cand[i].e.rec); s->st.pushes--; }
+    /* ---- commit with the sequential code, check against the plan ---- */
+    for (int i = 0; i < nacc; i++) {
+      plan_cand* c = &cand[i]; int r = c->e.rec; events++;
+      s->st.valid_pops++;
+      int merged; float mp = compute_priority(s, r, &merged);
+      if (mp != c->newmp || merged != c->merged) mno_model_mismatches++;
+      s->mp[r] = mp;
+      if (c->kind == 2) {
+        if (mp != c->e.mp) mno_model_mismatches++;
+        seg_merge(s, r, merged, NULL, 0);
+        for (int k = 0; k < c->nrec; k++) {
+          plan_rec* q = &pr[c->roff + k]; int w = q->u >= 0 ? q->u : q->t;
+          if (s->state[w] != 1 || s->mp[w] != q->mp || s->oml[w] != q->oml || s->same[w] != q->same ||
+              s->diff[w] != q->diff || s->lo[w] != q->lo || s->hi[w] != q->hi) mno_model_mismatches++;
+          if (q->u >= 0 && s->state[q->t] != 2) mno_model_mismatches++;
+        }
+      } else {
+        if (mp == c->e.mp) mno_model_mismatches++;
+        if (mp >= 0) { heap_push(s, mp, s->lo[r], s->hi[r], r); s->st.repushes++; }
+      }
+    }
+  }
+  seg_output(s, output, object_class);
+  if (out_rounds) *out_rounds = rounds;
+  if (out_events) *out_events = events;
+  free(cand); free(pr); free(tmpclp); free(wstamp); free(rstamp);
+  seg_free(s);
+  return (int)(mno_model_mismatches != 0);
 }

@@ -1,0 +1,160 @@
+// tests/emul/emul_merge.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the device scheduler source (mergenet_b200/csrc/mn_merge.cuh) for the HOST and runs it
+// with one logical thread, so the CPU test-suite can unit-test the scheduler's logic (queue tree,
+// plan/commit rounds, solo merges) against the oracle without a GPU.  The record construction
+// below is a plain host loop using libm (it is not the CUDA edge pass); only the scheduler is the
+// product's source.  Nothing in mergenet_b200/ can reach this file.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../mergenet_b200/csrc/mn_merge.cuh"
+
+template <typename T> static T* zalloc(size_t n) { return (T*)calloc(n ? n : 1, sizeof(T)); }
+
+extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, const float* adj_pred,
+                                     int offset_dim, int W, int H, int num_classes,
+                                     const int* offsets, int* output, int* object_class, float sdb,
+                                     float omf, float mlb, long long* stats /* 16 */) {
+  (void)class_dim; (void)sdb;
+  const int C = num_classes, K = offset_dim, N = H * W;
+  const size_t E = (size_t)N * K;
+  MnImage im;
+  memset(&im, 0, sizeof(im));
+  im.clp = zalloc<float>((size_t)N * C);
+  im.cls = zalloc<int>(N);
+  im.obj_nc = zalloc<uint32_t>(N);
+  im.obj_same = zalloc<float>(N);
+  im.parent = zalloc<int>(N);
+  im.live_mask = zalloc<uint32_t>(N);
+  im.pl_head = zalloc<int>(N);
+  im.pl_tail = zalloc<int>(N);
+  im.plc_cap = N / 2 + 1024;
+  im.plc_next = zalloc<int>(im.plc_cap);
+  im.plc_cnt = zalloc<int>(im.plc_cap);
+  im.plc_pix = zalloc<int>((size_t)im.plc_cap * MN_PLC);
+  im.plc_free = zalloc<int>(im.plc_cap);
+  im.rec_lh = zalloc<int2>(E);
+  im.rec_val = zalloc<float4>(E);
+  im.hash_nbuckets = (uint32_t)(E * 16 / 10 / 8 + 64);
+  im.hash = zalloc<uint32_t>((size_t)im.hash_nbuckets * 8);
+  im.hash_ovf_cap = 4096;
+  im.hash_ovf = zalloc<uint32_t>(im.hash_ovf_cap);
+  im.init_keys = zalloc<uint64_t>(E);
+  im.qc_cap = (int)(E / MN_QCH) + 65536 + MN_NROOTS;
+  im.q_ent = zalloc<uint4>((size_t)im.qc_cap * MN_QCH);
+  im.qc_next = zalloc<int>(im.qc_cap);
+  im.qc_cnt = zalloc<int>(im.qc_cap);
+  im.qc_free = zalloc<int>(im.qc_cap);
+  im.tn_cap = MN_NROOTS + MN_TREE_FANOUT * 8192;
+  im.tn_head = zalloc<int>(im.tn_cap);
+  im.tn_tail = zalloc<int>(im.tn_cap);
+  im.tn_cnt = zalloc<int>(im.tn_cap);
+  im.tn_child = zalloc<int>(im.tn_cap);
+  im.ctl = zalloc<MnCtl>(1);
+  for (int i = 0; i < im.tn_cap; i++) { im.tn_head[i] = -1; im.tn_tail[i] = -1; im.tn_child[i] = -1; }
+  im.ctl->tn_bump = MN_NROOTS;
+
+  MnMergeArgs A;
+  memset(&A, 0, sizeof(A));
+  A.C = C; A.K = K; A.N = N; A.W = W; A.omf = omf; A.mlb = mlb; A.max_rounds = 0;
+  A.off.K = K;
+  std::vector<std::pair<int, int>> mag;
+  for (int k = 0; k < K; k++) {
+    A.off.delta[k] = offsets[2 * k] * W + offsets[2 * k + 1];
+    mag.push_back(std::make_pair(abs(A.off.delta[k]), k));
+  }
+  std::sort(mag.begin(), mag.end());
+  int rank_of_k[MN_MAX_K];
+  for (int r = 0; r < K; r++) { A.off.k_of_rank[r] = mag[r].second; rank_of_k[mag[r].second] = r; }
+
+  // objects (cc:196-207) and records (cc:209-231): host loops, libm
+  for (int p = 0; p < N; p++) {
+    float best = 0; int bc = 0;
+    for (int c = 0; c < C; c++) {
+      float v = 0.0f + logf(class_pred[(size_t)c * N + p]);
+      im.clp[(size_t)p * C + c] = v;
+      if (c == 0 || v > best) { best = v; bc = c; }
+    }
+    im.cls[p] = bc;
+    im.obj_nc[p] = mn_pack_nc(1, bc);
+    im.parent[p] = p; im.pl_head[p] = -1; im.pl_tail[p] = -1;
+  }
+  for (int p = 0; p < N; p++) {
+    int row = p / W, col = p % W;
+    uint32_t m = 0;
+    for (int k = 0; k < K; k++) {
+      int r2 = row + offsets[2 * k], c2 = col + offsets[2 * k + 1];
+      if (r2 >= 0 && r2 < H && c2 >= 0 && c2 < W) m |= 1u << k;
+      r2 = row - offsets[2 * k]; c2 = col - offsets[2 * k + 1];
+      if (r2 >= 0 && r2 < H && c2 >= 0 && c2 < W) m |= 1u << (16 + k);
+    }
+    im.live_mask[p] = m;
+    for (int k = 0; k < K; k++) {
+      size_t r = (size_t)p * K + k;
+      int r2 = row + offsets[2 * k], c2 = col + offsets[2 * k + 1];
+      uint64_t key = ~0ull;
+      if (r2 >= 0 && r2 < H && c2 >= 0 && c2 < W) {
+        int q = r2 * W + c2, lo = p < q ? p : q, hi = p < q ? q : p;
+        float s = adj_pred[(size_t)k * N + p];
+        float diff = (float)log(1.0 - (double)s), same = logf(s), oml = same - diff;
+        float mp = mn_priority(oml, omf, mlb, C, 1, im.cls[lo], im.clp + (size_t)lo * C, 1, im.cls[hi],
+                               im.clp + (size_t)hi * C, nullptr);
+        im.rec_lh[r] = make_int2(lo, hi);
+        im.rec_val[r] = make_float4(oml, same, diff, mp);
+        mn_hash_insert(im, lo, hi, (int)r);
+        if (mp >= 0.0f) {
+          uint32_t ord = (uint32_t)lo * (uint32_t)K + (uint32_t)rank_of_k[k];
+          key = ((uint64_t)(~mn_f2u(mp == 0.0f ? 0.0f : mp)) << MN_ORD_BITS) | ord;
+        }
+      } else {
+        im.rec_lh[r] = make_int2(-1, -1);
+        im.rec_val[r] = make_float4(0, 0, 0, -1.0f);
+      }
+      im.init_keys[r] = key;
+    }
+  }
+  std::sort(im.init_keys, im.init_keys + E);
+
+  MnSm* sm = (MnSm*)calloc(1, sizeof(MnSm));
+  float* c_clp = zalloc<float>((size_t)MN_H * C);
+  mn_merge_image(im, *sm, A, c_clp);
+
+  // labels (cc:491-517): ascending surviving id, class-0 objects -> 0
+  std::vector<int> label(N, 0);
+  for (int i = 0; i < N; i++) { output[i] = 0; object_class[i] = -1; }
+  int k = 1;
+  for (int o = 0; o < N; o++) {
+    if (im.parent[o] != o) continue;
+    int cls = mn_nc_cls(im.obj_nc[o]);
+    if (cls == 0) continue;
+    object_class[k - 1] = cls;
+    label[o] = k++;
+  }
+  for (int p = 0; p < N; p++) {
+    int r = p;
+    while (im.parent[r] != r) r = im.parent[r];
+    output[p] = label[r];
+  }
+  int status = im.ctl->status;
+  if (getenv("EMUL_DEBUG")) {
+    for (size_t r = 0; r < E; r++) if (im.rec_lh[r].x >= 0 && im.rec_val[r].w >= 0.0f)
+      fprintf(stderr, "LEFTOVER rec %zu lo %d hi %d mp %.9g (bits %08x) root %d\n", r, im.rec_lh[r].x, im.rec_lh[r].y, im.rec_val[r].w, mn_f2u(im.rec_val[r].w), mn_root_of(im.rec_val[r].w));
+    fprintf(stderr, "status %d fail_line %d\n", im.ctl->status, im.ctl->fail_line);
+    fprintf(stderr, "tree_entries %d static_cursor %d n_init %d nins %d nhot %d cold_empty %d\n", im.ctl->tree_entries, im.ctl->static_cursor, im.ctl->n_init, sm->nins, sm->nhot, sm->cold_empty);
+  }
+  if (stats) {
+    MnCtl* c = im.ctl;
+    long long v[16] = {c->rounds, c->events, c->merges, c->restores, c->invalid_pops, c->solo_events,
+                       c->refills, c->flushes, c->splits, c->pairs, c->cuts_conflict, c->cuts_cascade,
+                       c->cuts_capacity, (long long)c->qc_bump, (long long)c->plc_bump, (long long)c->tn_bump};
+    memcpy(stats, v, sizeof(v));
+  }
+  // (leaks on purpose: short-lived test process helper)
+  return status;
+}
