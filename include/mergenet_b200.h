@@ -1,0 +1,124 @@
+/*
+ * mergenet_b200.h -- C ABI of the B200-native MergeNet merge segmenter (libmergenet_b200.so).
+ *
+ * Plain C, plain pointers and sizes, no torch types.  The library is CUDA-only (sm_100a): every
+ * entry point that computes fails with MN_ERR_CUDA when no device is usable; there is no CPU path.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   c_run_segmentation      <- utils/csegment/segment.cc:742-765 (extern "C", identical signature);
+ *                              it is what utils/csegment/c_segment.pyx:16-25,69-78 binds.
+ *   mn_segment_batch_*      <- additive: the same operation over B images of one shape (device or
+ *                              host buffers), used by the Python facade and the benchmark.
+ */
+#ifndef MERGENET_B200_H
+#define MERGENET_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes (0 = ok). */
+enum {
+  MN_STATUS_OK = 0,
+  MN_STATUS_BAD_ARG = 1,
+  MN_STATUS_PL_POOL = 2,
+  MN_STATUS_Q_POOL = 3,
+  MN_STATUS_TREE_POOL = 4,
+  MN_STATUS_HASH_FULL = 5,
+  MN_STATUS_INTERNAL = 6,
+  MN_STATUS_CUDA = 7,
+  MN_STATUS_LIMIT = 8
+};
+
+/*
+ * Drop-in for the reference symbol (segment.cc:742-752).  NOTE width before height.
+ *   class_pred   class_dim x H x W  fp32, C-contiguous, already clipped to [2^-23, 1-2^-23]
+ *   adj_pred     offset_dim x H x W fp32; REWRITTEN IN PLACE when same_different_bias != 0
+ *                (segment.cc:183-195)
+ *   offset_list  offset_dim x 2 int32 (row delta, col delta)   (segment.cc:166-169)
+ *   output       H x W int32, fully overwritten: 0 = class-0 objects, 1..n = instances
+ *   object_class H*W int32: -1 everywhere, then the class of label k at [k-1] (segment.cc:497-509)
+ * All buffers are HOST memory owned by the caller.  Returns nothing, like the reference; unlike
+ * the reference it never calls exit(): on failure the outputs are left as (0, -1) and the code is
+ * readable through mn_last_error().  Nothing is printed.
+ */
+void c_run_segmentation(float* class_pred, int class_dim, float* adj_pred, int offset_dim,
+                        int img_width, int img_height, int num_classes, int* offset_list,
+                        int* output, int* object_class, float same_different_bias,
+                        float object_merge_factor, float merge_logprob_bias);
+
+/* Status of the last call on this thread, and a static description of a status code. */
+int mn_last_error(void);
+const char* mn_status_string(int status);
+
+/* Number of usable CUDA devices (0 when the driver or a device is missing). */
+int mn_device_count(void);
+
+/* ---- batched interface ---------------------------------------------------------------------- */
+typedef struct mn_plan mn_plan; /* workspace for up to max_batch images of one shape on one GPU */
+
+/* Per-image statistics of the last run (north star: round count, merges, per-round latency). */
+typedef struct {
+  int status;
+  int fail_line;
+  int n_instances;
+  int n_init_entries;
+  long long rounds, events, merges, restores, invalid_pops, solo_events;
+  long long refills, flushes, splits, pairs, cuts_conflict, cuts_cascade, cuts_capacity;
+  long long queue_chunks_used, pixel_chunks_used, tree_nodes_used;
+} mn_image_stats;
+
+/* Device time of the phases of the last batch (CUDA events on the plan's stream), milliseconds. */
+typedef struct {
+  float h2d_ms, edge_ms, record_init_sort_ms, merge_ms, label_ms, d2h_ms, total_ms;
+  long long edge_launches, other_launches; /* kernels of this library launched by the last batch */
+} mn_timings;
+
+/* Bytes of device workspace one image of this shape needs (for sizing max_batch). */
+size_t mn_workspace_bytes_per_image(int height, int width, int num_classes, int num_offsets);
+
+int mn_plan_create(mn_plan** out, int max_batch, int height, int width, int num_classes,
+                   int num_offsets, const int* offset_list /* K x 2 (drow, dcol) */, int device);
+void mn_plan_destroy(mn_plan* plan);
+
+/*
+ * Segment `batch` images whose maps are ALREADY ON THE DEVICE of the plan.
+ *   d_class [B][C][H][W] fp32, d_adj [B][K][H][W] fp32 (rewritten when same_different_bias != 0),
+ *   d_mask [B][H][W] int32, d_object_class [B][H*W] int32, d_num_instances [B] int32.
+ *   clip != 0 applies the wrapper's clip to [2^-23, 1-2^-23] (c_segment.pyx:53-55) on the fly.
+ *   stream: a cudaStream_t (NULL = the plan's own stream).  The call returns after the work has
+ *   completed (it synchronises the stream to read the per-image status words).
+ */
+int mn_segment_batch_device(mn_plan* plan, int batch, const float* d_class, float* d_adj,
+                            int* d_mask, int* d_object_class, int* d_num_instances, int clip,
+                            float same_different_bias, float object_merge_factor,
+                            float merge_logprob_bias, void* stream);
+
+/* Same with HOST buffers (pinned or pageable): the copies are part of the call. */
+int mn_segment_batch_host(mn_plan* plan, int batch, const float* h_class, float* h_adj, int* h_mask,
+                          int* h_object_class, int* h_num_instances, int clip,
+                          float same_different_bias, float object_merge_factor,
+                          float merge_logprob_bias);
+
+int mn_plan_image_stats(mn_plan* plan, int image, mn_image_stats* out);
+int mn_plan_timings(mn_plan* plan, mn_timings* out);
+
+/* ---- test hooks (parity tests call these through the same library) --------------------------- */
+/* Edge pass + record init of ONE image (host buffers in, host buffers out), i.e. what the reference
+ * constructor computes (segment.cc:153-232): clp[N*C], cls[N], and per record slot pixel*K+k
+ * same/diff/oml/mp plus lo/hi (-1 when the offset leaves the image). */
+int mn_debug_edge_dump(int height, int width, int num_classes, int num_offsets,
+                       const int* offset_list, const float* h_class, float* h_adj,
+                       float same_different_bias, float object_merge_factor,
+                       float merge_logprob_bias, float* clp, int* cls, float* same, float* diff,
+                       float* oml, float* mp, int* lo, int* hi);
+/* Device libm restatements over n consecutive float bit patterns starting at first_bits:
+ * which = 0: logf(x); 1: (float)log(1.0 - (double)x); 2: the same_different_bias transform. */
+int mn_debug_libm(int which, unsigned first_bits, unsigned n, float bias, float* h_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

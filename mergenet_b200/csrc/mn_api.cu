@@ -1,0 +1,591 @@
+// mn_api.cu -- host driver and C ABI of libmergenet_b200.so (see include/mergenet_b200.h).
+//
+// Pipeline for a batch of B images of one shape, all on one CUDA stream:
+//   1. mn_edge_pass_kernel      whole GPU, HBM-bound, TMA-staged            (mn_edge.cuh)
+//   2. per image: mn_record_init_kernel -> radix sort of the initial queue keys (cub, library call)
+//   3. mn_merge_kernel          persistent, one CTA per image, order-exact scheduler (mn_merge.cuh)
+//   4. labels: root flags -> exclusive scan (cub) -> mask / object_class     (this file)
+// There is no CPU implementation behind this API: without a CUDA device every call fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cub/cub.cuh>
+#include <mutex>
+#include <vector>
+
+#include "../../include/mergenet_b200.h"
+#include "mn_common.h"
+#include "mn_edge.cuh"
+#include "mn_layout.h"
+#include "mn_merge.cuh"
+
+// ------------------------------------------------------------------------------------------------
+static thread_local int g_last_error = MN_STATUS_OK;
+
+#define MN_CUDA_OK(expr)                                                                \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      fprintf(stderr, "mergenet_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e__), \
+              __FILE__, __LINE__);                                                      \
+      g_last_error = MN_STATUS_CUDA;                                                    \
+      return MN_STATUS_CUDA;                                                            \
+    }                                                                                   \
+  } while (0)
+
+extern "C" int mn_last_error(void) { return g_last_error; }
+extern "C" const char* mn_status_string(int s) {
+  switch (s) {
+    case MN_STATUS_OK: return "ok";
+    case MN_STATUS_BAD_ARG: return "bad argument";
+    case MN_STATUS_PL_POOL: return "pixel-list chunk pool exhausted";
+    case MN_STATUS_Q_POOL: return "queue entry pool exhausted";
+    case MN_STATUS_TREE_POOL: return "queue tree node pool exhausted";
+    case MN_STATUS_HASH_FULL: return "record hash table full";
+    case MN_STATUS_INTERNAL: return "internal invariant failed";
+    case MN_STATUS_CUDA: return "CUDA error / no usable device";
+    case MN_STATUS_LIMIT: return "iteration guard tripped";
+  }
+  return "unknown";
+}
+extern "C" int mn_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels of this file
+__global__ void __launch_bounds__(256, 1) mn_merge_kernel(const MnImage* imgs, int nimg, MnMergeArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  MnSm& sm = *reinterpret_cast<MnSm*>(smem_raw);
+  float* c_clp = reinterpret_cast<float*>(smem_raw + ((sizeof(MnSm) + 15) / 16) * 16);
+  for (int b = blockIdx.x; b < nimg; b += gridDim.x) {
+    const MnImage im = imgs[b];
+    long long t0 = clock64();
+    mn_merge_image(im, sm, A, c_clp);
+    if (threadIdx.x == 0) im.ctl->cycles_total = clock64() - t0;
+    __syncthreads();
+  }
+}
+
+// control blocks, hash tables, tree nodes: reset before every run
+__global__ void mn_reset_kernel(const MnImage* imgs, int nimg) {
+  for (int b = blockIdx.y; b < nimg; b += gridDim.y) {
+    const MnImage im = imgs[b];
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    const long long nh = (long long)im.hash_nbuckets * 8;
+    for (long long i = tid; i < nh; i += nth) im.hash[i] = 0;
+    for (long long i = tid; i < im.tn_cap; i += nth) {
+      im.tn_head[i] = -1; im.tn_tail[i] = -1; im.tn_cnt[i] = 0; im.tn_child[i] = -1;
+    }
+    if (tid == 0) {
+      MnCtl z;
+      memset(&z, 0, sizeof(z));
+      z.tn_bump = MN_NROOTS;
+      *im.ctl = z;
+    }
+  }
+}
+
+// root flags: 1 for surviving objects with class != 0 (cc:503-508); written over the dead cls array
+__global__ void mn_label_flags_kernel(const MnImage* imgs, int nimg, int N) {
+  for (int b = blockIdx.y; b < nimg; b += gridDim.y) {
+    const MnImage im = imgs[b];
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x)
+      im.cls[p] = (im.parent[p] == p && mn_nc_cls(im.obj_nc[p]) != 0) ? 1 : 0;
+  }
+}
+// mask / object_class (cc:491-517); labels ascend with the surviving object's id
+__global__ void mn_label_write_kernel(const MnImage* imgs, int nimg, int N, int* d_mask,
+                                      int* d_object_class, int* d_ninst) {
+  for (int b = blockIdx.y; b < nimg; b += gridDim.y) {
+    const MnImage im = imgs[b];
+    const int* flags = im.cls;
+    const int* excl = im.pl_head;  // exclusive scan of flags (the pixel lists are dead by now)
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+      int r = p;
+      for (int g = 0; g < (1 << 26); g++) {
+        int q = im.parent[r];
+        if (q == r) break;
+        r = q;
+      }
+      int lab = flags[r] ? excl[r] + 1 : 0;
+      d_mask[(size_t)b * N + p] = lab;
+      if (r == p && flags[p]) d_object_class[(size_t)b * N + excl[p]] = mn_nc_cls(im.obj_nc[p]);
+      if (p == N - 1) {
+        int n = excl[N - 1] + flags[N - 1];
+        d_ninst[b] = n;
+        im.ctl->n_instances = n;
+      }
+    }
+  }
+}
+
+__global__ void mn_libm_kernel(int which, uint32_t first_bits, uint32_t n, float bias, float* out) {
+  __shared__ MnLogfTab tab[16];
+  if (threadIdx.x < 16) {
+    const MnLogfTab t16[16] = {MN_LOGF_TABLE};
+    tab[threadIdx.x] = t16[threadIdx.x];
+  }
+  __syncthreads();
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float x = __uint_as_float(first_bits + i);
+    float r;
+    if (which == 0) r = mn_logf_exact(x, tab);
+    else if (which == 1) r = mn_log1m_exact(x);
+    else r = mn_bias_sameness(x, bias, tab);
+    out[i] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct mn_plan {
+  int device, max_batch, H, W, C, K, N;
+  long long E;
+  int offsets[2 * MN_MAX_K];
+  int rank_of_k[MN_MAX_K];
+  MnOffsets off;
+  size_t per_image_bytes;
+  unsigned char* d_ws;        // max_batch * per_image_bytes
+  MnImage* d_imgs;            // device array of per-image pointer sets
+  std::vector<MnImage> h_imgs;
+  uint64_t* d_keys_scratch;   // E keys (record init writes, the sort reads)
+  void* d_cub_temp;
+  size_t cub_temp_bytes;
+  // staging for the host-buffer entry point
+  float* d_in_class; float* d_in_adj; int* d_out_mask; int* d_out_cls; int* d_out_ninst;
+  size_t staging_batch;
+  cudaStream_t stream;
+  cudaEvent_t ev[8];
+  int num_sms;
+  int edge_tp, edge_smem, merge_smem;
+  std::vector<MnCtl> h_ctl;
+  mn_timings timings;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct WsLayout {
+  size_t clp, cls, obj_nc, obj_same, parent, live_mask, pl_head, pl_tail, plc_next, plc_cnt, plc_pix,
+      plc_free, rec_lh, rec_val, rec_sd, hash, hash_ovf, init_keys, qc_next, qc_cnt, qc_free, tn, ctl, total;
+  int plc_cap, qc_cap, tn_cap;
+  uint32_t hash_nbuckets, hash_ovf_cap;
+};
+static WsLayout ws_layout(int H, int W, int C, int K) {
+  WsLayout L;
+  const size_t N = (size_t)H * W, E = N * K;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
+  L.plc_cap = (int)(N / 2 + 4096);
+  // queue entry pool: 16-byte entries in chunks of MN_QCH; it aliases rec_same+rec_diff (8*E bytes)
+  // and extends past them: one chunk per live tree leaf plus the pending entries themselves.
+  L.qc_cap = (int)(E / MN_QCH + 65536 + MN_NROOTS);
+  L.tn_cap = MN_NROOTS + MN_TREE_FANOUT * 8192;
+  L.hash_nbuckets = (uint32_t)(E * 16 / 10 / 8 + 64);
+  L.hash_ovf_cap = 4096;
+  L.clp = take(N * C * 4);
+  L.cls = take(N * 4);
+  L.obj_nc = take(N * 4);
+  L.obj_same = take(N * 4);
+  L.parent = take(N * 4);
+  L.live_mask = take(N * 4);
+  L.pl_head = take(N * 4);
+  L.pl_tail = take(N * 4);
+  L.plc_next = take((size_t)L.plc_cap * 4);
+  L.plc_cnt = take((size_t)L.plc_cap * 4);
+  L.plc_pix = take((size_t)L.plc_cap * MN_PLC * 4);
+  L.plc_free = take((size_t)L.plc_cap * 4);
+  L.rec_lh = take(E * 8);
+  L.rec_val = take(E * 16);
+  L.rec_sd = take(std::max(E * 8, (size_t)L.qc_cap * MN_QCH * 16));  // rec_same|rec_diff, then q_ent
+  L.hash = take((size_t)L.hash_nbuckets * 8 * 4);
+  L.hash_ovf = take((size_t)L.hash_ovf_cap * 4);
+  L.init_keys = take(E * 8);
+  L.qc_next = take((size_t)L.qc_cap * 4);
+  L.qc_cnt = take((size_t)L.qc_cap * 4);
+  L.qc_free = take((size_t)L.qc_cap * 4);
+  L.tn = take((size_t)L.tn_cap * 4 * 4);
+  L.ctl = take(sizeof(MnCtl));
+  L.total = o;
+  return L;
+}
+
+extern "C" size_t mn_workspace_bytes_per_image(int H, int W, int C, int K) {
+  if (H <= 0 || W <= 0 || C <= 0 || K <= 0) return 0;
+  return ws_layout(H, W, C, K).total;
+}
+
+static int choose_edge_tile(int C, int K, int* smem_bytes) {
+  // per pixel: double-buffered inputs 2*(C+K) floats + staged outputs (C + 2K) floats
+  const size_t per_px = 4 * (size_t)(2 * (C + K) + C + 2 * K);
+  size_t budget = 200 * 1024;
+  int tp = (int)(budget / per_px);
+  tp = std::min(tp, 512);
+  tp = tp / 4 * 4;
+  if (tp >= 128) tp = tp / 128 * 128;
+  if (tp < 4) tp = 4;
+  *smem_bytes = (int)(128 + per_px * tp + 16 * sizeof(MnLogfTab) + 64);
+  return tp;
+}
+
+extern "C" void mn_plan_destroy(mn_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  cudaFree(p->d_ws); cudaFree(p->d_imgs); cudaFree(p->d_keys_scratch); cudaFree(p->d_cub_temp);
+  cudaFree(p->d_in_class); cudaFree(p->d_in_adj); cudaFree(p->d_out_mask); cudaFree(p->d_out_cls);
+  cudaFree(p->d_out_ninst);
+  for (int i = 0; i < 8; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C, int K,
+                              const int* offset_list, int device) {
+  g_last_error = MN_STATUS_OK;
+  if (!out || max_batch <= 0 || H <= 0 || W <= 0 || C <= 0 || C >= MN_MAX_C || K <= 0 || K > MN_MAX_K ||
+      !offset_list || (long long)H * W * K > (1ll << MN_ORD_BITS) || (long long)H * W >= (1 << 24)) {
+    g_last_error = MN_STATUS_BAD_ARG;
+    return MN_STATUS_BAD_ARG;
+  }
+  // the reference's config contract (core_config.py:66-73): no (0,0), no duplicates, no negated
+  // pairs; additionally two offsets must not alias to the same linear delta
+  for (int a = 0; a < K; a++) {
+    int da = offset_list[2 * a] * W + offset_list[2 * a + 1];
+    if (da == 0 || abs(offset_list[2 * a + 1]) >= W || abs(offset_list[2 * a]) >= H + 0 * 1) {
+      if (da == 0) { g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
+    }
+    for (int b = 0; b < a; b++) {
+      int db = offset_list[2 * b] * W + offset_list[2 * b + 1];
+      if (da == db || da == -db) { g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
+    }
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    g_last_error = MN_STATUS_CUDA;
+    return MN_STATUS_CUDA;
+  }
+  MN_CUDA_OK(cudaSetDevice(device));
+  mn_plan* p = new mn_plan();
+  memset(&p->timings, 0, sizeof(p->timings));
+  p->device = device; p->max_batch = max_batch; p->H = H; p->W = W; p->C = C; p->K = K; p->N = H * W;
+  p->E = (long long)p->N * K;
+  p->d_ws = nullptr; p->d_imgs = nullptr; p->d_keys_scratch = nullptr; p->d_cub_temp = nullptr;
+  p->d_in_class = nullptr; p->d_in_adj = nullptr; p->d_out_mask = nullptr; p->d_out_cls = nullptr; p->d_out_ninst = nullptr;
+  p->staging_batch = 0; p->stream = nullptr;
+  for (int i = 0; i < 8; i++) p->ev[i] = nullptr;
+  memcpy(p->offsets, offset_list, sizeof(int) * 2 * K);
+  std::vector<std::pair<int, int>> mag;
+  p->off.K = K;
+  for (int k = 0; k < K; k++) {
+    p->off.delta[k] = offset_list[2 * k] * W + offset_list[2 * k + 1];
+    mag.push_back(std::make_pair(abs(p->off.delta[k]), k));
+  }
+  std::sort(mag.begin(), mag.end());
+  for (int r = 0; r < K; r++) { p->off.k_of_rank[r] = mag[r].second; p->rank_of_k[mag[r].second] = r; }
+
+  cudaDeviceProp prop;
+  MN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  p->num_sms = prop.multiProcessorCount;
+  WsLayout L = ws_layout(H, W, C, K);
+  p->per_image_bytes = L.total;
+  auto fail = [&](int code) { mn_plan_destroy(p); g_last_error = code; return code; };
+  if (cudaMalloc(&p->d_ws, L.total * (size_t)max_batch) != cudaSuccess) return fail(MN_STATUS_CUDA);
+  if (cudaMalloc(&p->d_imgs, sizeof(MnImage) * max_batch) != cudaSuccess) return fail(MN_STATUS_CUDA);
+  if (cudaMalloc(&p->d_keys_scratch, (size_t)p->E * 8) != cudaSuccess) return fail(MN_STATUS_CUDA);
+  p->h_imgs.resize(max_batch);
+  for (int b = 0; b < max_batch; b++) {
+    unsigned char* base = p->d_ws + (size_t)b * L.total;
+    MnImage im;
+    memset(&im, 0, sizeof(im));
+    im.clp = (float*)(base + L.clp); im.cls = (int*)(base + L.cls);
+    im.obj_nc = (uint32_t*)(base + L.obj_nc); im.obj_same = (float*)(base + L.obj_same);
+    im.parent = (int*)(base + L.parent); im.live_mask = (uint32_t*)(base + L.live_mask);
+    im.pl_head = (int*)(base + L.pl_head); im.pl_tail = (int*)(base + L.pl_tail);
+    im.plc_next = (int*)(base + L.plc_next); im.plc_cnt = (int*)(base + L.plc_cnt);
+    im.plc_pix = (int*)(base + L.plc_pix); im.plc_free = (int*)(base + L.plc_free);
+    im.rec_lh = (int2*)(base + L.rec_lh); im.rec_val = (float4*)(base + L.rec_val);
+    im.rec_same = (float*)(base + L.rec_sd); im.rec_diff = im.rec_same + p->E;
+    im.hash = (uint32_t*)(base + L.hash); im.hash_ovf = (uint32_t*)(base + L.hash_ovf);
+    im.hash_nbuckets = L.hash_nbuckets; im.hash_ovf_cap = L.hash_ovf_cap;
+    im.init_keys = (uint64_t*)(base + L.init_keys);
+    im.q_ent = (uint4*)(base + L.rec_sd);
+    im.qc_next = (int*)(base + L.qc_next); im.qc_cnt = (int*)(base + L.qc_cnt); im.qc_free = (int*)(base + L.qc_free);
+    im.tn_head = (int*)(base + L.tn); im.tn_tail = im.tn_head + L.tn_cap; im.tn_cnt = im.tn_tail + L.tn_cap;
+    im.tn_child = im.tn_cnt + L.tn_cap;
+    im.plc_cap = L.plc_cap; im.qc_cap = L.qc_cap; im.tn_cap = L.tn_cap;
+    im.out_mask = nullptr; im.out_cls = nullptr;
+    im.ctl = (MnCtl*)(base + L.ctl);
+    p->h_imgs[b] = im;
+  }
+  if (cudaMemcpy(p->d_imgs, p->h_imgs.data(), sizeof(MnImage) * max_batch, cudaMemcpyHostToDevice) != cudaSuccess)
+    return fail(MN_STATUS_CUDA);
+  // cub temp storage: the larger of the key sort and the label scan
+  size_t t1 = 0, t2 = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, t1, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)p->E, 0, 32 + MN_ORD_BITS);
+  cub::DeviceScan::ExclusiveSum(nullptr, t2, (const int*)nullptr, (int*)nullptr, p->N);
+  p->cub_temp_bytes = std::max(t1, t2);
+  if (cudaMalloc(&p->d_cub_temp, p->cub_temp_bytes) != cudaSuccess) return fail(MN_STATUS_CUDA);
+  if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(MN_STATUS_CUDA);
+  for (int i = 0; i < 8; i++)
+    if (cudaEventCreate(&p->ev[i]) != cudaSuccess) return fail(MN_STATUS_CUDA);
+  p->edge_tp = choose_edge_tile(C, K, &p->edge_smem);
+  p->merge_smem = (int)(((sizeof(MnSm) + 15) / 16) * 16 + (size_t)MN_H * C * 4);
+  if (cudaFuncSetAttribute(mn_edge_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->edge_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(mn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->merge_smem) != cudaSuccess)
+    return fail(MN_STATUS_CUDA);
+  p->h_ctl.resize(max_batch);
+  *out = p;
+  return MN_STATUS_OK;
+}
+
+// edge pass + record init + sort for images [0, B)
+static int run_front(mn_plan* p, int B, const float* d_class, float* d_adj, int clip, float sdb, float omf,
+                     float mlb, cudaStream_t s, bool sort_keys) {
+  const int N = p->N, C = p->C, K = p->K;
+  {
+    dim3 g((unsigned)std::min<long long>(4096, (p->h_imgs[0].hash_nbuckets * 8ll + 255) / 256), (unsigned)std::min(B, 65535));
+    mn_reset_kernel<<<g, 256, 0, s>>>(p->d_imgs, B);
+    p->timings.other_launches++;
+  }
+  MN_CUDA_OK(cudaEventRecord(p->ev[1], s));
+  MnEdgeParams P;
+  P.class_pred = d_class; P.adj_pred = d_adj; P.adj_pred_rw = sdb != 0.0f ? d_adj : nullptr;
+  P.imgs = p->d_imgs;
+  P.B = B; P.C = C; P.K = K; P.N = N; P.TP = p->edge_tp;
+  P.tiles_per_image = (N + P.TP - 1) / P.TP;
+  P.use_tma = (N % 4 == 0) && (((uintptr_t)d_class & 15) == 0) && (((uintptr_t)d_adj & 15) == 0);
+  P.clip = clip; P.sdb = sdb;
+  long long tiles = (long long)B * P.tiles_per_image;
+  int grid = (int)std::min<long long>(tiles, p->num_sms);
+  mn_edge_pass_kernel<<<grid, 512, p->edge_smem, s>>>(P);
+  p->timings.edge_launches++;
+  MN_CUDA_OK(cudaEventRecord(p->ev[2], s));
+  for (int b = 0; b < B; b++) {
+    MnRecInitParams R;
+    R.im = p->h_imgs[b];
+    R.keys_out = sort_keys ? p->d_keys_scratch : p->h_imgs[b].init_keys;
+    R.H = p->H; R.W = p->W; R.C = C; R.K = K; R.N = N; R.omf = omf; R.mlb = mlb;
+    for (int k = 0; k < K; k++) { R.off_r[k] = p->offsets[2 * k]; R.off_c[k] = p->offsets[2 * k + 1]; R.rank_of_k[k] = p->rank_of_k[k]; }
+    int g = (int)std::min<long long>((p->E + 255) / 256, (long long)p->num_sms * 16);
+    mn_record_init_kernel<<<g, 256, 0, s>>>(R);
+    p->timings.other_launches++;
+    if (sort_keys) {
+      size_t tb = p->cub_temp_bytes;
+      MN_CUDA_OK(cub::DeviceRadixSort::SortKeys(p->d_cub_temp, tb, (const uint64_t*)p->d_keys_scratch,
+                                                p->h_imgs[b].init_keys, (int)p->E, 0, 32 + MN_ORD_BITS, s));
+    }
+  }
+  MN_CUDA_OK(cudaEventRecord(p->ev[3], s));
+  MN_CUDA_OK(cudaGetLastError());
+  return MN_STATUS_OK;
+}
+
+extern "C" int mn_segment_batch_device(mn_plan* p, int B, const float* d_class, float* d_adj, int* d_mask,
+                                       int* d_object_class, int* d_ninst, int clip, float sdb, float omf,
+                                       float mlb, void* stream) {
+  g_last_error = MN_STATUS_OK;
+  if (!p || B <= 0 || B > p->max_batch || !d_class || !d_adj || !d_mask || !d_object_class || !d_ninst) {
+    g_last_error = MN_STATUS_BAD_ARG;
+    return MN_STATUS_BAD_ARG;
+  }
+  MN_CUDA_OK(cudaSetDevice(p->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : p->stream;
+  const int N = p->N;
+  p->timings.edge_launches = 0; p->timings.other_launches = 0;
+  int rc = run_front(p, B, d_class, d_adj, clip, sdb, omf, mlb, s, true);
+  if (rc) return rc;
+  MnMergeArgs A;
+  memset(&A, 0, sizeof(A));
+  A.C = p->C; A.K = p->K; A.N = N; A.W = p->W; A.omf = omf; A.mlb = mlb; A.off = p->off; A.max_rounds = 40ll * N + 100000;  // guard: rounds <= events, a few per pixel
+  int grid = std::min(B, p->num_sms);
+  mn_merge_kernel<<<grid, 256, p->merge_smem, s>>>(p->d_imgs, B, A);
+  p->timings.other_launches++;
+  MN_CUDA_OK(cudaEventRecord(p->ev[4], s));
+  // labels
+  {
+    dim3 g((unsigned)std::min(1024, (N + 255) / 256), (unsigned)std::min(B, 65535));
+    mn_label_flags_kernel<<<g, 256, 0, s>>>(p->d_imgs, B, N);
+    for (int b = 0; b < B; b++) {
+      size_t tb = p->cub_temp_bytes;
+      MN_CUDA_OK(cub::DeviceScan::ExclusiveSum(p->d_cub_temp, tb, (const int*)p->h_imgs[b].cls, p->h_imgs[b].pl_head, N, s));
+    }
+    MN_CUDA_OK(cudaMemsetAsync(d_object_class, 0xFF, (size_t)B * N * 4, s));
+    mn_label_write_kernel<<<g, 256, 0, s>>>(p->d_imgs, B, N, d_mask, d_object_class, d_ninst);
+    p->timings.other_launches += 2;
+  }
+  MN_CUDA_OK(cudaEventRecord(p->ev[5], s));
+  MN_CUDA_OK(cudaGetLastError());
+  // per-image status / statistics
+  for (int b = 0; b < B; b++)
+    MN_CUDA_OK(cudaMemcpyAsync(&p->h_ctl[b], p->h_imgs[b].ctl, sizeof(MnCtl), cudaMemcpyDeviceToHost, s));
+  MN_CUDA_OK(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, p->ev[1], p->ev[2]); p->timings.edge_ms = ms;
+  cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); p->timings.record_init_sort_ms = ms;
+  cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->timings.merge_ms = ms;
+  cudaEventElapsedTime(&ms, p->ev[4], p->ev[5]); p->timings.label_ms = ms;
+  cudaEventElapsedTime(&ms, p->ev[1], p->ev[5]); p->timings.total_ms = ms;
+  int worst = MN_STATUS_OK;
+  for (int b = 0; b < B; b++)
+    if (p->h_ctl[b].status != MN_OK && worst == MN_STATUS_OK) worst = p->h_ctl[b].status;
+  g_last_error = worst;
+  return worst;
+}
+
+static int ensure_staging(mn_plan* p, int B) {
+  if ((size_t)B <= p->staging_batch) return MN_STATUS_OK;
+  cudaFree(p->d_in_class); cudaFree(p->d_in_adj); cudaFree(p->d_out_mask); cudaFree(p->d_out_cls); cudaFree(p->d_out_ninst);
+  p->d_in_class = nullptr; p->d_in_adj = nullptr; p->d_out_mask = nullptr; p->d_out_cls = nullptr; p->d_out_ninst = nullptr;
+  p->staging_batch = 0;
+  const size_t N = p->N;
+  MN_CUDA_OK(cudaMalloc(&p->d_in_class, (size_t)B * p->C * N * 4));
+  MN_CUDA_OK(cudaMalloc(&p->d_in_adj, (size_t)B * p->K * N * 4));
+  MN_CUDA_OK(cudaMalloc(&p->d_out_mask, (size_t)B * N * 4));
+  MN_CUDA_OK(cudaMalloc(&p->d_out_cls, (size_t)B * N * 4));
+  MN_CUDA_OK(cudaMalloc(&p->d_out_ninst, (size_t)B * 4));
+  p->staging_batch = B;
+  return MN_STATUS_OK;
+}
+
+extern "C" int mn_segment_batch_host(mn_plan* p, int B, const float* h_class, float* h_adj, int* h_mask,
+                                     int* h_object_class, int* h_ninst, int clip, float sdb, float omf,
+                                     float mlb) {
+  g_last_error = MN_STATUS_OK;
+  if (!p || B <= 0 || B > p->max_batch || !h_class || !h_adj || !h_mask || !h_object_class) {
+    g_last_error = MN_STATUS_BAD_ARG;
+    return MN_STATUS_BAD_ARG;
+  }
+  MN_CUDA_OK(cudaSetDevice(p->device));
+  int rc = ensure_staging(p, B);
+  if (rc) return rc;
+  const size_t N = p->N;
+  cudaStream_t s = p->stream;
+  MN_CUDA_OK(cudaEventRecord(p->ev[0], s));
+  MN_CUDA_OK(cudaMemcpyAsync(p->d_in_class, h_class, (size_t)B * p->C * N * 4, cudaMemcpyHostToDevice, s));
+  MN_CUDA_OK(cudaMemcpyAsync(p->d_in_adj, h_adj, (size_t)B * p->K * N * 4, cudaMemcpyHostToDevice, s));
+  rc = mn_segment_batch_device(p, B, p->d_in_class, p->d_in_adj, p->d_out_mask, p->d_out_cls, p->d_out_ninst,
+                               clip, sdb, omf, mlb, s);
+  MN_CUDA_OK(cudaEventRecord(p->ev[6], s));
+  MN_CUDA_OK(cudaMemcpyAsync(h_mask, p->d_out_mask, (size_t)B * N * 4, cudaMemcpyDeviceToHost, s));
+  MN_CUDA_OK(cudaMemcpyAsync(h_object_class, p->d_out_cls, (size_t)B * N * 4, cudaMemcpyDeviceToHost, s));
+  if (h_ninst) MN_CUDA_OK(cudaMemcpyAsync(h_ninst, p->d_out_ninst, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  if (sdb != 0.0f)  // the reference rewrites the caller's buffer (segment.cc:187-191)
+    MN_CUDA_OK(cudaMemcpyAsync(h_adj, p->d_in_adj, (size_t)B * p->K * N * 4, cudaMemcpyDeviceToHost, s));
+  MN_CUDA_OK(cudaEventRecord(p->ev[7], s));
+  MN_CUDA_OK(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->timings.h2d_ms = ms;
+  cudaEventElapsedTime(&ms, p->ev[6], p->ev[7]); p->timings.d2h_ms = ms;
+  g_last_error = rc;
+  return rc;
+}
+
+extern "C" int mn_plan_image_stats(mn_plan* p, int image, mn_image_stats* o) {
+  if (!p || !o || image < 0 || image >= p->max_batch) return MN_STATUS_BAD_ARG;
+  const MnCtl& c = p->h_ctl[image];
+  o->status = c.status; o->fail_line = c.fail_line; o->n_instances = c.n_instances; o->n_init_entries = c.n_init;
+  o->rounds = c.rounds; o->events = c.events; o->merges = c.merges; o->restores = c.restores;
+  o->invalid_pops = c.invalid_pops; o->solo_events = c.solo_events; o->refills = c.refills;
+  o->flushes = c.flushes; o->splits = c.splits; o->pairs = c.pairs; o->cuts_conflict = c.cuts_conflict;
+  o->cuts_cascade = c.cuts_cascade; o->cuts_capacity = c.cuts_capacity;
+  o->queue_chunks_used = c.qc_bump; o->pixel_chunks_used = c.plc_bump; o->tree_nodes_used = c.tn_bump;
+  return MN_STATUS_OK;
+}
+extern "C" int mn_plan_timings(mn_plan* p, mn_timings* o) {
+  if (!p || !o) return MN_STATUS_BAD_ARG;
+  *o = p->timings;
+  return MN_STATUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// drop-in symbol (segment.cc:742-752): one cached plan per thread, re-created when the shape changes
+struct PlanCache {
+  mn_plan* plan = nullptr;
+  int H = 0, W = 0, C = 0, K = 0;
+  int offsets[2 * MN_MAX_K];
+  ~PlanCache() { /* process teardown: the driver may already be gone; leak on purpose */ }
+};
+static thread_local PlanCache g_cache;
+
+extern "C" void c_run_segmentation(float* class_pred, int class_dim, float* adj_pred, int offset_dim,
+                                   int img_width, int img_height, int num_classes, int* offset_list,
+                                   int* output, int* object_class, float sdb, float omf, float mlb) {
+  g_last_error = MN_STATUS_OK;
+  const long long N = (long long)img_width * img_height;
+  if (output && N > 0) memset(output, 0, sizeof(int) * (size_t)N);
+  if (object_class && N > 0) memset(object_class, 0xFF, sizeof(int) * (size_t)N);
+  if (!class_pred || !adj_pred || !offset_list || !output || !object_class || class_dim != num_classes ||
+      offset_dim <= 0 || offset_dim > MN_MAX_K) {
+    g_last_error = MN_STATUS_BAD_ARG;
+    return;
+  }
+  PlanCache& c = g_cache;
+  bool same = c.plan && c.H == img_height && c.W == img_width && c.C == num_classes && c.K == offset_dim &&
+              memcmp(c.offsets, offset_list, sizeof(int) * 2 * offset_dim) == 0;
+  if (!same) {
+    if (c.plan) { mn_plan_destroy(c.plan); c.plan = nullptr; }
+    int rc = mn_plan_create(&c.plan, 1, img_height, img_width, num_classes, offset_dim, offset_list, 0);
+    if (rc) { c.plan = nullptr; return; }
+    c.H = img_height; c.W = img_width; c.C = num_classes; c.K = offset_dim;
+    memcpy(c.offsets, offset_list, sizeof(int) * 2 * offset_dim);
+  }
+  int ninst = 0;
+  mn_segment_batch_host(c.plan, 1, class_pred, adj_pred, output, object_class, &ninst, 0, sdb, omf, mlb);
+  if (g_last_error != MN_STATUS_OK) {
+    memset(output, 0, sizeof(int) * (size_t)N);
+    memset(object_class, 0xFF, sizeof(int) * (size_t)N);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// test hooks
+extern "C" int mn_debug_edge_dump(int H, int W, int C, int K, const int* offset_list, const float* h_class,
+                                  float* h_adj, float sdb, float omf, float mlb, float* clp, int* cls,
+                                  float* same, float* diff, float* oml, float* mp, int* lo, int* hi) {
+  mn_plan* p = nullptr;
+  int rc = mn_plan_create(&p, 1, H, W, C, K, offset_list, 0);
+  if (rc) return rc;
+  auto done = [&](int code) { mn_plan_destroy(p); g_last_error = code; return code; };
+  if (ensure_staging(p, 1)) return done(MN_STATUS_CUDA);
+  const size_t N = p->N, E = (size_t)p->E;
+  cudaStream_t s = p->stream;
+  cudaMemcpyAsync(p->d_in_class, h_class, (size_t)C * N * 4, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(p->d_in_adj, h_adj, (size_t)K * N * 4, cudaMemcpyHostToDevice, s);
+  rc = run_front(p, 1, p->d_in_class, p->d_in_adj, 0, sdb, omf, mlb, s, false);
+  if (rc) return done(rc);
+  std::vector<int2> lh(E);
+  std::vector<float4> val(E);
+  const MnImage& im = p->h_imgs[0];
+  cudaMemcpyAsync(clp, im.clp, N * C * 4, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(cls, im.cls, N * 4, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(lh.data(), im.rec_lh, E * 8, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(val.data(), im.rec_val, E * 16, cudaMemcpyDeviceToHost, s);
+  if (sdb != 0.0f) cudaMemcpyAsync(h_adj, p->d_in_adj, (size_t)K * N * 4, cudaMemcpyDeviceToHost, s);
+  if (cudaStreamSynchronize(s) != cudaSuccess) return done(MN_STATUS_CUDA);
+  for (size_t r = 0; r < E; r++) {
+    lo[r] = lh[r].x; hi[r] = lh[r].y;
+    bool v = lh[r].x >= 0;
+    oml[r] = v ? val[r].x : 0.f; same[r] = v ? val[r].y : 0.f; diff[r] = v ? val[r].z : 0.f; mp[r] = v ? val[r].w : 0.f;
+  }
+  return done(MN_STATUS_OK);
+}
+
+extern "C" int mn_debug_libm(int which, unsigned first_bits, unsigned n, float bias, float* h_out) {
+  g_last_error = MN_STATUS_OK;
+  if (n == 0 || !h_out) return MN_STATUS_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  float* d = nullptr;
+  MN_CUDA_OK(cudaMalloc(&d, (size_t)n * 4));
+  mn_libm_kernel<<<1184, 256>>>(which, first_bits, n, bias, d);
+  cudaError_t e = cudaMemcpy(h_out, d, (size_t)n * 4, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  return MN_STATUS_OK;
+}

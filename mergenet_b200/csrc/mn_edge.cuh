@@ -86,14 +86,12 @@ struct MnEdgeParams {
   const float* class_pred;  // [B][C][N]
   const float* adj_pred;    // [B][K][N]
   float* adj_pred_rw;       // same buffer, written in place when sdb != 0 (cc:187-191), else null
-  float* clp;               // [B][N][C]
-  int* cls;                 // [B][N]
-  float* rec_same;          // [B][N*K]
-  float* rec_diff;          // [B][N*K]
+  const MnImage* imgs;      // per-image workspace: clp [N][C], cls [N], rec_same / rec_diff [N*K]
   int B, C, K, N;
   int TP;                   // pixels per tile (multiple of 4)
   int tiles_per_image;
   int use_tma;              // N % 4 == 0 and 16-byte aligned bases
+  int clip;                 // apply the wrapper's clip to [2^-23, 1-2^-23] (c_segment.pyx:53-55)
   float sdb;
 };
 
@@ -146,6 +144,10 @@ __global__ void __launch_bounds__(512, 1) mn_edge_pass_kernel(MnEdgeParams P) {
     const int start = (int)(tile % P.tiles_per_image) * TP;
     const int tl = min(TP, P.N - start);
     float* in = stage ? in1 : in0;
+    float* im_clp = P.imgs[b].clp;
+    int* im_cls = P.imgs[b].cls;
+    float* im_same = P.imgs[b].rec_same;
+    float* im_diff = P.imgs[b].rec_diff;
     if (P.use_tma) {
       // prefetch the next tile into the other stage (its previous readers passed the
       // __syncthreads at the end of the last iteration)
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(512, 1) mn_edge_pass_kernel(MnEdgeParams P) {
     for (int i = tid; i < items; i += nt) {
       int pl = i / tl, px = i - pl * tl;
       float v = in[(size_t)pl * TP + px];
+      if (P.clip) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
       if (pl < C) {
         out_clp[px * C + pl] = MN_FADD(0.0f, mn_logf_exact(v, tab));  // cc:11-16
       } else {
@@ -200,12 +203,12 @@ __global__ void __launch_bounds__(512, 1) mn_edge_pass_kernel(MnEdgeParams P) {
           bc = c;
         }
       }
-      P.cls[(size_t)b * P.N + start + px] = bc;
+      im_cls[start + px] = bc;
     }
     // ---- results leave as bulk stores (contiguous in global: pixel-major tiles) ----
-    float* g_clp = P.clp + ((size_t)b * P.N + start) * C;
-    float* g_same = P.rec_same + ((size_t)b * P.N + start) * K;
-    float* g_diff = P.rec_diff + ((size_t)b * P.N + start) * K;
+    float* g_clp = im_clp + (size_t)start * C;
+    float* g_same = im_same + (size_t)start * K;
+    float* g_diff = im_diff + (size_t)start * K;
     if (P.use_tma) {
       mn_fence_proxy_async();
       __syncthreads();
@@ -230,9 +233,9 @@ __global__ void __launch_bounds__(512, 1) mn_edge_pass_kernel(MnEdgeParams P) {
 
 // ---------------------------------------------------------------------------------------------
 struct MnRecInitParams {
-  MnImage img0;  // image 0's pointers; image b = img0 advanced by b * stride (see mn_layout.h)
-  MnStrides st;
-  int B, H, W, C, K, N;
+  MnImage im;  // one image per launch (its sort keys go to a scratch buffer shared by the batch)
+  uint64_t* keys_out;
+  int H, W, C, K, N;
   int off_r[MN_MAX_K], off_c[MN_MAX_K];
   int rank_of_k[MN_MAX_K];  // rank of |linear delta| among the offsets (tie-break ordinal)
   float omf, mlb;
@@ -240,12 +243,10 @@ struct MnRecInitParams {
 
 __global__ void __launch_bounds__(256) mn_record_init_kernel(MnRecInitParams P) {
   const long long E = (long long)P.N * P.K;
-  const long long total = E * P.B;
-  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+  const MnImage& im = P.im;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < E;
        g += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(g / E);
-    const int r = (int)(g - (long long)b * E);
-    MnImage im = mn_image_at(P.img0, P.st, b);
+    const int r = (int)g;
     const int p = r / P.K, k = r - p * P.K;
     const int row = p / P.W, col = p - row * P.W;
     if (k == 0) {
@@ -280,12 +281,12 @@ __global__ void __launch_bounds__(256) mn_record_init_kernel(MnRecInitParams P) 
       mn_hash_insert(im, lo, hi, r);
       if (mp >= 0.0f) {  // cc:225-227
         uint32_t ord = (uint32_t)lo * (uint32_t)P.K + (uint32_t)P.rank_of_k[k];
-        key = ((uint64_t)(~mn_f2u(mp)) << MN_ORD_BITS) | ord;
+        key = ((uint64_t)(~mn_f2u(mp == 0.0f ? 0.0f : mp)) << MN_ORD_BITS) | ord;
       }
     } else {
       im.rec_lh[r] = make_int2(-1, -1);
       im.rec_val[r] = make_float4(0.f, 0.f, 0.f, -1.0f);
     }
-    im.init_keys[r] = key;
+    P.keys_out[r] = key;
   }
 }

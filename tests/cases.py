@@ -1,0 +1,63 @@
+"""Seeded test inputs shared by the CPU and GPU suites (sizes the oracle finishes in seconds)."""
+import numpy as np
+
+from mergenet_b200 import synth
+
+RECIPE_OPTS = (0.0, 1.0, 0.03)   # egs/cityscape/local/segment.py:134-136
+PLAIN_OPTS = (0.0, 1.0, 0.0)
+QUARTER_OPTS = (0.0, 0.25, 0.0)  # ObjectSegmenterOption default omf (segment.h:250-254)
+
+
+def cityscapes_like(h, w, seed, soft, n_shapes=None, rmax=20):
+    offs = synth.generate_offsets(40, 10)
+    n_shapes = n_shapes if n_shapes is not None else max(3, h * w // 2000)
+    m, cl = synth.gt_instance_mask(h, w, n_shapes, rmax, 9, seed)
+    if soft:
+        cp, sp = synth.soft_maps(m, cl, 9, offs, seed + 5)
+    else:
+        cp, sp = synth.oracle_mode_maps(m, cl, 9, offs)
+    return cp, sp, 9, offs
+
+
+def coco_like(h, w, seed, soft):
+    offs = synth.generate_offsets(40, 16)
+    m, cl = synth.gt_instance_mask(h, w, max(4, h * w // 300), 8, 81, seed)
+    if soft:
+        cp, sp = synth.soft_maps(m, cl, 81, offs, seed + 11)
+    else:
+        cp, sp = synth.oracle_mode_maps(m, cl, 81, offs)
+    return cp, sp, 81, offs
+
+
+def smooth(h, w, seed):
+    offs = synth.generate_offsets(40, 10)
+    cp, sp = synth.smooth_random_maps(h, w, 9, 10, seed)
+    return cp, sp, 9, offs
+
+
+def small_cases():
+    """(name, class_pred, adj_pred, C, offsets) -- the parity matrix."""
+    out = []
+    out.append(("city_soft_48x64", ) + cityscapes_like(48, 64, 0, True))
+    out.append(("city_oracle_48x64", ) + cityscapes_like(48, 64, 1, False))
+    out.append(("city_soft_odd_45x67", ) + cityscapes_like(45, 67, 2, True))
+    out.append(("smooth_40x56", ) + smooth(40, 56, 3))
+    out.append(("coco_oracle_48x48", ) + coco_like(48, 48, 4, False))
+    out.append(("coco_soft_44x52", ) + coco_like(44, 52, 5, True))
+    out.append(("tiny_1x7", ) + cityscapes_like(1, 7, 6, True, n_shapes=1, rmax=3))
+    out.append(("tiny_3x3", ) + cityscapes_like(3, 3, 7, True, n_shapes=1, rmax=3))
+    return out
+
+
+def medium_cases():
+    out = []
+    out.append(("city_soft_128x192", ) + cityscapes_like(128, 192, 10, True, rmax=30))
+    out.append(("city_oracle_96x160", ) + cityscapes_like(96, 160, 11, False, rmax=30))
+    out.append(("smooth_96x128", ) + smooth(96, 128, 12))
+    return out
+
+
+def same_result(oracle, a, b):
+    ca = oracle.canonical_result(*a)
+    cb = oracle.canonical_result(*b)
+    return np.array_equal(ca[0], cb[0]) and list(ca[1]) == list(cb[1])

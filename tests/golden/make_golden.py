@@ -1,0 +1,39 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref/libsegment_ref.so,
+built from /root/reference/utils/csegment/segment.cc by oracle/Makefile) on small seeded inputs.
+Run from the repo root in the build container (the reference tree cannot travel):
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases  # noqa: E402
+import oracle  # noqa: E402
+
+
+def main():
+    assert oracle.have_reference() or os.path.exists("/root/reference"), "reference needed"
+    oracle.build()
+    out = os.path.dirname(os.path.abspath(__file__))
+    sel = {"city_soft_48x64": cases.RECIPE_OPTS, "city_oracle_48x64": cases.RECIPE_OPTS,
+           "smooth_40x56": cases.PLAIN_OPTS, "coco_oracle_48x48": cases.RECIPE_OPTS,
+           "city_soft_odd_45x67": cases.QUARTER_OPTS}
+    for name, cp, sp, C, offs in cases.small_cases():
+        if name not in sel:
+            continue
+        opts = sel[name]
+        mask, ocls = oracle.ref_run_segmentation(cp, sp, C, offs, *opts)
+        np.savez_compressed(os.path.join(out, name + ".npz"), class_pred=cp,
+                            adj_pred=sp, num_classes=np.int32(C), offsets=np.array(offs, np.int32),
+                            opts=np.array(opts, np.float32), ref_mask=mask.astype(np.int16),
+                            ref_object_class=np.array(ocls, np.int32))
+        print(name, mask.shape, len(ocls), "instances")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+"""CPU: the CUDA scheduler source (mergenet_b200/csrc/mn_merge.cuh) compiled for the host and run with
+one logical thread (tests/emul) must reproduce the oracle: identical masks / classes and the same
+number of executed events and merges.  This tests the scheduler's logic; the GPU suite tests the
+real kernels."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMUL_DIR = os.path.join(HERE, "emul")
+EMUL_SO = os.path.join(EMUL_DIR, "libemul.so")
+NAMES = ['rounds', 'events', 'merges', 'restores', 'invalid', 'solo', 'refills', 'flushes', 'splits', 'pairs',
+         'cut_conf', 'cut_casc', 'cut_cap', 'qc_bump', 'plc_bump', 'tn_bump']
+
+
+@pytest.fixture(scope="module")
+def emul():
+    srcs = [os.path.join(EMUL_DIR, "emul_merge.cpp")] + [
+        os.path.join(HERE, "..", "mergenet_b200", "csrc", f) for f in ("mn_merge.cuh", "mn_layout.h", "mn_common.h")]
+    if not os.path.exists(EMUL_SO) or any(os.path.getmtime(s) > os.path.getmtime(EMUL_SO) for s in srcs):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off",
+                               "-o", EMUL_SO, srcs[0]])
+    lib = ctypes.CDLL(EMUL_SO)
+    F = ctypes.POINTER(ctypes.c_float); I = ctypes.POINTER(ctypes.c_int); LL = ctypes.POINTER(ctypes.c_longlong)
+    lib.emul_run_segmentation.argtypes = [F, ctypes.c_int, F, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          I, I, I, ctypes.c_float, ctypes.c_float, ctypes.c_float, LL]
+    return lib
+
+
+def run_emul(emul, oracle, cp, sp, C, offs, opts):
+    cpc, apc, off, mask, ocls = oracle._glue(cp, sp, offs)
+    st = (ctypes.c_longlong * 16)()
+    rc = emul.emul_run_segmentation(oracle._fp(cpc), C, oracle._fp(apc), apc.shape[0], apc.shape[2], apc.shape[1],
+                                    C, oracle._ip(off), oracle._ip(mask), oracle._ip(ocls), *opts, st)
+    return rc, mask, oracle._trim(ocls), dict(zip(NAMES, list(st)))
+
+
+@pytest.mark.parametrize("opts", [cases.RECIPE_OPTS, cases.PLAIN_OPTS])
+def test_emulated_scheduler_matches_oracle_small(emul, oracle_mod, opts):
+    for name, cp, sp, C, offs in cases.small_cases():
+        m0, c0, st0 = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)
+        rc, m1, c1, st = run_emul(emul, oracle_mod, cp, sp, C, offs, opts)
+        assert rc == 0, (name, rc)
+        assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), name
+        assert st["merges"] == st0["merges"], name
+
+
+def test_emulated_scheduler_matches_oracle_medium(emul, oracle_mod):
+    for name, cp, sp, C, offs in cases.medium_cases():
+        m0, c0, st0 = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *cases.RECIPE_OPTS)
+        rc, m1, c1, st = run_emul(emul, oracle_mod, cp, sp, C, offs, cases.RECIPE_OPTS)
+        assert rc == 0, (name, rc)
+        assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), name
+        assert st["merges"] == st0["merges"], name

@@ -1,0 +1,152 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same
+seeded inputs, against the committed golden fixtures (outputs of the reference itself), and through
+size-independent invariants.  Bit-exact: masks after canonical relabel, per-instance classes."""
+import ctypes
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _edge_dump(lib_mod, cp, sp, C, offs, opts):
+    L = lib_mod.lib()
+    F = ctypes.POINTER(ctypes.c_float); I = ctypes.POINTER(ctypes.c_int)
+    K, H, W = sp.shape
+    N = H * W
+    off = np.ascontiguousarray(np.array(offs, np.int32))
+    sp = sp.copy()
+    d = dict(clp=np.zeros((N, C), np.float32), cls=np.zeros(N, np.int32), same=np.zeros(N * K, np.float32),
+             diff=np.zeros(N * K, np.float32), oml=np.zeros(N * K, np.float32), mp=np.zeros(N * K, np.float32),
+             lo=np.zeros(N * K, np.int32), hi=np.zeros(N * K, np.int32))
+    st = L.mn_debug_edge_dump(H, W, C, K, off.ctypes.data_as(I), cp.ctypes.data_as(F), sp.ctypes.data_as(F),
+                              *[float(o) for o in opts], d["clp"].ctypes.data_as(F), d["cls"].ctypes.data_as(I),
+                              d["same"].ctypes.data_as(F), d["diff"].ctypes.data_as(F), d["oml"].ctypes.data_as(F),
+                              d["mp"].ctypes.data_as(F), d["lo"].ctypes.data_as(I), d["hi"].ctypes.data_as(I))
+    assert st == 0
+    d["adj"] = sp
+    return d
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.mark.parametrize("opts", [cases.RECIPE_OPTS, cases.QUARTER_OPTS, (0.5, 1.0, 0.03)])
+def test_edge_pass_bitwise_equals_reference_constructor(oracle_mod, lib_mod, opts):
+    """segment.cc:153-232: clp, cls, same, diff, oml, initial mp per record -- every bit."""
+    for name, cp, sp, C, offs in cases.small_cases() + cases.medium_cases()[:1]:
+        ref = oracle_mod.oracle_init_dump(cp, sp, C, offs, *opts)
+        got = _edge_dump(lib_mod, cp, sp, C, offs, opts)
+        valid = ref["valid"].astype(bool)
+        assert np.array_equal(valid, got["lo"] >= 0), name
+        assert np.array_equal(_bits(ref["clp"]), _bits(got["clp"])), name
+        assert np.array_equal(ref["cls"], got["cls"]), name
+        for k in ("same", "diff", "oml", "mp"):
+            assert np.array_equal(_bits(ref[k])[valid], _bits(got[k])[valid]), (name, k)
+        if opts[0] != 0:  # in-place rewrite of the caller's sameness buffer (segment.cc:187-191)
+            assert np.array_equal(_bits(ref["adj_pred"]), _bits(got["adj"])), name
+
+
+@pytest.mark.parametrize("opts", [cases.RECIPE_OPTS, cases.PLAIN_OPTS, cases.QUARTER_OPTS])
+def test_drop_in_c_abi_matches_oracle_small(oracle_mod, lib_mod, opts):
+    from mergenet_b200 import c_segment
+    for name, cp, sp, C, offs in cases.small_cases():
+        m0, c0, st0 = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)
+        m1, c1 = c_segment.run_segmentation(cp, sp, C, offs, *opts)
+        assert m1.dtype == np.int32 and m1.shape == m0.shape
+        assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), name
+        lp0 = oracle_mod.total_logprob_from_scratch(m0, c0, cp, sp, offs, opts[1])
+        lp1 = oracle_mod.total_logprob_from_scratch(m1, c1, cp, sp, offs, opts[1])
+        assert abs(lp0 - lp1) <= 1e-5 * abs(lp0), name  # north-star tolerance (identical partitions)
+
+
+def test_drop_in_matches_oracle_medium(oracle_mod, lib_mod):
+    from mergenet_b200 import c_segment
+    for name, cp, sp, C, offs in cases.medium_cases():
+        m0, c0, st0 = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *cases.RECIPE_OPTS)
+        m1, c1 = c_segment.run_segmentation(cp, sp, C, offs, *cases.RECIPE_OPTS)
+        assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), name
+
+
+def test_same_different_bias_path(oracle_mod, lib_mod):
+    from mergenet_b200 import c_segment
+    name, cp, sp, C, offs = cases.small_cases()[0]
+    for sdb in (0.5, -0.7):
+        m0, c0, _ = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, sdb, 1.0, 0.0)
+        m1, c1 = c_segment.run_segmentation(cp, sp, C, offs, sdb, 1.0, 0.0)
+        assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), (name, sdb)
+
+
+def test_golden_fixtures_from_the_reference(oracle_mod, lib_mod):
+    from mergenet_b200 import c_segment
+    files = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+    assert files
+    for f in files:
+        g = np.load(f)
+        offs = [tuple(int(v) for v in o) for o in g["offsets"]]
+        opts = tuple(float(v) for v in g["opts"])
+        m1, c1 = c_segment.run_segmentation(np.ascontiguousarray(g["class_pred"]), np.ascontiguousarray(g["adj_pred"]),
+                                            int(g["num_classes"]), offs, *opts)
+        ref = (g["ref_mask"].astype(np.int32), [int(v) for v in g["ref_object_class"]])
+        assert cases.same_result(oracle_mod, ref, (m1, c1)), os.path.basename(f)
+
+
+def test_python_class_facade(oracle_mod, lib_mod):
+    from mergenet_b200 import ObjectSegmenter, SegmenterOptions
+    name, cp, sp, C, offs = cases.small_cases()[1]
+    opts = SegmenterOptions(0.0, 1.0, 0.03)
+    m1, c1 = ObjectSegmenter(cp, sp, C, offs, opts).run_segmentation()
+    m0, c0, _ = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)
+    assert cases.same_result(oracle_mod, (m0, c0), (m1, c1))
+
+
+def test_batch_api_host_and_device_agree_and_are_deterministic(oracle_mod, lib_mod):
+    import torch
+    from mergenet_b200 import BatchSegmenter, SegmenterOptions
+    H, W = 48, 64
+    items = [cases.cityscapes_like(H, W, s, s % 2 == 0) for s in range(5)]
+    C, offs = items[0][2], items[0][3]
+    cp = np.ascontiguousarray(np.stack([it[0] for it in items]))
+    sp = np.ascontiguousarray(np.stack([it[1] for it in items]))
+    opts = SegmenterOptions(*cases.RECIPE_OPTS)
+    seg = BatchSegmenter(8, H, W, C, offs)
+    m_h, oc_h, n_h = seg.segment_host(cp, sp, opts)
+    stats = [seg.stats(b) for b in range(5)]
+    m_d, oc_d, n_d = seg.segment_device(torch.from_numpy(cp).cuda(), torch.from_numpy(sp).cuda(), opts)
+    m_d2, oc_d2, n_d2 = seg.segment_device(torch.from_numpy(cp).cuda(), torch.from_numpy(sp).cuda(), opts)
+    assert np.array_equal(m_h, m_d.cpu().numpy()) and np.array_equal(oc_h, oc_d.cpu().numpy())
+    assert torch.equal(m_d, m_d2) and torch.equal(oc_d, oc_d2) and torch.equal(n_d, n_d2)
+    for b, it in enumerate(items):
+        m0, c0, st0 = oracle_mod.oracle_run_segmentation(it[0], it[1], C, offs, *cases.RECIPE_OPTS)
+        got = (m_h[b], [int(v) for v in oc_h[b][:n_h[b]]])
+        assert cases.same_result(oracle_mod, (m0, c0), got), b
+        assert stats[b]["merges"] == st0["merges"], b
+        assert stats[b]["status"] == 0
+    seg.close()
+
+
+def test_invariants_at_larger_size(oracle_mod, lib_mod):
+    """Size-independent properties (no oracle needed): labels are 1..n, every labelled object is one
+    4... offset-connected set of pixels, idempotent determinism, and merges = N - surviving objects."""
+    from mergenet_b200 import BatchSegmenter, SegmenterOptions
+    H, W = 256, 384
+    cp, sp, C, offs = cases.cityscapes_like(H, W, 21, True, rmax=40)
+    seg = BatchSegmenter(1, H, W, C, offs)
+    opts = SegmenterOptions(*cases.RECIPE_OPTS)
+    m, oc, n = seg.segment_host(cp[None], sp[None], opts)
+    st = seg.stats(0)
+    m2, oc2, n2 = seg.segment_host(cp[None], sp[None], opts)
+    assert np.array_equal(m, m2) and np.array_equal(oc, oc2)
+    n = int(n[0])
+    labs = np.unique(m[0])
+    assert labs.min() >= 0 and labs.max() == n and len(labs[labs > 0]) == n
+    assert np.all(oc[0][:n] > 0) and np.all(oc[0][n:] == -1)
+    assert st["status"] == 0 and st["events"] == st["merges"] + st["restores"]
+    assert st["merges"] <= H * W - 1
+    seg.close()

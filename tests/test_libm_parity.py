@@ -1,0 +1,66 @@
+"""libm parity: the fp64 recipe behind the CUDA edge pass must reproduce the
+host libm bit for bit on the whole clipped domain [2^-23, 1-2^-23] = float bits 0x34000000..0x3f7ffffe.
+CPU: the oracle's restatement of the recipe vs libm (exhaustive).  GPU: the device functions vs host
+tables produced by the oracle library (exhaustive, chunked)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+LO_BITS = 0x34000000
+HI_BITS = 0x3F7FFFFE
+
+
+def test_logf_recipe_equals_libm_exhaustive(oracle_mod):
+    bad = oracle_mod.oracle_lib().mno_logf_recipe_mismatches(LO_BITS, HI_BITS, 1)
+    assert bad == 0
+
+
+def _device_vs_host(oracle_mod, lib_mod, which, host_fn, stride_chunks=1, bias=0.0):
+    L = lib_mod.lib()
+    F = ctypes.POINTER(ctypes.c_float)
+    chunk = 1 << 24
+    bad = 0
+    first_bad = []
+    idx = 0
+    for start in range(LO_BITS, HI_BITS + 1, chunk):
+        idx += 1
+        if stride_chunks > 1 and idx % stride_chunks:
+            continue
+        n = min(chunk, HI_BITS + 1 - start)
+        dev = np.empty(n, np.float32)
+        host = np.empty(n, np.float32)
+        st = L.mn_debug_libm(which, start, n, float(bias), dev.ctypes.data_as(F))
+        assert st == 0
+        if which == 2:
+            host_fn(start, n, float(bias), host.ctypes.data_as(F))
+        else:
+            host_fn(start, n, host.ctypes.data_as(F))
+        neq = dev.view(np.uint32) != host.view(np.uint32)
+        c = int(neq.sum())
+        if c:
+            bad += c
+            i = int(np.flatnonzero(neq)[0])
+            first_bad.append((hex(start + i), float(dev[i]), float(host[i])))
+    return bad, first_bad
+
+
+@pytest.mark.gpu
+def test_device_logf_equals_host_exhaustive(oracle_mod, lib_mod):
+    bad, first = _device_vs_host(oracle_mod, lib_mod, 0, oracle_mod.oracle_lib().mno_host_logf_table)
+    assert bad == 0, first[:5]
+
+
+@pytest.mark.gpu
+def test_device_log1m_equals_host_exhaustive(oracle_mod, lib_mod):
+    bad, first = _device_vs_host(oracle_mod, lib_mod, 1, oracle_mod.oracle_lib().mno_host_log1m_table)
+    assert bad == 0, first[:5]
+
+
+@pytest.mark.gpu
+def test_device_bias_transform_equals_host_sampled(oracle_mod, lib_mod):
+    # same_different_bias != 0 (segment.cc:183-195): every 4th 16M-chunk of the domain, two biases
+    for bias in (0.5, -1.25):
+        bad, first = _device_vs_host(oracle_mod, lib_mod, 2, oracle_mod.oracle_lib().mno_host_bias_table,
+                                     stride_chunks=4, bias=bias)
+        assert bad == 0, (bias, first[:5])

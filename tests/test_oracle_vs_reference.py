@@ -1,0 +1,70 @@
+"""CPU: the C restatement (oracle/mergenet_oracle.c) against the reference itself and the committed
+golden fixtures.  This is what pins the oracle (the reference ships no vectors of its own)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("opts", [cases.RECIPE_OPTS, cases.PLAIN_OPTS, cases.QUARTER_OPTS])
+def test_oracle_matches_reference_small(oracle_mod, opts):
+    if not oracle_mod.have_reference():
+        pytest.skip("oracle/_ref/libsegment_ref.so not built (reference tree absent)")
+    for name, cp, sp, C, offs in cases.small_cases():
+        ref = oracle_mod.ref_run_segmentation(cp, sp, C, offs, *opts)
+        ora = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)[:2]
+        assert cases.same_result(oracle_mod, ref, ora), name
+
+
+def test_oracle_matches_reference_with_bias(oracle_mod):
+    if not oracle_mod.have_reference():
+        pytest.skip("reference .so absent")
+    name, cp, sp, C, offs = cases.small_cases()[0]
+    for sdb in (0.5, -0.7):
+        ref = oracle_mod.ref_run_segmentation(cp, sp, C, offs, sdb, 1.0, 0.0)
+        ora = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, sdb, 1.0, 0.0)[:2]
+        assert cases.same_result(oracle_mod, ref, ora), (name, sdb)
+
+
+def test_oracle_matches_golden_fixtures(oracle_mod):
+    files = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+    assert files, "golden fixtures missing"
+    for f in files:
+        g = np.load(f)
+        offs = [tuple(int(v) for v in o) for o in g["offsets"]]
+        opts = tuple(float(v) for v in g["opts"])
+        ora = oracle_mod.oracle_run_segmentation(g["class_pred"], g["adj_pred"], int(g["num_classes"]), offs, *opts)[:2]
+        ref = (g["ref_mask"], [int(v) for v in g["ref_object_class"]])
+        assert cases.same_result(oracle_mod, ref, ora), os.path.basename(f)
+
+
+def test_round_model_equals_sequential(oracle_mod):
+    """The plan/commit round rule the CUDA scheduler implements, executed on the host."""
+    import ctypes
+    lib = oracle_mod.oracle_lib()
+    F = ctypes.POINTER(ctypes.c_float); I = ctypes.POINTER(ctypes.c_int); LL = ctypes.POINTER(ctypes.c_longlong)
+    lib.mno_run_rounds_model.argtypes = [F, ctypes.c_int, F, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         I, I, I, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, LL, LL]
+    for name, cp, sp, C, offs in cases.small_cases()[:4]:
+        seq = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *cases.RECIPE_OPTS)[:2]
+        cpc, apc, off, mask, ocls = oracle_mod._glue(cp, sp, offs)
+        r = ctypes.c_longlong(); e = ctypes.c_longlong()
+        rc = lib.mno_run_rounds_model(oracle_mod._fp(cpc), C, oracle_mod._fp(apc), apc.shape[0], apc.shape[2],
+                                      apc.shape[1], C, oracle_mod._ip(off), oracle_mod._ip(mask), oracle_mod._ip(ocls),
+                                      *cases.RECIPE_OPTS, 32, ctypes.byref(r), ctypes.byref(e))
+        assert rc == 0, name
+        assert cases.same_result(oracle_mod, seq, (mask, oracle_mod._trim(ocls))), name
+
+
+def test_from_scratch_logprob_is_partition_function(oracle_mod):
+    name, cp, sp, C, offs = cases.small_cases()[0]
+    m, oc, _ = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *cases.RECIPE_OPTS)
+    a = oracle_mod.total_logprob_from_scratch(m, oc, cp, sp, offs, 1.0)
+    cm, ccls = oracle_mod.canonical_result(m, oc)
+    b = oracle_mod.total_logprob_from_scratch(cm, ccls, cp, sp, offs, 1.0)
+    assert abs(a - b) <= 1e-9 * abs(a)
