@@ -68,6 +68,10 @@ typedef struct {
   long long rounds, events, merges, restores, invalid_pops, solo_events;
   long long refills, flushes, splits, pairs, cuts_conflict, cuts_cascade, cuts_capacity;
   long long queue_chunks_used, pixel_chunks_used, tree_nodes_used;
+  /* SM cycles of the image's CTA: total, and by phase (select, plan, accept, commit, hot-queue update,
+   * flush, refill, split, solo merges, gc) */
+  long long cycles_total;
+  long long cycles[10];
 } mn_image_stats;
 
 /* Device time of the phases of the last batch (CUDA events on the plan's stream), milliseconds. */

@@ -57,10 +57,15 @@ class ImageStats(ctypes.Structure):
                 ("n_init_entries", ctypes.c_int)] + [(n, ctypes.c_longlong) for n in (
                     "rounds", "events", "merges", "restores", "invalid_pops", "solo_events", "refills",
                     "flushes", "splits", "pairs", "cuts_conflict", "cuts_cascade", "cuts_capacity",
-                    "queue_chunks_used", "pixel_chunks_used", "tree_nodes_used")]
+                    "queue_chunks_used", "pixel_chunks_used", "tree_nodes_used", "cycles_total")] + [
+        ("cycles", ctypes.c_longlong * 10)]
+
+    CYCLE_NAMES = ("select", "plan", "accept", "commit", "hot", "flush", "refill", "split", "solo", "gc")
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "cycles"}
+        d["cycles"] = dict(zip(self.CYCLE_NAMES, list(self.cycles)))
+        return d
 
 
 class Timings(ctypes.Structure):

@@ -187,7 +187,7 @@ static WsLayout ws_layout(int H, int W, int C, int K) {
   L.qc_cap = (int)(E / MN_QCH + 65536 + MN_NROOTS);
   L.tn_cap = MN_NROOTS + MN_TREE_FANOUT * 8192;
   L.hash_nbuckets = (uint32_t)(E * 16 / 10 / 8 + 64);
-  L.hash_ovf_cap = 4096;
+  L.hash_ovf_cap = 16384;
   L.clp = take(N * C * 4);
   L.cls = take(N * 4);
   L.obj_nc = take(N * 4);
@@ -253,17 +253,15 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
     g_last_error = MN_STATUS_BAD_ARG;
     return MN_STATUS_BAD_ARG;
   }
-  // the reference's config contract (core_config.py:66-73): no (0,0), no duplicates, no negated
-  // pairs; additionally two offsets must not alias to the same linear delta
+  // the reference's config contract (core_config.py:66-73): no (0,0), no duplicates, no negated pairs
   for (int a = 0; a < K; a++) {
-    int da = offset_list[2 * a] * W + offset_list[2 * a + 1];
-    if (da == 0 || abs(offset_list[2 * a + 1]) >= W || abs(offset_list[2 * a]) >= H + 0 * 1) {
-      if (da == 0) { g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
+    int ar = offset_list[2 * a], ac = offset_list[2 * a + 1];
+    bool bad = (ar == 0 && ac == 0);
+    for (int b = 0; b < a && !bad; b++) {
+      int br = offset_list[2 * b], bc = offset_list[2 * b + 1];
+      bad = (ar == br && ac == bc) || (ar == -br && ac == -bc);
     }
-    for (int b = 0; b < a; b++) {
-      int db = offset_list[2 * b] * W + offset_list[2 * b + 1];
-      if (da == db || da == -db) { g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
-    }
+    if (bad) { g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
@@ -494,6 +492,8 @@ extern "C" int mn_plan_image_stats(mn_plan* p, int image, mn_image_stats* o) {
   o->invalid_pops = c.invalid_pops; o->solo_events = c.solo_events; o->refills = c.refills;
   o->flushes = c.flushes; o->splits = c.splits; o->pairs = c.pairs; o->cuts_conflict = c.cuts_conflict;
   o->cuts_cascade = c.cuts_cascade; o->cuts_capacity = c.cuts_capacity;
+  for (int i = 0; i < 10; i++) o->cycles[i] = c.cyc[i];
+  o->cycles_total = c.cycles_total;
   o->queue_chunks_used = c.qc_bump; o->pixel_chunks_used = c.plc_bump; o->tree_nodes_used = c.tn_bump;
   return MN_STATUS_OK;
 }

@@ -103,6 +103,7 @@ struct MnCtl {
   long long rounds, events, merges, restores, invalid_pops, solo_events;
   long long refills, flushes, splits, pairs, cuts_conflict, cuts_cascade, cuts_capacity;
   long long cycles_total;
+  long long cyc[10];   // cycle buckets (MN_CY_*)
 };
 
 struct MnImage {
@@ -198,11 +199,16 @@ MN_HD int mn_hash_find(const MnImage& im, int lo, int hi) {
   return -1;
 }
 // rec_lh[rec] must already hold (lo,hi).  Safe against concurrent inserts/erases of other keys.
+// Two-choice placement: the emptier of the two candidate buckets first.
 MN_HD void mn_hash_insert(const MnImage& im, int lo, int hi, int rec) {
   MnHashPos p = mn_hash_pos(im.hash_nbuckets, lo, hi);
   uint32_t val = (p.fp << MN_HASH_FP_SHIFT) | (uint32_t)(rec + 1);
+  uint32_t* bk1 = im.hash + (size_t)p.b1 * 8;
+  uint32_t* bk2 = im.hash + (size_t)p.b2 * 8;
+  int f1 = 0, f2 = 0;
+  for (int s = 0; s < 8; s++) { f1 += bk1[s] == 0; f2 += bk2[s] == 0; }
   for (int w = 0; w < 2; w++) {
-    uint32_t* bk = im.hash + (size_t)(w ? p.b2 : p.b1) * 8;
+    uint32_t* bk = ((w == 0) == (f1 >= f2)) ? bk1 : bk2;
     for (int s = 0; s < 8; s++) {
       if (bk[s] == 0 && MN_ATOMIC_CAS(&bk[s], 0u, val) == 0u) return;
     }

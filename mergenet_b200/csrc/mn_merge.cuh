@@ -44,6 +44,19 @@
 #define MN_REFILL_TARGET 384      // stop loading tree leaves once this many entries are staged
 #define MN_REFILL_STATIC_MIN 128  // sort-buffer slots always left for initial entries
 #define MN_NEG_INF (-3.0e38f)
+#define MN_RANK_MAX 640  // up to this many entries are ordered by brute-force ranking (no barriers)
+// cycle accounting buckets (thread 0, clock64)
+#define MN_NCYC 10
+#define MN_CY_SELECT 0   // classify + work lists
+#define MN_CY_PLAN 1
+#define MN_CY_ACCEPT 2
+#define MN_CY_COMMIT 3
+#define MN_CY_HOT 4
+#define MN_CY_FLUSH 5
+#define MN_CY_REFILL 6
+#define MN_CY_SPLIT 7
+#define MN_CY_SOLO 8
+#define MN_CY_GC 9
 
 struct MnOffsets {
   int K;
@@ -58,8 +71,11 @@ struct MnSm {
   float ins_mp[MN_IC]; int ins_lo[MN_IC]; int ins_hi[MN_IC]; int ins_rec[MN_IC];
   float ne_mp[MN_NE]; int ne_lo[MN_NE]; int ne_hi[MN_NE]; int ne_rec[MN_NE]; int ne_pos[MN_NE];
   float sb_mp[MN_SB]; int sb_lo[MN_SB]; int sb_hi[MN_SB]; int sb_rec[MN_SB];
-  unsigned long long sb_key[MN_SB];  // (node << 32 | index) for distribute()
   int sb_node[MN_SB];
+  // distribute() scratch: per entry (group << 16 | index in group); per group node / count / old tail /
+  // (old fill | directory base << 8); directory of freshly allocated chunks
+  int ds_el[MN_SB]; int ds_node[MN_SB]; int ds_cnt[MN_SB]; int ds_tail[MN_SB]; int ds_fd[MN_SB];
+  int ds_dir[MN_SB + 128];
   uint32_t root_bits[(MN_NROOTS + 31) / 32];
   uint32_t root_sum[((MN_NROOTS + 31) / 32 + 31) / 32];
   // candidates
@@ -79,9 +95,11 @@ struct MnSm {
   // scalars
   int nhot, nins, nne, ncw, npw, npr, ncand, nacc, cutpos, solo, done, tmp0, tmp1, tmp2, tmp3;
   int plcache_n, plcache_used;
+  int ds_ngroups, ds_ndir;  // distribute() counters
   int cold_empty;  // 1: nothing outside `hot` -> every new entry goes to hot
   float b_mp; int b_lo; int b_hi;  // bound: entries popping strictly after it are cold
   int path[20]; int path_n;
+  long long cyc[MN_NCYC]; long long cyc_t0;
   long long st_rounds, st_events, st_merges, st_restores, st_invalid, st_solo, st_refills,
       st_flushes, st_splits, st_pairs, st_cut_conf, st_cut_casc, st_cut_cap;
 };
@@ -101,6 +119,13 @@ struct MnMergeArgs {
 #define MN_CLZ(x) __clz((int)(x))
 #else
 #define MN_CLZ(x) __builtin_clz((unsigned)(x))
+#endif
+#if defined(__CUDA_ARCH__)
+#define MN_TIC() do { if (MN_T0) sm.cyc_t0 = clock64(); } while (0)
+#define MN_TOC(k) do { if (MN_T0) { long long t__ = clock64(); sm.cyc[k] += t__ - sm.cyc_t0; sm.cyc_t0 = t__; } } while (0)
+#else
+#define MN_TIC() ((void)0)
+#define MN_TOC(k) ((void)0)
 #endif
 #define MN_FOR(i, n) for (int i = MN_TID; i < (n); i += MN_NT)
 #define MN_T0 (MN_TID == 0)
@@ -126,21 +151,6 @@ MN_D void mn_sort_sb(MnSm& sm, int n2) {  // n2 = power of two, pads carry mp = 
             int u = sm.sb_lo[i]; sm.sb_lo[i] = sm.sb_lo[l]; sm.sb_lo[l] = u;
             u = sm.sb_hi[i]; sm.sb_hi[i] = sm.sb_hi[l]; sm.sb_hi[l] = u;
             u = sm.sb_rec[i]; sm.sb_rec[i] = sm.sb_rec[l]; sm.sb_rec[l] = u;
-          }
-        }
-      }
-      MN_SYNC();
-    }
-}
-MN_D void mn_sort_keys(unsigned long long* a, int n2) {  // ascending
-  for (int k = 2; k <= n2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      MN_FOR(i, n2) {
-        int l = i ^ j;
-        if (l > i) {
-          bool up = ((i & k) == 0);
-          if (up ? (a[l] < a[i]) : (a[i] < a[l])) {
-            unsigned long long t = a[i]; a[i] = a[l]; a[l] = t;
           }
         }
       }
@@ -192,40 +202,68 @@ MN_D void mn_qc_free(const MnImage& im, int c) {  // called only from phases tha
   im.qc_free[t] = c;
 }
 
+// conflict-table helpers are also used as a small node -> group hash by distribute()
+MN_D int mn_ct_slot(MnSm& sm, int obj);
+MN_D int mn_ct_find(const MnSm& sm, int obj);
+
 // Append the n entries staged in sm.sb_* (sb_node[i] = destination leaf) to their leaves.
-// One thread per destination group appends sequentially; groups run in parallel.
+// No sorting: entries are grouped by destination through a shared-memory hash, one thread per
+// group reserves the space (linking fresh chunks), then every entry writes itself.
 MN_D void mn_distribute(const MnImage& im, MnSm& sm, int n) {
   if (n <= 0) return;
-  int n2 = mn_pow2_ge(n);
-  MN_FOR(i, n2) sm.sb_key[i] = i < n ? (((unsigned long long)(uint32_t)sm.sb_node[i] << 32) | (uint32_t)i) : ~0ull;
+  MN_FOR(i, MN_CT) { sm.ct_obj[i] = -1; sm.ct_w[i] = -1; }
+  if (MN_T0) { sm.ds_ngroups = 0; sm.ds_ndir = 0; }
   MN_SYNC();
-  mn_sort_keys(sm.sb_key, n2);
-  MN_FOR(i, n) {
-    int node = (int)(sm.sb_key[i] >> 32);
-    if (i == 0 || (int)(sm.sb_key[i - 1] >> 32) != node) {
-      int tail = im.tn_tail[node];
-      int fill = tail >= 0 ? im.qc_cnt[tail] : MN_QCH;
-      int added = 0;
-      for (int q = i; q < n && (int)(sm.sb_key[q] >> 32) == node; q++) {
-        int src = (int)(sm.sb_key[q] & 0xffffffffu);
-        if (fill == MN_QCH) {
-          int c = mn_qc_alloc(im);
-          if (c < 0) break;
-          im.qc_next[c] = -1;
-          im.qc_cnt[c] = 0;
-          if (tail >= 0) { im.qc_cnt[tail] = fill; im.qc_next[tail] = c; }
-          else im.tn_head[node] = c;
-          tail = c;
-          fill = 0;
-        }
-        im.q_ent[(size_t)tail * MN_QCH + fill] = make_uint4(mn_f2u(sm.sb_mp[src]), (uint32_t)sm.sb_rec[src], (uint32_t)sm.sb_lo[src], (uint32_t)sm.sb_hi[src]);
-        fill++;
-        added++;
-      }
-      if (tail >= 0) im.qc_cnt[tail] = fill;
-      im.tn_tail[node] = tail;
-      im.tn_cnt[node] += added;
+  MN_FOR(i, n) { if (mn_ct_slot(sm, sm.sb_node[i]) < 0) mn_fail(im, MN_ERR_INTERNAL); }
+  MN_SYNC();
+  MN_FOR(s, MN_CT) {
+    if (sm.ct_obj[s] != -1) {
+      int g = MN_ATOMIC_ADD(&sm.ds_ngroups, 1);
+      sm.ct_w[s] = g; sm.ds_node[g] = sm.ct_obj[s]; sm.ds_cnt[g] = 0;
     }
+  }
+  MN_SYNC();
+  MN_FOR(i, n) {
+    int s = mn_ct_find(sm, sm.sb_node[i]);
+    int g = s >= 0 ? sm.ct_w[s] : 0;
+    int local = MN_ATOMIC_ADD(&sm.ds_cnt[g], 1);
+    sm.ds_el[i] = (g << 16) | local;
+  }
+  MN_SYNC();
+  const int ngroups = sm.ds_ngroups;
+  MN_FOR(g, ngroups) {
+    int node = sm.ds_node[g], cnt = sm.ds_cnt[g];
+    int tail = im.tn_tail[node];
+    int fill = tail >= 0 ? im.qc_cnt[tail] : MN_QCH;
+    int room = MN_QCH - fill;
+    int nnew = cnt > room ? (cnt - room + MN_QCH - 1) / MN_QCH : 0;
+    int base = nnew ? MN_ATOMIC_ADD(&sm.ds_ndir, nnew) : 0;
+    sm.ds_tail[g] = tail;
+    sm.ds_fd[g] = fill | (base << 8);
+    if (tail >= 0) im.qc_cnt[tail] = cnt > room ? MN_QCH : fill + cnt;
+    int prev = tail, left = cnt - room;
+    for (int j = 0; j < nnew; j++) {
+      int c = mn_qc_alloc(im);
+      if (base + j < MN_SB + 128) sm.ds_dir[base + j] = c;
+      if (c < 0) break;
+      im.qc_next[c] = -1;
+      im.qc_cnt[c] = left > MN_QCH ? MN_QCH : left;
+      left -= MN_QCH;
+      if (prev >= 0) im.qc_next[prev] = c; else im.tn_head[node] = c;
+      prev = c;
+    }
+    if (nnew) im.tn_tail[node] = prev;
+    im.tn_cnt[node] += cnt;
+  }
+  MN_SYNC();
+  MN_FOR(i, n) {
+    int g = sm.ds_el[i] >> 16, local = sm.ds_el[i] & 0xffff;
+    int fill = sm.ds_fd[g] & 0xff, base = sm.ds_fd[g] >> 8;
+    int pos = fill + local, chunk, slot;
+    if (pos < MN_QCH) { chunk = sm.ds_tail[g]; slot = pos; }
+    else { int q = pos - MN_QCH; chunk = sm.ds_dir[base + q / MN_QCH]; slot = q % MN_QCH; }
+    if (chunk >= 0)
+      im.q_ent[(size_t)chunk * MN_QCH + slot] = make_uint4(mn_f2u(sm.sb_mp[i]), (uint32_t)sm.sb_rec[i], (uint32_t)sm.sb_lo[i], (uint32_t)sm.sb_hi[i]);
   }
   MN_SYNC();
 }
@@ -388,7 +426,9 @@ MN_D int mn_top_leaf(const MnImage& im, MnSm& sm, int* root_out, bool allow_spli
     *root_out = root;
     if (im.tn_cnt[node] <= MN_LEAFCAP || level >= mn_max_level(root)) return node;
     if (!allow_split) return -2;  // the caller's staging buffers are in use
+    MN_TOC(MN_CY_REFILL);
     mn_split_leaf(im, sm, root, node, level);
+    MN_TOC(MN_CY_SPLIT);
     if (im.ctl->status != MN_OK) return -1;
   }
   mn_fail(im, MN_ERR_LIMIT);
@@ -406,6 +446,27 @@ MN_D void mn_decode_init(const MnImage& im, const MnMergeArgs& A, uint64_t key, 
   *lo = l; *hi = h;
   int p = d > 0 ? l : h;
   *rec = p * A.K + k;
+}
+
+// exclusive prefix sum of n 0/1 flags (all threads call it); returns the total
+MN_D int mn_exclusive_scan(MnSm& sm, const int* flags, int* out, int n) {
+  const int nt = MN_NT, t = MN_TID;
+  const int per = (n + nt - 1) / nt;
+  const int b = t * per, e = b + per < n ? b + per : n;
+  int ssum = 0;
+  for (int i = b; i < e; i++) ssum += flags[i];
+  if (t < MN_SB) sm.ds_cnt[t] = ssum;
+  MN_SYNC();
+  if (MN_T0) {
+    int acc = 0;
+    for (int k = 0; k < nt && k < MN_SB; k++) { int v = sm.ds_cnt[k]; sm.ds_cnt[k] = acc; acc += v; }
+    sm.tmp3 = acc;
+  }
+  MN_SYNC();
+  int acc = t < MN_SB ? sm.ds_cnt[t] : 0;
+  for (int i = b; i < e; i++) { out[i] = acc; acc += flags[i]; }
+  MN_SYNC();
+  return sm.tmp3;
 }
 
 // Refill the (empty) hot buffer.  Afterwards: hot holds every entry popping before-or-at `bound`.
@@ -557,32 +618,77 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
       MN_SYNC();
       return;  // nothing left anywhere (cold_empty set above)
     }
-    const int n2 = mn_pow2_ge(n);
-    MN_FOR(i, n2 - n) { sm.sb_mp[n + i] = MN_NEG_INF; sm.sb_lo[n + i] = INT_MAX; sm.sb_hi[n + i] = INT_MAX; sm.sb_rec[n + i] = -1; }
-    MN_SYNC();
-    mn_sort_sb(sm, n2);
-    // valid entries first (pads / invalid sort last); drop duplicates of the same record
-    if (MN_T0) sm.tmp0 = 0;
-    MN_SYNC();
-    MN_FOR(i, n) {
-      bool valid = sm.sb_mp[i] > MN_NEG_INF;
-      bool dup = i > 0 && sm.sb_rec[i - 1] == sm.sb_rec[i] && sm.sb_mp[i - 1] == sm.sb_mp[i] &&
-                 sm.sb_lo[i - 1] == sm.sb_lo[i] && sm.sb_hi[i - 1] == sm.sb_hi[i];
-      sm.sb_node[i] = (valid && !dup) ? 1 : 0;
-    }
-    MN_SYNC();
-    // compact in order (duplicates are rare: serial fix-up by one thread keeps the order exact)
-    if (MN_T0) {
-      int o = 0;
-      for (int i = 0; i < n; i++) {
+    if (nleaf <= MN_RANK_MAX) {
+      // ---- fast path, no barrier-heavy sort: rank the (few) leaf entries by brute force, compact the
+      //      already sorted initial entries with a scan, then merge the two runs by binary search.
+      //      Duplicates of one record stay adjacent and are dropped when they are popped. ----
+      if (MN_T0) sm.tmp0 = 0;
+      MN_SYNC();
+      MN_FOR(i, nleaf) {
+        int rk = -1;
+        if (sm.sb_mp[i] > MN_NEG_INF) {
+          rk = 0;
+          for (int q = 0; q < nleaf; q++) {
+            if (q == i || !(sm.sb_mp[q] > MN_NEG_INF)) continue;
+            bool qb = mn_before(sm.sb_mp[q], sm.sb_lo[q], sm.sb_hi[q], sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i]);
+            bool ib = mn_before(sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i], sm.sb_mp[q], sm.sb_lo[q], sm.sb_hi[q]);
+            if (qb || (!ib && q < i)) rk++;
+          }
+          MN_ATOMIC_ADD(&sm.tmp0, 1);
+        }
+        sm.ne_pos[i] = rk;
+      }
+      MN_FOR(i, ntake) sm.sb_node[i] = sm.sb_mp[nleaf + i] > MN_NEG_INF ? 1 : 0;
+      MN_SYNC();
+      const int nl = sm.tmp0;
+      MN_FOR(i, nleaf) {
+        int p = sm.ne_pos[i];
+        if (p >= 0) { sm.ne_mp[p] = sm.sb_mp[i]; sm.ne_lo[p] = sm.sb_lo[i]; sm.ne_hi[p] = sm.sb_hi[i]; sm.ne_rec[p] = sm.sb_rec[i]; }
+      }
+      const int ns = mn_exclusive_scan(sm, sm.sb_node, sm.ds_el, ntake);
+      const int cur = sm.hsel, dst = sm.hsel ^ 1;
+      MN_FOR(i, ntake) {
         if (sm.sb_node[i]) {
-          HOT_MP(o) = sm.sb_mp[i]; HOT_LO(o) = sm.sb_lo[i]; HOT_HI(o) = sm.sb_hi[i]; HOT_REC(o) = sm.sb_rec[i];
-          o++;
+          int p = sm.ds_el[i], q = nleaf + i;
+          sm.hot_mp[cur][p] = sm.sb_mp[q]; sm.hot_lo[cur][p] = sm.sb_lo[q]; sm.hot_hi[cur][p] = sm.sb_hi[q]; sm.hot_rec[cur][p] = sm.sb_rec[q];
         }
       }
-      sm.nhot = o;
+      MN_SYNC();
+      MN_FOR(i, nl) {  // leaf entry i -> i + #initial entries popping before-or-equal it
+        float mp = sm.ne_mp[i]; int lo = sm.ne_lo[i], hi = sm.ne_hi[i];
+        int a = 0, bnd = ns;
+        while (a < bnd) { int mid = (a + bnd) >> 1; if (mn_before(mp, lo, hi, sm.hot_mp[cur][mid], sm.hot_lo[cur][mid], sm.hot_hi[cur][mid])) bnd = mid; else a = mid + 1; }
+        int p = i + a;
+        sm.hot_mp[dst][p] = mp; sm.hot_lo[dst][p] = lo; sm.hot_hi[dst][p] = hi; sm.hot_rec[dst][p] = sm.ne_rec[i];
+      }
+      MN_FOR(j, ns) {  // initial entry j -> j + #leaf entries popping strictly before it
+        float mp = sm.hot_mp[cur][j]; int lo = sm.hot_lo[cur][j], hi = sm.hot_hi[cur][j];
+        int a = 0, bnd = nl;
+        while (a < bnd) { int mid = (a + bnd) >> 1; if (mn_before(sm.ne_mp[mid], sm.ne_lo[mid], sm.ne_hi[mid], mp, lo, hi)) a = mid + 1; else bnd = mid; }
+        int p = j + a;
+        sm.hot_mp[dst][p] = mp; sm.hot_lo[dst][p] = lo; sm.hot_hi[dst][p] = hi; sm.hot_rec[dst][p] = sm.hot_rec[cur][j];
+      }
+      MN_SYNC();
+      if (MN_T0) { sm.hsel = dst; sm.nhot = nl + ns; }
+      MN_SYNC();
+    } else {
+      const int n2 = mn_pow2_ge(n);
+      MN_FOR(i, n2 - n) { sm.sb_mp[n + i] = MN_NEG_INF; sm.sb_lo[n + i] = INT_MAX; sm.sb_hi[n + i] = INT_MAX; sm.sb_rec[n + i] = -1; }
+      MN_SYNC();
+      mn_sort_sb(sm, n2);
+      // valid entries first (pads / invalid sort last); they are a prefix after the sort
+      if (MN_T0) sm.tmp0 = 0;
+      MN_SYNC();
+      MN_FOR(i, n) {
+        if (sm.sb_mp[i] > MN_NEG_INF) {
+          MN_ATOMIC_ADD(&sm.tmp0, 1);
+          HOT_MP(i) = sm.sb_mp[i]; HOT_LO(i) = sm.sb_lo[i]; HOT_HI(i) = sm.sb_hi[i]; HOT_REC(i) = sm.sb_rec[i];
+        }
+      }
+      MN_SYNC();
+      if (MN_T0) sm.nhot = sm.tmp0;
+      MN_SYNC();
     }
-    MN_SYNC();
     if (sm.nhot > 0 || sm.cold_empty) return;
     // everything loaded was invalid: lower the bound again
   }
@@ -778,7 +884,7 @@ MN_D void mn_hot_update(const MnImage& im, MnSm& sm, int cut) {
   const int nh = sm.nhot - cut;
   if (m == 0 && cut == 0) return;
   if (m > 0) {
-    if (m <= 96) {  // rank by brute force
+    if (m <= MN_RANK_MAX) {  // rank by brute force
       MN_FOR(i, m) {
         int rk = 0;
         for (int q = 0; q < m; q++) {
@@ -1006,6 +1112,8 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     sm.b_mp = 0; sm.b_lo = 0; sm.b_hi = 0; sm.path_n = 0;
     sm.st_rounds = sm.st_events = sm.st_merges = sm.st_restores = sm.st_invalid = sm.st_solo = 0;
     sm.st_refills = sm.st_flushes = sm.st_splits = sm.st_pairs = sm.st_cut_conf = sm.st_cut_casc = sm.st_cut_cap = 0;
+    for (int i = 0; i < MN_NCYC; i++) sm.cyc[i] = 0;
+    sm.cyc_t0 = 0;
     // number of real (non-sentinel) initial entries: first index whose key is the sentinel
     long long E = (long long)A.N * A.K;
     long long a = 0, b = E;
@@ -1021,9 +1129,11 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     MN_SYNC();
     if (im.ctl->status != MN_OK) break;
     if (A.max_rounds > 0 && round >= A.max_rounds) { if (MN_T0) mn_fail(im, MN_ERR_LIMIT); break; }
-    if (sm.nins > MN_IC - MN_NE - 64) mn_flush_ins(im, sm);
+    MN_TIC();
+    if (sm.nins > MN_IC - MN_NE - 64) { mn_flush_ins(im, sm); MN_TOC(MN_CY_FLUSH); }
     if (sm.nhot == 0) {
       mn_refill(im, sm, A);
+      MN_TOC(MN_CY_REFILL);
       if (im.ctl->status != MN_OK) break;
       if (sm.nhot == 0) break;  // queue empty: cc:542
     }
@@ -1046,7 +1156,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
       sm.ncand = n; sm.solo = solo; sm.tmp0 = f; sm.ncw = 0; sm.npw = 0; sm.npr = 0;
     }
     MN_SYNC();
-    if (sm.solo) { mn_solo_merge(im, sm, A, c_clp, sm.tmp0); if (MN_T0) sm.st_rounds++; continue; }
+    if (sm.solo) { mn_solo_merge(im, sm, A, c_clp, sm.tmp0); if (MN_T0) sm.st_rounds++; MN_TOC(MN_CY_SOLO); continue; }
     MN_FOR(j, sm.ncand) {
       if (sm.c_kind[j] == 2) {
         int p = MN_ATOMIC_ADD(&sm.npw, 1);
@@ -1090,7 +1200,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
       sm.ncand = n; sm.npr = tot; sm.solo = solo;
     }
     MN_SYNC();
-    if (sm.solo) { mn_solo_merge(im, sm, A, c_clp, sm.tmp0); if (MN_T0) sm.st_rounds++; continue; }
+    if (sm.solo) { mn_solo_merge(im, sm, A, c_clp, sm.tmp0); if (MN_T0) sm.st_rounds++; MN_TOC(MN_CY_SOLO); continue; }
     const int ncand = sm.ncand, npr = sm.npr;
     // ---- phase 4: pair lists + staged class vectors ----
     {
@@ -1110,9 +1220,11 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     }
     mn_stage_clp(im, sm, A, c_clp, 0, ncand);
     MN_SYNC();
+    MN_TOC(MN_CY_SELECT);
     // ---- phase 5: plan ----
     mn_plan_pairs(im, sm, A, c_clp, 0, npr);
     MN_SYNC();
+    MN_TOC(MN_CY_PLAN);
     // ---- phase 6: footprints into the conflict table ----
     MN_FOR(j, ncand) {
       if (sm.c_kind[j] == 0) continue;
@@ -1161,6 +1273,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
 #ifdef MN_EMUL_TRACE
     fprintf(stderr, "round: ncand %d nacc %d cut %d nhot %d nins %d npr %d cold_empty %d key0 %.9g\n", ncand, sm.nacc, sm.cutpos, sm.nhot, sm.nins, npr, sm.cold_empty, sm.c_key[0]);
 #endif
+    MN_TOC(MN_CY_ACCEPT);
     // ---- phase 8: commit ----
     MN_FOR(j, ncand) {
       if (!sm.c_accept[j]) continue;
@@ -1180,8 +1293,10 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     }
     mn_commit_pairs(im, sm, A, 0, npr);
     MN_SYNC();
+    MN_TOC(MN_CY_COMMIT);
     // ---- phase 9: queue maintenance ----
     mn_hot_update(im, sm, sm.cutpos);
+    MN_TOC(MN_CY_HOT);
   }
   MN_SYNC();
   if (MN_T0) {
@@ -1190,6 +1305,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     c->invalid_pops = sm.st_invalid; c->solo_events = sm.st_solo; c->refills = sm.st_refills;
     c->flushes = sm.st_flushes; c->splits = sm.st_splits; c->pairs = sm.st_pairs;
     c->cuts_conflict = sm.st_cut_conf; c->cuts_cascade = sm.st_cut_casc; c->cuts_capacity = sm.st_cut_cap;
+    for (int i = 0; i < MN_NCYC; i++) c->cyc[i] = sm.cyc[i];
   }
   MN_SYNC();
 }
