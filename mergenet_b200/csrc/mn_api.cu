@@ -185,7 +185,7 @@ static WsLayout ws_layout(int H, int W, int C, int K) {
   // queue entry pool: 16-byte entries in chunks of MN_QCH; it aliases rec_same+rec_diff (8*E bytes)
   // and extends past them: one chunk per live tree leaf plus the pending entries themselves.
   L.qc_cap = (int)(E / MN_QCH + 65536 + MN_NROOTS);
-  L.tn_cap = MN_NROOTS + MN_TREE_FANOUT * 8192;
+  L.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)std::max<size_t>(8192, E / 256);
   L.hash_nbuckets = (uint32_t)(E * 16 / 10 / 8 + 64);
   L.hash_ovf_cap = 16384;
   L.clp = take(N * C * 4);
