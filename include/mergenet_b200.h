@@ -67,7 +67,9 @@ typedef struct {
   int n_init_entries;
   long long rounds, events, merges, restores, invalid_pops, solo_events;
   long long refills, flushes, splits, pairs, cuts_conflict, cuts_cascade, cuts_capacity;
-  long long queue_chunks_used, pixel_chunks_used, tree_nodes_used;
+  long long queue_chunks_used, pixel_pool_used, tree_nodes_used;
+  long long requeues; /* guard entries replaced by an exact entry (lazy queue) */
+  long long hash_overflow; /* records living in the hash overflow area */
   /* SM cycles of the image's CTA: total, and by phase (select, plan, accept, commit, hot-queue update,
    * flush, refill, split, solo merges, gc) */
   long long cycles_total;

@@ -80,9 +80,7 @@ __global__ void mn_reset_kernel(const MnImage* imgs, int nimg) {
     const long long nth = (long long)gridDim.x * blockDim.x;
     const long long nh = (long long)im.hash_nbuckets * 8;
     for (long long i = tid; i < nh; i += nth) im.hash[i] = 0;
-    for (long long i = tid; i < im.tn_cap; i += nth) {
-      im.tn_head[i] = -1; im.tn_tail[i] = -1; im.tn_cnt[i] = 0; im.tn_child[i] = -1;
-    }
+    for (long long i = tid; i < im.tn_cap; i += nth) im.tn[i] = make_int4(-1, -1, 0, -1);
     if (tid == 0) {
       MnCtl z;
       memset(&z, 0, sizeof(z));
@@ -97,7 +95,7 @@ __global__ void mn_label_flags_kernel(const MnImage* imgs, int nimg, int N) {
   for (int b = blockIdx.y; b < nimg; b += gridDim.y) {
     const MnImage im = imgs[b];
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x)
-      im.cls[p] = (im.parent[p] == p && mn_nc_cls(im.obj_nc[p]) != 0) ? 1 : 0;
+      im.cls[p] = (im.parent[p] == p && mn_nc_cls(im.obj[p].x) != 0) ? 1 : 0;
   }
 }
 // mask / object_class (cc:491-517); labels ascend with the surviving object's id
@@ -106,7 +104,7 @@ __global__ void mn_label_write_kernel(const MnImage* imgs, int nimg, int N, int*
   for (int b = blockIdx.y; b < nimg; b += gridDim.y) {
     const MnImage im = imgs[b];
     const int* flags = im.cls;
-    const int* excl = im.pl_head;  // exclusive scan of flags (the pixel lists are dead by now)
+    const int* excl = (const int*)im.live_mask;  // exclusive scan of flags (the live masks are dead by now)
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
       int r = p;
       for (int g = 0; g < (1 << 26); g++) {
@@ -116,7 +114,7 @@ __global__ void mn_label_write_kernel(const MnImage* imgs, int nimg, int N, int*
       }
       int lab = flags[r] ? excl[r] + 1 : 0;
       d_mask[(size_t)b * N + p] = lab;
-      if (r == p && flags[p]) d_object_class[(size_t)b * N + excl[p]] = mn_nc_cls(im.obj_nc[p]);
+      if (r == p && flags[p]) d_object_class[(size_t)b * N + excl[p]] = mn_nc_cls(im.obj[p].x);
       if (p == N - 1) {
         int n = excl[N - 1] + flags[N - 1];
         d_ninst[b] = n;
@@ -163,7 +161,7 @@ struct mn_plan {
   cudaStream_t stream;
   cudaEvent_t ev[8];
   int num_sms;
-  int edge_tp, edge_smem, merge_smem;
+  int edge_tp, edge_smem, merge_smem, merge_H;
   std::vector<MnCtl> h_ctl;
   mn_timings timings;
 };
@@ -171,9 +169,9 @@ struct mn_plan {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t clp, cls, obj_nc, obj_same, parent, live_mask, pl_head, pl_tail, plc_next, plc_cnt, plc_pix,
-      plc_free, rec_lh, rec_val, rec_sd, hash, hash_ovf, init_keys, qc_next, qc_cnt, qc_free, tn, ctl, total;
-  int plc_cap, qc_cap, tn_cap;
+  size_t clp, cls, obj, parent, live_mask, pix_pool, rec_lh, rec_val, rec_same, rec_diff, hash, hash_ovf,
+      init_keys, qc_next, qc_free, tn, tn_dir, ctl, total;
+  int pix_cap, qc_cap, tn_cap;
   uint32_t hash_nbuckets, hash_ovf_cap;
 };
 static WsLayout ws_layout(int H, int W, int C, int K) {
@@ -181,35 +179,30 @@ static WsLayout ws_layout(int H, int W, int C, int K) {
   const size_t N = (size_t)H * W, E = N * K;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
-  L.plc_cap = (int)(N / 2 + 4096);
-  // queue entry pool: 16-byte entries in chunks of MN_QCH; it aliases rec_same+rec_diff (8*E bytes)
-  // and extends past them: one chunk per live tree leaf plus the pending entries themselves.
-  L.qc_cap = (int)(E / MN_QCH + 65536 + MN_NROOTS);
-  L.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)std::max<size_t>(8192, E / 256);
-  L.hash_nbuckets = (uint32_t)(E * 16 / 10 / 8 + 64);
+  L.pix_cap = (int)(16 * N + 4096);
+  // queue entry pool: 16-byte entries in chunks of MN_QCH; it aliases rec_same (4*E bytes, dead after
+  // record init) and extends past it: one chunk per live tree leaf plus the pending entries.
+  L.qc_cap = (int)(E * 3 / 4 / MN_QCH + 4 * MN_NROOTS + 4096);  // measured peak: 0.6 E entries
+  L.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)std::max<size_t>(2048, E / 1024);
+  L.hash_nbuckets = (uint32_t)(E * 18 / 10 / 8 + 64);
   L.hash_ovf_cap = 16384;
   L.clp = take(N * C * 4);
   L.cls = take(N * 4);
-  L.obj_nc = take(N * 4);
-  L.obj_same = take(N * 4);
+  L.obj = take(N * 16);
   L.parent = take(N * 4);
   L.live_mask = take(N * 4);
-  L.pl_head = take(N * 4);
-  L.pl_tail = take(N * 4);
-  L.plc_next = take((size_t)L.plc_cap * 4);
-  L.plc_cnt = take((size_t)L.plc_cap * 4);
-  L.plc_pix = take((size_t)L.plc_cap * MN_PLC * 4);
-  L.plc_free = take((size_t)L.plc_cap * 4);
+  L.pix_pool = take((size_t)L.pix_cap * 4);
   L.rec_lh = take(E * 8);
   L.rec_val = take(E * 16);
-  L.rec_sd = take(std::max(E * 8, (size_t)L.qc_cap * MN_QCH * 16));  // rec_same|rec_diff, then q_ent
+  L.rec_diff = take(E * 4);
+  L.rec_same = take(std::max(E * 4, (size_t)L.qc_cap * MN_QCH * 16));  // rec_same, then q_ent
   L.hash = take((size_t)L.hash_nbuckets * 8 * 4);
   L.hash_ovf = take((size_t)L.hash_ovf_cap * 4);
   L.init_keys = take(E * 8);
   L.qc_next = take((size_t)L.qc_cap * 4);
-  L.qc_cnt = take((size_t)L.qc_cap * 4);
   L.qc_free = take((size_t)L.qc_cap * 4);
-  L.tn = take((size_t)L.tn_cap * 4 * 4);
+  L.tn = take((size_t)L.tn_cap * 16);
+  L.tn_dir = take((size_t)L.tn_cap * 8 * 4);
   L.ctl = take(sizeof(MnCtl));
   L.total = o;
   return L;
@@ -302,21 +295,18 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
     MnImage im;
     memset(&im, 0, sizeof(im));
     im.clp = (float*)(base + L.clp); im.cls = (int*)(base + L.cls);
-    im.obj_nc = (uint32_t*)(base + L.obj_nc); im.obj_same = (float*)(base + L.obj_same);
+    im.obj = (uint4*)(base + L.obj);
     im.parent = (int*)(base + L.parent); im.live_mask = (uint32_t*)(base + L.live_mask);
-    im.pl_head = (int*)(base + L.pl_head); im.pl_tail = (int*)(base + L.pl_tail);
-    im.plc_next = (int*)(base + L.plc_next); im.plc_cnt = (int*)(base + L.plc_cnt);
-    im.plc_pix = (int*)(base + L.plc_pix); im.plc_free = (int*)(base + L.plc_free);
+    im.pix_pool = (int*)(base + L.pix_pool);
     im.rec_lh = (int2*)(base + L.rec_lh); im.rec_val = (float4*)(base + L.rec_val);
-    im.rec_same = (float*)(base + L.rec_sd); im.rec_diff = im.rec_same + p->E;
+    im.rec_same = (float*)(base + L.rec_same); im.rec_diff = (float*)(base + L.rec_diff);
     im.hash = (uint32_t*)(base + L.hash); im.hash_ovf = (uint32_t*)(base + L.hash_ovf);
     im.hash_nbuckets = L.hash_nbuckets; im.hash_ovf_cap = L.hash_ovf_cap;
     im.init_keys = (uint64_t*)(base + L.init_keys);
-    im.q_ent = (uint4*)(base + L.rec_sd);
-    im.qc_next = (int*)(base + L.qc_next); im.qc_cnt = (int*)(base + L.qc_cnt); im.qc_free = (int*)(base + L.qc_free);
-    im.tn_head = (int*)(base + L.tn); im.tn_tail = im.tn_head + L.tn_cap; im.tn_cnt = im.tn_tail + L.tn_cap;
-    im.tn_child = im.tn_cnt + L.tn_cap;
-    im.plc_cap = L.plc_cap; im.qc_cap = L.qc_cap; im.tn_cap = L.tn_cap;
+    im.q_ent = (uint4*)(base + L.rec_same);
+    im.qc_next = (int*)(base + L.qc_next); im.qc_free = (int*)(base + L.qc_free);
+    im.tn = (int4*)(base + L.tn); im.tn_dir = (int*)(base + L.tn_dir);
+    im.pix_cap = L.pix_cap; im.qc_cap = L.qc_cap; im.tn_cap = L.tn_cap;
     im.out_mask = nullptr; im.out_cls = nullptr;
     im.ctl = (MnCtl*)(base + L.ctl);
     p->h_imgs[b] = im;
@@ -333,7 +323,16 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
   for (int i = 0; i < 8; i++)
     if (cudaEventCreate(&p->ev[i]) != cudaSuccess) return fail(MN_STATUS_CUDA);
   p->edge_tp = choose_edge_tile(C, K, &p->edge_smem);
-  p->merge_smem = (int)(((sizeof(MnSm) + 15) / 16) * 16 + (size_t)MN_H * C * 4);
+  {
+    // window: as many candidates as the staged class vectors (3 per candidate) leave room for
+    const size_t base = ((sizeof(MnSm) + 15) / 16) * 16;
+    const size_t limit = (size_t)prop.sharedMemPerBlockOptin;
+    int Hwin = MN_H;
+    while (Hwin > 1 && base + (size_t)Hwin * 3 * C * 4 > limit) Hwin--;
+    p->merge_H = Hwin;
+    p->merge_smem = (int)(base + (size_t)Hwin * 3 * C * 4);
+    if ((size_t)p->merge_smem > limit) return fail(MN_STATUS_BAD_ARG);
+  }
   if (cudaFuncSetAttribute(mn_edge_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->edge_smem) != cudaSuccess ||
       cudaFuncSetAttribute(mn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->merge_smem) != cudaSuccess)
     return fail(MN_STATUS_CUDA);
@@ -400,7 +399,7 @@ extern "C" int mn_segment_batch_device(mn_plan* p, int B, const float* d_class, 
   if (rc) return rc;
   MnMergeArgs A;
   memset(&A, 0, sizeof(A));
-  A.C = p->C; A.K = p->K; A.N = N; A.W = p->W; A.omf = omf; A.mlb = mlb; A.off = p->off; A.max_rounds = 40ll * N + 100000;  // guard: rounds <= events, a few per pixel
+  A.C = p->C; A.K = p->K; A.N = N; A.W = p->W; A.omf = omf; A.mlb = mlb; A.off = p->off; A.H = p->merge_H; A.max_rounds = 40ll * N + 100000;  // guard: rounds <= events, a few per pixel
   int grid = std::min(B, p->num_sms);
   mn_merge_kernel<<<grid, 256, p->merge_smem, s>>>(p->d_imgs, B, A);
   p->timings.other_launches++;
@@ -411,7 +410,7 @@ extern "C" int mn_segment_batch_device(mn_plan* p, int B, const float* d_class, 
     mn_label_flags_kernel<<<g, 256, 0, s>>>(p->d_imgs, B, N);
     for (int b = 0; b < B; b++) {
       size_t tb = p->cub_temp_bytes;
-      MN_CUDA_OK(cub::DeviceScan::ExclusiveSum(p->d_cub_temp, tb, (const int*)p->h_imgs[b].cls, p->h_imgs[b].pl_head, N, s));
+      MN_CUDA_OK(cub::DeviceScan::ExclusiveSum(p->d_cub_temp, tb, (const int*)p->h_imgs[b].cls, (int*)p->h_imgs[b].live_mask, N, s));
     }
     MN_CUDA_OK(cudaMemsetAsync(d_object_class, 0xFF, (size_t)B * N * 4, s));
     mn_label_write_kernel<<<g, 256, 0, s>>>(p->d_imgs, B, N, d_mask, d_object_class, d_ninst);
@@ -494,7 +493,8 @@ extern "C" int mn_plan_image_stats(mn_plan* p, int image, mn_image_stats* o) {
   o->cuts_cascade = c.cuts_cascade; o->cuts_capacity = c.cuts_capacity;
   for (int i = 0; i < 10; i++) o->cycles[i] = c.cyc[i];
   o->cycles_total = c.cycles_total;
-  o->queue_chunks_used = c.qc_bump; o->pixel_chunks_used = c.plc_bump; o->tree_nodes_used = c.tn_bump;
+  o->queue_chunks_used = c.qc_bump; o->pixel_pool_used = c.pix_bump; o->tree_nodes_used = c.tn_bump;
+  o->requeues = c.requeues; o->hash_overflow = c.hash_ovf_n;
   return MN_STATUS_OK;
 }
 extern "C" int mn_plan_timings(mn_plan* p, mn_timings* o) {
@@ -561,17 +561,19 @@ extern "C" int mn_debug_edge_dump(int H, int W, int C, int K, const int* offset_
   if (rc) return done(rc);
   std::vector<int2> lh(E);
   std::vector<float4> val(E);
+  std::vector<float> dif(E);
   const MnImage& im = p->h_imgs[0];
   cudaMemcpyAsync(clp, im.clp, N * C * 4, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(cls, im.cls, N * 4, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(lh.data(), im.rec_lh, E * 8, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(val.data(), im.rec_val, E * 16, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(dif.data(), im.rec_diff, E * 4, cudaMemcpyDeviceToHost, s);
   if (sdb != 0.0f) cudaMemcpyAsync(h_adj, p->d_in_adj, (size_t)K * N * 4, cudaMemcpyDeviceToHost, s);
   if (cudaStreamSynchronize(s) != cudaSuccess) return done(MN_STATUS_CUDA);
   for (size_t r = 0; r < E; r++) {
     lo[r] = lh[r].x; hi[r] = lh[r].y;
     bool v = lh[r].x >= 0;
-    oml[r] = v ? val[r].x : 0.f; same[r] = v ? val[r].y : 0.f; diff[r] = v ? val[r].z : 0.f; mp[r] = v ? val[r].w : 0.f;
+    oml[r] = v ? val[r].x : 0.f; same[r] = v ? val[r].y : 0.f; diff[r] = v ? dif[r] : 0.f; mp[r] = v ? val[r].w : 0.f;
   }
   return done(MN_STATUS_OK);
 }

@@ -75,11 +75,43 @@ __device__ __forceinline__ void mn_fence_proxy_async() {
 // diff = (float)log(1.0 - (double)s)   (cc:34).  1.0 - s is exact in fp64 for s >= 2^-23.
 __device__ __forceinline__ float mn_log1m_exact(float s) { return (float)log(1.0 - (double)s); }
 
+// glibc-exact expf for |x| < 88 (no overflow / underflow handling: the biased logit of a clipped
+// probability is far inside): the public glibc / ARM optimized-routines algorithm (N = 32 table,
+// degree-3 polynomial, all in fp64).  The x86-64 libm selects its FMA build, so the three
+// polynomial steps are fused exactly as that build fuses them; with separate multiply-adds 2 of the
+// 1.78e9 inputs in [-80, 80] differ.  Pinned to the host libm by tests/test_libm_parity.py.
+__constant__ unsigned long long mn_exp2f_tab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+__device__ __forceinline__ float mn_expf_exact(float x) {
+  const double InvLn2N = 0x1.71547652b82fep+0 * 32.0, SHIFT = 0x1.8p+52;
+  const double C0 = 0x1.c6af84b912394p-5 / 32768.0, C1 = 0x1.ebfce50fac4f3p-3 / 1024.0, C2 = 0x1.62e42ff0c52d6p-1 / 32.0;
+  double z = __dmul_rn(InvLn2N, (double)x);
+  double kd = __dadd_rn(z, SHIFT);
+  unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+  kd = __dadd_rn(kd, -SHIFT);
+  double r = __dadd_rn(z, -kd);
+  unsigned long long t = mn_exp2f_tab[ki & 31ull] + (ki << 47);
+  double s = __longlong_as_double((long long)t);
+  z = __fma_rn(C0, r, C1);
+  double r2 = __dmul_rn(r, r);
+  double y = __fma_rn(C2, r, 1.0);
+  y = __fma_rn(z, r2, y);
+  y = __dmul_rn(y, s);
+  return (float)y;
+}
+
 // same_different_bias transform (cc:183-195), evaluated like the reference: logf + fp64 log,
 // rounded to float, expf, then 1/(1+e) in fp64 rounded to float.
 __device__ __forceinline__ float mn_bias_sameness(float s, float sdb, const MnLogfTab* tab) {
   float logit = (float)(((double)mn_logf_exact(s, tab) - log(1.0 - (double)s)) + (double)sdb);
-  return (float)(1.0 / (1.0 + (double)expf(-logit)));
+  return (float)(1.0 / (1.0 + (double)mn_expf_exact(-logit)));
 }
 
 struct MnEdgeParams {
@@ -261,10 +293,7 @@ __global__ void __launch_bounds__(256) mn_record_init_kernel(MnRecInitParams P) 
       }
       im.live_mask[p] = m;
       im.parent[p] = p;
-      im.obj_nc[p] = mn_pack_nc(1, im.cls[p]);
-      im.obj_same[p] = 0.0f;
-      im.pl_head[p] = -1;
-      im.pl_tail[p] = -1;
+      im.obj[p] = make_uint4(mn_pack_nc(1, im.cls[p]), 0u /* sameness sum 0.0f */, 0xffffffffu /* no pixel array */, 0u);
     }
     const int r2 = row + P.off_r[k], c2 = col + P.off_c[k];
     uint64_t key = ~0ull;
@@ -277,7 +306,7 @@ __global__ void __launch_bounds__(256) mn_record_init_kernel(MnRecInitParams P) 
       const float mp = mn_priority(oml, P.omf, P.mlb, P.C, 1, cl, im.clp + (size_t)lo * P.C, 1, ch,
                                    im.clp + (size_t)hi * P.C, nullptr);  // cc:45
       im.rec_lh[r] = make_int2(lo, hi);
-      im.rec_val[r] = make_float4(oml, same, diff, mp);
+      im.rec_val[r] = make_float4(oml, same, mp >= 0.0f ? mp : -1.0f, mp);  // rec_diff[r] already holds diff
       mn_hash_insert(im, lo, hi, r);
       if (mp >= 0.0f) {  // cc:225-227
         uint32_t ord = (uint32_t)lo * (uint32_t)P.K + (uint32_t)P.rank_of_k[k];
@@ -285,7 +314,7 @@ __global__ void __launch_bounds__(256) mn_record_init_kernel(MnRecInitParams P) 
       }
     } else {
       im.rec_lh[r] = make_int2(-1, -1);
-      im.rec_val[r] = make_float4(0.f, 0.f, 0.f, -1.0f);
+      im.rec_val[r] = make_float4(0.f, 0.f, -1.0f, -1.0f);
     }
     P.keys_out[r] = key;
   }

@@ -2,8 +2,9 @@
 // primitives every kernel shares (packed object word, (lo,hi)->record hash, SPMD/atomic shims).
 //
 // HBM layout per image (N = H*W pixels, E = N*K record slots, slot r = pixel*K + k):
-//   objects   clp[N*C] f32 | obj_nc[N] (npix | cls<<24) | obj_same[N] f32 | parent[N] | live_mask[N]
-//             | pl_head[N] pl_tail[N] + pixel-list chunk pool           (Object, h:85-137)
+//   objects   clp[N*C] f32 | obj[N] uint4 (npix | cls<<24, sameness sum, pixel-array offset, -) |
+//             parent[N] | live_mask[N] | pix_pool: one contiguous pixel array per multi-pixel
+//             object, capacity = next power of two >= npix (>= 4)          (Object, h:85-137)
 //   records   rec_lh[E] int2 (lo,hi; lo=-1 = dead) | rec_val[E] float4 (oml,same,diff,mp)
 //             (AdjacencyRecord, h:175-232)
 //   hash      2-choice, 8-slot buckets of u32 (fingerprint<<26 | rec+1): (lo,hi) -> record
@@ -24,6 +25,8 @@ struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r = {x, y, z, w}; return r; }
 struct float4 { float x, y, z, w; };
+struct int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { int4 r = {x, y, z, w}; return r; }
 static inline int2 make_int2(int x, int y) { int2 r = {x, y}; return r; }
 static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r = {x, y}; return r; }
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
@@ -64,13 +67,12 @@ template <typename T> static inline T mn_h_cas(T* p, T c, T v) { T o = *p; if (o
 #endif
 
 #define MN_ORD_BITS 25       // initial-entry tie-break ordinal lo*K + rank  (N*K <= 2^25)
-#define MN_PLC 30            // pixels per pixel-list chunk (+ next, cnt = 32 words)
-#define MN_QCH 16            // queue entries per tree chunk (16 B each)
+#define MN_QCH 64            // queue entries per tree chunk (16 B each)
 #define MN_HASH_FP_SHIFT 26  // slot = fingerprint(6) << 26 | (rec + 1)
 #define MN_TREE_FANOUT 64    // children per split (6-bit digits)
 
-// queue tree roots: one per 2^12 float-bit patterns over [MN_ROOT_LO, MN_ROOT_HI)
-#define MN_ROOT_SHIFT 12
+// queue tree roots: one per 2^15 float-bit patterns over [MN_ROOT_LO, MN_ROOT_HI)
+#define MN_ROOT_SHIFT 15
 #define MN_ROOT_LO_BITS 0x39800000u  // 2^-12
 #define MN_ROOT_HI_BITS 0x43800000u  // 2^8
 #define MN_NROOTS (((MN_ROOT_HI_BITS - MN_ROOT_LO_BITS) >> MN_ROOT_SHIFT) + 2)
@@ -78,7 +80,7 @@ template <typename T> static inline T mn_h_cas(T* p, T c, T v) { T o = *p; if (o
 enum MnStatus {
   MN_OK = 0,
   MN_ERR_BAD_ARG = 1,
-  MN_ERR_PL_POOL = 2,     // pixel-list chunk pool exhausted
+  MN_ERR_PL_POOL = 2,     // pixel-array pool exhausted
   MN_ERR_Q_POOL = 3,      // queue entry pool exhausted
   MN_ERR_TREE_POOL = 4,   // queue tree node pool exhausted
   MN_ERR_HASH_FULL = 5,   // both hash buckets full and overflow area full
@@ -92,17 +94,19 @@ struct MnCtl {
   int status;
   int n_init;          // non-sentinel entries in init_keys
   int static_cursor;
-  int plc_bump, plc_free_top;
+  int pix_bump;
   int qc_bump, qc_free_top;
   int tn_bump;
   int hash_ovf_n;
   int tree_entries;    // entries currently stored in the tree
+  int peak_entries, peak_chunks;  // high-water marks of the tree
   int n_instances;     // output: labels 1..n
   int fail_line;       // source line of the first failure (diagnostics)
   // statistics (north star: per-round latency, round count, merges/s)
   long long rounds, events, merges, restores, invalid_pops, solo_events;
   long long refills, flushes, splits, pairs, cuts_conflict, cuts_cascade, cuts_capacity;
   long long cycles_total;
+  long long requeues;
   long long cyc[10];   // cycle buckets (MN_CY_*)
 };
 
@@ -110,21 +114,15 @@ struct MnImage {
   // objects
   float* clp;
   int* cls;  // argmax class per pixel from the edge pass (consumed by record init)
-  uint32_t* obj_nc;
-  float* obj_same;
+  uint4* obj;  // x = npix | cls << 24, y = bits of the object's sameness sum (h:131), z = pixel array offset (-1: single pixel)
   int* parent;
   uint32_t* live_mask;
-  int* pl_head;
-  int* pl_tail;
-  int* plc_next;
-  int* plc_cnt;
-  int* plc_pix;
-  int* plc_free;
+  int* pix_pool;
   // records
   int2* rec_lh;
-  float4* rec_val;
+  float4* rec_val;  // (oml, sameness sum, qmp = priority of the record's earliest queued entry or -1, mp)
   float* rec_same;  // edge-pass output; dead after record init, then aliased by q_ent
-  float* rec_diff;
+  float* rec_diff;  // edge-pass output, then the record's differentness sum (h:196-199)
   // hash
   uint32_t* hash;
   uint32_t* hash_ovf;  // small linear overflow area of rec+1 values
@@ -134,13 +132,10 @@ struct MnImage {
   uint64_t* init_keys;
   uint4* q_ent;  // [qc_cap * MN_QCH] (mp bits, rec, lo, hi): validated against the record on load
   int* qc_next;
-  int* qc_cnt;
   int* qc_free;
-  int* tn_head;
-  int* tn_tail;
-  int* tn_cnt;
-  int* tn_child;
-  int plc_cap, qc_cap, tn_cap;
+  int4* tn;     // tree nodes: (first chunk, last chunk, entries below, first child)
+  int* tn_dir;  // first 8 chunk ids of every leaf
+  int pix_cap, qc_cap, tn_cap;
   // outputs
   int* out_mask;
   int* out_cls;
@@ -150,6 +145,13 @@ struct MnImage {
 MN_HD uint32_t mn_pack_nc(int npix, int cls) { return (uint32_t)npix | ((uint32_t)cls << 24); }
 MN_HD int mn_nc_npix(uint32_t nc) { return (int)(nc & 0xFFFFFFu); }
 MN_HD int mn_nc_cls(uint32_t nc) { return (int)(nc >> 24); }
+// capacity of the pixel array of an object of n pixels (0: the single pixel is the object id itself)
+MN_HD int mn_pix_cap(int n) {
+  if (n <= 1) return 0;
+  int c = 4;
+  while (c < n) c <<= 1;
+  return c;
+}
 
 // ---- (lo,hi) -> record hash ---------------------------------------------------------------------
 MN_HD uint64_t mn_mix64(uint64_t k) {

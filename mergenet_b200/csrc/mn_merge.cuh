@@ -4,23 +4,33 @@
 // the tie order among equal priorities (deterministic here: mp desc, lo asc, hi asc).
 //
 // The reference's lazy heap is observationally an indexed map  record -> stored priority  holding
-// the records with stored mp >= 0 (cc:554-565).  A ROUND takes the next MN_H valid entries in pop
+// the records with stored mp >= 0 (cc:554-565).  A ROUND takes the next MN_H queue entries in pop
 // order, PLANS each against the round-start state (read only), then COMMITS the longest prefix
 // that the sequential heap would provably execute in exactly this order with exactly these results:
 //   (a) no member reads or writes an object written by an earlier member, and writes none an
 //       earlier member read (objects written by a merge: both endpoints; read: every neighbour of
 //       the absorbed object, whose records are rewired -- cc:650-707; a non-merging pop reads its
 //       two endpoints and re-stores only its own priority -- cc:560-565);
-//   (b) no earlier member creates a queue entry that would pop before a later member.
+//   (b) no earlier member stores a priority that would pop before a later member.
 // Rule (a)+(b) was validated against the sequential restatement on the host
 // (oracle/mergenet_oracle.c: mno_run_rounds_model).  Member 0 always commits, so every round makes
 // progress.  All state of an image is private to its CTA: no inter-CTA communication.
 //
-// Queue: `hot` (shared memory, sorted) holds every entry that pops before-or-at `bound`; colder
+// A round is organised around the number of DEPENDENT global-memory round trips, not around
+// instruction count: every load a phase needs is issued by a different thread in the same phase
+// (stage: record + both objects + class vectors + hash buckets of a candidate at once; pixels ->
+// live masks; pair: record -> {neighbour object, four hash buckets} -> partner record).
+//
+// Queue.  `hot` (shared memory, sorted) holds every entry that pops before-or-at `bound`; colder
 // entries live in HBM: the sorted initial entries (init_keys, cursor) and, for entries created
-// later, a lazily split radix tree of unsorted chunks keyed by (mp bits, lo, hi).  Entries are
-// validated lazily against the record's stored (mp, lo, hi) when they are loaded and again when
-// they are popped, which is what the reference's `merge_priority != arec->GetPriority()` test does.
+// later, a lazily split radix tree of unsorted chunks keyed by (mp bits, lo, hi).  The queue is lazy
+// in two ways.  Like the reference's heap, an entry that no longer describes its record is dropped
+// when it surfaces (cc:554-559).  Unlike it, a record whose priority is re-stored LATER in pop order
+// than an entry it already has gets no new entry: rec_val.z (`qmp`) remembers the priority of the
+// record's earliest queued entry (the "guard"); when the guard surfaces and the stored priority is
+// lower, an exact entry is queued then ("requeue").  Invariant: every live record with stored
+// mp >= 0 has a queued entry popping before-or-at its true position, so no pop can be missed, and
+// the sequence of EXACT pops -- the only ones with side effects -- is the reference's.
 //
 // The file is written as SPMD phases (see mn_layout.h) and also compiles for the host, where
 // tests/emul runs it single-threaded to unit-test the logic; that build is test infrastructure.
@@ -32,7 +42,7 @@
 
 #define MN_H 32          // candidates per round
 #define MN_PW 1024       // pixel work-list capacity
-#define MN_CW 256        // pixel-chunk work-list capacity
+#define MN_CW 64         // queue-chunk work-list capacity
 #define MN_WL 960        // (candidate, record) pair work-list capacity
 #define MN_HC 1024       // hot capacity
 #define MN_IC 2048       // insert-buffer capacity
@@ -40,14 +50,14 @@
 #define MN_SB 1024       // sort buffer capacity
 #define MN_LEAFCAP 512   // tree leaves larger than this are split before they are loaded
 #define MN_CT 2048       // conflict-table slots (power of two)
-#define MN_PLCACHE 64    // pre-popped pixel-list chunks per round
+#define MN_OVF 128        // records in the hash overflow area (cached in shared memory)
 #define MN_REFILL_TARGET 384      // stop loading tree leaves once this many entries are staged
 #define MN_REFILL_STATIC_MIN 128  // sort-buffer slots always left for initial entries
 #define MN_NEG_INF (-3.0e38f)
-#define MN_RANK_MAX 640  // up to this many entries are ordered by brute-force ranking (no barriers)
+#define MN_RANK_MAX 256  // up to this many entries are ordered by brute-force ranking (no barriers)
 // cycle accounting buckets (thread 0, clock64)
 #define MN_NCYC 10
-#define MN_CY_SELECT 0   // classify + work lists
+#define MN_CY_SELECT 0   // stage + classify + work lists
 #define MN_CY_PLAN 1
 #define MN_CY_ACCEPT 2
 #define MN_CY_COMMIT 3
@@ -57,6 +67,13 @@
 #define MN_CY_SPLIT 7
 #define MN_CY_SOLO 8
 #define MN_CY_GC 9
+
+// candidate kinds
+#define MN_K_DROP 0      // stale entry: dropped when consumed
+#define MN_K_RESTORE 1   // exact pop whose recomputed priority differs: re-store (cc:563-565)
+#define MN_K_MERGE 2     // exact pop that merges (cc:561-562)
+#define MN_K_REQUEUE 3   // guard entry of a record whose stored priority is lower: queue the exact entry
+#define MN_K_UNGUARD 4   // guard entry of a dormant record (stored mp < 0): forget the guard
 
 struct MnOffsets {
   int K;
@@ -72,40 +89,60 @@ struct MnSm {
   float ne_mp[MN_NE]; int ne_lo[MN_NE]; int ne_hi[MN_NE]; int ne_rec[MN_NE]; int ne_pos[MN_NE];
   float sb_mp[MN_SB]; int sb_lo[MN_SB]; int sb_hi[MN_SB]; int sb_rec[MN_SB];
   int sb_node[MN_SB];
-  // distribute() scratch: per entry (group << 16 | index in group); per group node / count / old tail /
-  // (old fill | directory base << 8); directory of freshly allocated chunks
-  int ds_el[MN_SB]; int ds_node[MN_SB]; int ds_cnt[MN_SB]; int ds_tail[MN_SB]; int ds_fd[MN_SB];
-  int ds_dir[MN_SB + 128];
   uint32_t root_bits[(MN_NROOTS + 31) / 32];
   uint32_t root_sum[((MN_NROOTS + 31) / 32 + 31) / 32];
-  // candidates
+  int cw_chunk[MN_CW];
+  int4 scan_nd[MN_TREE_FANOUT]; int4 leaf_nd; int path_cnt[20];
+  int qc_free_top, qc_bump, tn_bump, tree_entries, static_cursor, n_init;  // mirrors of MnCtl
+  int peak_entries, peak_chunks;
+  // candidates: staged loads
   int c_rec[MN_H]; float c_key[MN_H]; int c_lo[MN_H]; int c_hi[MN_H]; int c_kind[MN_H];
-  float c_newmp[MN_H]; int c_merged[MN_H]; int c_surv[MN_H]; int c_abs[MN_H]; int c_na[MN_H];
-  float c_rsame[MN_H]; int c_npairs[MN_H]; int c_pbase[MN_H]; int c_pfill[MN_H];
-  uint32_t c_maxnew[MN_H]; int c_conflict[MN_H]; int c_npix[MN_H]; int c_accept[MN_H];
+  float4 c_val[MN_H]; int2 c_lh[MN_H]; uint4 c_obj[MN_H][2]; uint32_t c_lm[MN_H][2]; uint32_t c_hb[MN_H][16];
+  float c_rdiff[MN_H]; int c_dup[MN_H];
+  // candidates: classification
+  float c_newmp[MN_H]; int c_merged[MN_H]; int c_surv[MN_H]; int c_abs[MN_H]; int c_na[MN_H]; int c_nb[MN_H];
+  int c_ptra[MN_H]; int c_ptrb[MN_H]; int c_newptr[MN_H]; int c_cpbase[MN_H];
+  float c_same[MN_H]; int c_eslot[MN_H];
+  int c_pwbase[MN_H]; int c_npairs[MN_H]; int c_pbase[MN_H]; int c_pfill[MN_H];
+  uint32_t c_maxnew[MN_H]; int c_conflict[MN_H]; int c_accept[MN_H];
+  int m_list[MN_H]; int m_base[MN_H + 1]; int nm;      // merging candidates and their pixel ranges
+  int cp_list[MN_H]; int cp_base[MN_H + 1]; int ncp;   // accepted merges whose survivor array moves
   // work lists
-  int cw_cand[MN_CW]; int cw_chunk[MN_CW];
-  int pw_cand[MN_PW]; int pw_pix[MN_PW];
-  int pr_cand[MN_WL]; int pr_t[MN_WL]; int pr_x[MN_WL]; int pr_u[MN_WL];
-  float pr_oml[MN_WL]; float pr_same[MN_WL]; float pr_diff[MN_WL]; float pr_mp[MN_WL];
-  int pr_lo[MN_WL]; int pr_hi[MN_WL];
+  int pw_pix[MN_PW]; uint32_t pw_mask[MN_PW]; int pw_cand[MN_PW]; int pw_cnt[MN_PW]; int pw_off[MN_PW];
+  // the (candidate, record) pair plan of a round and the scratch of distribute() are never live together
+  union {
+    struct {
+      int cand[MN_WL]; int t[MN_WL]; int x[MN_WL]; int u[MN_WL];
+      float oml[MN_WL]; float same[MN_WL]; float diff[MN_WL]; float mp[MN_WL]; float q[MN_WL];
+      int lo[MN_WL]; int hi[MN_WL]; int eslot[MN_WL]; int islot[MN_WL];
+    } pr;
+    // distribute(): per entry (group << 16 | index in group); per group node / count / old tail /
+    // (old fill | directory base << 8); directory of freshly allocated chunks
+    struct {
+      int el[MN_SB]; int node[MN_SB]; int cnt[MN_SB]; int tail[MN_SB]; int fd[MN_SB];
+      int dir[MN_SB + 128];
+    } ds;
+  } w;
   // conflict table: object -> (min writer candidate, min reader candidate)
   int ct_obj[MN_CT]; int ct_w[MN_CT]; int ct_r[MN_CT];
-  int plcache[MN_PLCACHE];
   // scalars
-  int nhot, nins, nne, ncw, npw, npr, ncand, nacc, cutpos, solo, done, tmp0, tmp1, tmp2, tmp3;
-  int plcache_n, plcache_used;
+  int nhot, nins, nne, ncw, npw, npr, ncand, nacc, cutpos, solo, first, tmp0, tmp1, tmp2, tmp3;
   int ds_ngroups, ds_ndir;  // distribute() counters
+  int pix_bump;             // pixel-array pool bump pointer (mirrors MnCtl)
+  int hash_ovf_n;           // entries of the overflow cache below (tombstones included)
+  int ovf_lo[MN_OVF]; int ovf_hi[MN_OVF]; int ovf_rec[MN_OVF];  // records that fit neither hash bucket
+  int failed;               // sticky copy of ctl->status != 0
   int cold_empty;  // 1: nothing outside `hot` -> every new entry goes to hot
   float b_mp; int b_lo; int b_hi;  // bound: entries popping strictly after it are cold
   int path[20]; int path_n;
   long long cyc[MN_NCYC]; long long cyc_t0;
   long long st_rounds, st_events, st_merges, st_restores, st_invalid, st_solo, st_refills,
-      st_flushes, st_splits, st_pairs, st_cut_conf, st_cut_casc, st_cut_cap;
+      st_flushes, st_splits, st_pairs, st_cut_conf, st_cut_casc, st_cut_cap, st_requeues;
 };
 
 struct MnMergeArgs {
   int C, K, N, W;
+  int H;  // candidates per round (<= MN_H; smaller when the staged class vectors would not fit)
   float omf, mlb;
   MnOffsets off;
   long long max_rounds;  // safety guard (0 = none)
@@ -117,8 +154,10 @@ struct MnMergeArgs {
 #define HOT_REC(i) sm.hot_rec[sm.hsel][i]
 #if defined(__CUDA_ARCH__)
 #define MN_CLZ(x) __clz((int)(x))
+#define MN_POPC(x) __popc((unsigned)(x))
 #else
 #define MN_CLZ(x) __builtin_clz((unsigned)(x))
+#define MN_POPC(x) __builtin_popcount((unsigned)(x))
 #endif
 #if defined(__CUDA_ARCH__)
 #define MN_TIC() do { if (MN_T0) sm.cyc_t0 = clock64(); } while (0)
@@ -127,13 +166,18 @@ struct MnMergeArgs {
 #define MN_TIC() ((void)0)
 #define MN_TOC(k) ((void)0)
 #endif
+#if defined(MN_EMUL_WATCH)
+#define MN_WATCH(rec, ...) do { if ((rec) == MN_EMUL_WATCH) { fprintf(stderr, "W%d: ", (int)(rec)); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } } while (0)
+#else
+#define MN_WATCH(rec, ...) ((void)0)
+#endif
 #define MN_FOR(i, n) for (int i = MN_TID; i < (n); i += MN_NT)
 #define MN_T0 (MN_TID == 0)
 
 MN_D void mn_fail_at(const MnImage& im, int code, int line) {
   if (im.ctl->status == MN_OK) { im.ctl->status = code; im.ctl->fail_line = line; }
 }
-#define mn_fail(im, code) mn_fail_at((im), (code), __LINE__)
+#define mn_fail(im, code) do { mn_fail_at((im), (code), __LINE__); sm.failed = 1; } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // sorting
@@ -168,10 +212,10 @@ MN_D int mn_root_of(float mp) {
   return (int)((b - MN_ROOT_LO_BITS) >> MN_ROOT_SHIFT) + 1;
 }
 // 6-bit digit `level` (1-based, below the root) of the 80-bit pop-order key [~mpbits:32][lo:24][hi:24].
-// Regular roots fix the top 20 key bits, so their digits start at bit 20; the two open-ended roots
+// Regular roots fix the top 32 - MN_ROOT_SHIFT key bits, where their digits start; the two open-ended roots
 // start at bit 0.  Smaller digit = pops first.
 MN_D int mn_digit(int root, int level, float mp, int lo, int hi) {
-  int start = (root == 0 || root == MN_NROOTS - 1) ? 0 : 20;
+  int start = (root == 0 || root == MN_NROOTS - 1) ? 0 : 32 - MN_ROOT_SHIFT;
   int pos = start + 6 * (level - 1);  // bit offset from the top of the 80-bit key
   unsigned long long hi64 = ((unsigned long long)(~mn_f2u(mp)) << 32) | ((unsigned long long)(uint32_t)lo << 8) |
                             ((unsigned long long)(uint32_t)hi >> 16);
@@ -187,24 +231,29 @@ MN_D int mn_digit(int root, int level, float mp, int lo, int hi) {
   }
   return d;
 }
-MN_D int mn_max_level(int root) { return (root == 0 || root == MN_NROOTS - 1) ? 14 : 10; }
+MN_D int mn_max_level(int root) { return (root == 0 || root == MN_NROOTS - 1) ? 14 : (80 - (32 - MN_ROOT_SHIFT) + 5) / 6; }
 
-MN_D int mn_qc_alloc(const MnImage& im) {  // called only from phases that never free
-  int t = MN_ATOMIC_SUB(&im.ctl->qc_free_top, 1);
+MN_D int mn_qc_alloc(const MnImage& im, MnSm& sm) {  // called only from phases that never free
+  int t = MN_ATOMIC_SUB(&sm.qc_free_top, 1);
   if (t > 0) return im.qc_free[t - 1];
-  MN_ATOMIC_ADD(&im.ctl->qc_free_top, 1);
-  int c = MN_ATOMIC_ADD(&im.ctl->qc_bump, 1);
+  MN_ATOMIC_ADD(&sm.qc_free_top, 1);
+  int c = MN_ATOMIC_ADD(&sm.qc_bump, 1);
   if (c >= im.qc_cap) { mn_fail(im, MN_ERR_Q_POOL); return -1; }
   return c;
 }
-MN_D void mn_qc_free(const MnImage& im, int c) {  // called only from phases that never allocate
-  int t = MN_ATOMIC_ADD(&im.ctl->qc_free_top, 1);
+MN_D void mn_qc_free(const MnImage& im, MnSm& sm, int c) {  // called only from phases that never allocate
+  int t = MN_ATOMIC_ADD(&sm.qc_free_top, 1);
   im.qc_free[t] = c;
 }
 
 // conflict-table helpers are also used as a small node -> group hash by distribute()
 MN_D int mn_ct_slot(MnSm& sm, int obj);
 MN_D int mn_ct_find(const MnSm& sm, int obj);
+
+// Tree node (int4): x = first chunk, y = last chunk, z = entries below (a leaf: its own), w = first of
+// its 64 children (-1: leaf).  A leaf's entries fill its chunks in order, so the fill of the last
+// chunk follows from z; tn_dir holds the first 8 chunk ids of a leaf (8 * MN_QCH = MN_LEAFCAP
+// entries: what a refill loads) so that they can be fetched together instead of chain-walked.
 
 // Append the n entries staged in sm.sb_* (sb_node[i] = destination leaf) to their leaves.
 // No sorting: entries are grouped by destination through a shared-memory hash, one thread per
@@ -219,49 +268,49 @@ MN_D void mn_distribute(const MnImage& im, MnSm& sm, int n) {
   MN_FOR(s, MN_CT) {
     if (sm.ct_obj[s] != -1) {
       int g = MN_ATOMIC_ADD(&sm.ds_ngroups, 1);
-      sm.ct_w[s] = g; sm.ds_node[g] = sm.ct_obj[s]; sm.ds_cnt[g] = 0;
+      sm.ct_w[s] = g; sm.w.ds.node[g] = sm.ct_obj[s]; sm.w.ds.cnt[g] = 0;
     }
   }
   MN_SYNC();
   MN_FOR(i, n) {
     int s = mn_ct_find(sm, sm.sb_node[i]);
     int g = s >= 0 ? sm.ct_w[s] : 0;
-    int local = MN_ATOMIC_ADD(&sm.ds_cnt[g], 1);
-    sm.ds_el[i] = (g << 16) | local;
+    int local = MN_ATOMIC_ADD(&sm.w.ds.cnt[g], 1);
+    sm.w.ds.el[i] = (g << 16) | local;
   }
   MN_SYNC();
   const int ngroups = sm.ds_ngroups;
   MN_FOR(g, ngroups) {
-    int node = sm.ds_node[g], cnt = sm.ds_cnt[g];
-    int tail = im.tn_tail[node];
-    int fill = tail >= 0 ? im.qc_cnt[tail] : MN_QCH;
-    int room = MN_QCH - fill;
-    int nnew = cnt > room ? (cnt - room + MN_QCH - 1) / MN_QCH : 0;
-    int base = nnew ? MN_ATOMIC_ADD(&sm.ds_ndir, nnew) : 0;
-    sm.ds_tail[g] = tail;
-    sm.ds_fd[g] = fill | (base << 8);
-    if (tail >= 0) im.qc_cnt[tail] = cnt > room ? MN_QCH : fill + cnt;
-    int prev = tail, left = cnt - room;
+    const int node = sm.w.ds.node[g], cnt = sm.w.ds.cnt[g];
+    const int4 nd = im.tn[node];
+    const int have = nd.z, tail = nd.y;
+    const int fill = (tail >= 0 && have > 0) ? ((have - 1) % MN_QCH) + 1 : MN_QCH;
+    const int room = MN_QCH - fill;
+    const int nch0 = (tail >= 0 && have > 0) ? (have + MN_QCH - 1) / MN_QCH : 0;
+    const int nnew = cnt > room ? (cnt - room + MN_QCH - 1) / MN_QCH : 0;
+    const int base = nnew ? MN_ATOMIC_ADD(&sm.ds_ndir, nnew) : 0;
+    sm.w.ds.tail[g] = tail;
+    sm.w.ds.fd[g] = fill | (base << 8);
+    int prev = tail, head = (tail >= 0 && have > 0) ? nd.x : -1;
+    if (prev >= 0 && !(have > 0)) prev = -1;
     for (int j = 0; j < nnew; j++) {
-      int c = mn_qc_alloc(im);
-      if (base + j < MN_SB + 128) sm.ds_dir[base + j] = c;
+      int c = mn_qc_alloc(im, sm);
+      if (base + j < MN_SB + 128) sm.w.ds.dir[base + j] = c;
       if (c < 0) break;
       im.qc_next[c] = -1;
-      im.qc_cnt[c] = left > MN_QCH ? MN_QCH : left;
-      left -= MN_QCH;
-      if (prev >= 0) im.qc_next[prev] = c; else im.tn_head[node] = c;
+      if (prev >= 0) im.qc_next[prev] = c; else head = c;
+      if (nch0 + j < 8) im.tn_dir[(size_t)node * 8 + nch0 + j] = c;
       prev = c;
     }
-    if (nnew) im.tn_tail[node] = prev;
-    im.tn_cnt[node] += cnt;
+    im.tn[node] = make_int4(head, prev, have + cnt, nd.w);
   }
   MN_SYNC();
   MN_FOR(i, n) {
-    int g = sm.ds_el[i] >> 16, local = sm.ds_el[i] & 0xffff;
-    int fill = sm.ds_fd[g] & 0xff, base = sm.ds_fd[g] >> 8;
+    int g = sm.w.ds.el[i] >> 16, local = sm.w.ds.el[i] & 0xffff;
+    int fill = sm.w.ds.fd[g] & 0xff, base = sm.w.ds.fd[g] >> 8;
     int pos = fill + local, chunk, slot;
-    if (pos < MN_QCH) { chunk = sm.ds_tail[g]; slot = pos; }
-    else { int q = pos - MN_QCH; chunk = sm.ds_dir[base + q / MN_QCH]; slot = q % MN_QCH; }
+    if (pos < MN_QCH) { chunk = sm.w.ds.tail[g]; slot = pos; }
+    else { int q = pos - MN_QCH; chunk = sm.w.ds.dir[base + q / MN_QCH]; slot = q % MN_QCH; }
     if (chunk >= 0)
       im.q_ent[(size_t)chunk * MN_QCH + slot] = make_uint4(mn_f2u(sm.sb_mp[i]), (uint32_t)sm.sb_rec[i], (uint32_t)sm.sb_lo[i], (uint32_t)sm.sb_hi[i]);
   }
@@ -274,10 +323,12 @@ MN_D int mn_descend_for_insert(const MnImage& im, MnSm& sm, float mp, int lo, in
   MN_ATOMIC_OR(&sm.root_bits[root >> 5], 1u << (root & 31));
   MN_ATOMIC_OR(&sm.root_sum[root >> 10], 1u << ((root >> 5) & 31));
   int node = root, level = 0;
-  while (im.tn_child[node] >= 0) {
-    MN_ATOMIC_ADD(&im.tn_cnt[node], 1);
+  int child = im.tn[node].w;
+  while (child >= 0) {
+    MN_ATOMIC_ADD(&im.tn[node].z, 1);
     level++;
-    node = im.tn_child[node] + mn_digit(root, level, mp, lo, hi);
+    node = child + mn_digit(root, level, mp, lo, hi);
+    child = im.tn[node].w;
   }
   return node;
 }
@@ -298,145 +349,184 @@ MN_D void mn_flush_ins(const MnImage& im, MnSm& sm) {
     mn_distribute(im, sm, n);
   }
   if (MN_T0) {
-    im.ctl->tree_entries += total;
+    sm.tree_entries += total;
     sm.nins = 0;
     sm.st_flushes++;
+    if (sm.tree_entries > sm.peak_entries) sm.peak_entries = sm.tree_entries;
+    const int used = sm.qc_bump - (sm.qc_free_top > 0 ? sm.qc_free_top : 0);
+    if (used > sm.peak_chunks) sm.peak_chunks = used;
   }
   MN_SYNC();
 }
 
-// Split leaf `node` (at depth `level` under `root`): its entries move to 64 children by the next
-// digit.  Entries are validated on the way (dead ones are dropped: garbage collection).
-MN_D void mn_split_leaf(const MnImage& im, MnSm& sm, int root, int node, int level) {
+// What a queue entry (emp, elo, ehi) is against its record (rec_lh, rec_val = oml, same, qmp, mp):
+//   DROP     the record is dead, or another entry guards it (emp != qmp), or it was re-keyed at the
+//            same priority (a fresh entry was queued then);
+//   exact    emp == qmp == mp and the key matches: the reference's valid pop (cc:554-559);
+//   REQUEUE  emp == qmp > mp >= 0: the guard of a record whose priority was re-stored lower;
+//   UNGUARD  emp == qmp and mp < 0: the guard of a record that went dormant.
+// Returns MN_K_DROP / MN_K_RESTORE (meaning "exact") / MN_K_REQUEUE / MN_K_UNGUARD.
+MN_D int mn_entry_state(float emp, int elo, int ehi, int2 lh, float4 v) {
+  if (lh.x < 0) return MN_K_DROP;
+  if (!(v.z == emp)) return MN_K_DROP;
+  if (v.w == emp) return (lh.x == elo && lh.y == ehi) ? MN_K_RESTORE : MN_K_DROP;
+  if (v.w >= 0.0f) return MN_K_REQUEUE;
+  return MN_K_UNGUARD;
+}
+
+// chunk ids [k0, k0 + n) of leaf `node` into sm.cw_chunk (thread 0 follows the chain past the directory;
+// `prev` = id of chunk k0 - 1 or -1)
+MN_D void mn_leaf_chunks(const MnImage& im, MnSm& sm, int node, int k0, int n, int prev) {
+  MN_FOR(i, n) if (k0 + i < 8) sm.cw_chunk[i] = im.tn_dir[(size_t)node * 8 + k0 + i];
+  MN_SYNC();
+  if (MN_T0 && k0 + n > 8) {
+    int i0 = k0 < 8 ? 8 - k0 : 0;
+    int c = i0 > 0 ? sm.cw_chunk[i0 - 1] : prev;
+    for (int i = i0; i < n; i++) { c = c >= 0 ? im.qc_next[c] : -1; sm.cw_chunk[i] = c; }
+  }
+  MN_SYNC();
+}
+
+// clear the bit of an emptied root (thread 0)
+MN_D void mn_root_clear(MnSm& sm, int root) {
+  sm.root_bits[root >> 5] &= ~(1u << (root & 31));
+  if (sm.root_bits[root >> 5] == 0) sm.root_sum[root >> 10] &= ~(1u << ((root >> 5) & 31));
+}
+
+// Split leaf `node` (at depth `level` under `root`, `have` entries): its entries move to 64 children by
+// the next digit.  Entries are validated on the way (dead ones are dropped: garbage collection).
+MN_D void mn_split_leaf(const MnImage& im, MnSm& sm, int root, int node, int level, int have) {
   if (MN_T0) {
-    int base = MN_ATOMIC_ADD(&im.ctl->tn_bump, MN_TREE_FANOUT);
+    int base = MN_ATOMIC_ADD(&sm.tn_bump, MN_TREE_FANOUT);
     if (base + MN_TREE_FANOUT > im.tn_cap) { mn_fail(im, MN_ERR_TREE_POOL); base = -1; }
     sm.tmp0 = base;
-    sm.tmp1 = im.tn_head[node];
     sm.tmp2 = 0;  // surviving entries
     sm.st_splits++;
   }
   MN_SYNC();
-  int base = sm.tmp0;
+  const int base = sm.tmp0;
   if (base < 0) return;
-  MN_FOR(i, MN_TREE_FANOUT) {
-    im.tn_head[base + i] = -1; im.tn_tail[base + i] = -1; im.tn_cnt[base + i] = 0; im.tn_child[base + i] = -1;
-  }
+  MN_FOR(i, MN_TREE_FANOUT) im.tn[base + i] = make_int4(-1, -1, 0, -1);
   MN_SYNC();
-  int chunk = sm.tmp1;
-  int guard = 0;
-  while (chunk >= 0) {
-    // stage up to MN_SB entries (MN_SB / MN_QCH chunks)
+  const int nch = (have + MN_QCH - 1) / MN_QCH;
+  const int per = MN_SB / MN_QCH < MN_CW ? MN_SB / MN_QCH : MN_CW;
+  int prev = -1;
+  for (int k0 = 0; k0 < nch; k0 += per) {
+    const int n = nch - k0 < per ? nch - k0 : per;
+    mn_leaf_chunks(im, sm, node, k0, n, prev);
+    if (MN_T0) sm.npr = 0;
     MN_SYNC();
-    if (MN_T0) {
-      int n = 0, c = chunk, nch = 0;
-      while (c >= 0 && nch < MN_SB / MN_QCH) {
-        sm.cw_chunk[nch++] = c;
-        n += im.qc_cnt[c];
-        c = im.qc_next[c];
-      }
-      sm.tmp1 = c;
-      sm.tmp3 = nch;
-      sm.npr = 0;
-    }
-    MN_SYNC();
-    int nch = sm.tmp3;
-    MN_FOR(i, nch * MN_QCH) {
-      int c = sm.cw_chunk[i / MN_QCH], s = i % MN_QCH;
-      if (s < im.qc_cnt[c]) {
-        uint4 e = im.q_ent[(size_t)c * MN_QCH + s];
-        int rec = (int)e.y;
-        int2 lh = im.rec_lh[rec];
-        float4 v = im.rec_val[rec];
-        if (lh.x == (int)e.z && lh.y == (int)e.w && mn_f2u(v.w) == e.x) {
-          int p = MN_ATOMIC_ADD(&sm.npr, 1);
-          sm.sb_mp[p] = v.w; sm.sb_lo[p] = lh.x; sm.sb_hi[p] = lh.y; sm.sb_rec[p] = rec;
-          sm.sb_node[p] = base + mn_digit(root, level + 1, v.w, lh.x, lh.y);
-        }
+    prev = sm.cw_chunk[n - 1];
+    const int ents = (have - k0 * MN_QCH) < n * MN_QCH ? (have - k0 * MN_QCH) : n * MN_QCH;
+    MN_FOR(i, ents) {
+      const int c = sm.cw_chunk[i / MN_QCH], s = i % MN_QCH;
+      if (c < 0) { mn_fail(im, MN_ERR_INTERNAL); continue; }
+      uint4 e = im.q_ent[(size_t)c * MN_QCH + s];
+      int rec = (int)e.y;
+      int2 lh = im.rec_lh[rec];
+      float4 v = im.rec_val[rec];
+      float emp = mn_u2f(e.x);
+      int st = mn_entry_state(emp, (int)e.z, (int)e.w, lh, v);
+      if (st == MN_K_UNGUARD) { v.z = -1.0f; im.rec_val[rec] = v; }
+      else if (st != MN_K_DROP) {  // the entry keeps its own key (a guard stays where it is)
+        int p = MN_ATOMIC_ADD(&sm.npr, 1);
+        sm.sb_mp[p] = emp; sm.sb_lo[p] = (int)e.z; sm.sb_hi[p] = (int)e.w; sm.sb_rec[p] = rec;
+        sm.sb_node[p] = base + mn_digit(root, level + 1, emp, (int)e.z, (int)e.w);
       }
     }
     MN_SYNC();
-    int n = sm.npr;
-    mn_distribute(im, sm, n);
-    MN_FOR(i, nch) mn_qc_free(im, sm.cw_chunk[i]);
-    if (MN_T0) sm.tmp2 += n;
+    const int m = sm.npr;
+    mn_distribute(im, sm, m);
+    MN_FOR(i, n) if (sm.cw_chunk[i] >= 0) mn_qc_free(im, sm, sm.cw_chunk[i]);
+    if (MN_T0) sm.tmp2 += m;
     MN_SYNC();
-    chunk = sm.tmp1;
-    if (++guard > (1 << 24)) { mn_fail(im, MN_ERR_LIMIT); break; }
+    if (sm.failed) return;
   }
-  MN_SYNC();
   if (MN_T0) {
-    // fix the counts on the path: the node now holds only the survivors
-    int removed = im.tn_cnt[node] - sm.tmp2;
-    for (int i = 0; i < sm.path_n; i++) im.tn_cnt[sm.path[i]] -= removed;
-    im.tn_cnt[node] = sm.tmp2;
-    im.ctl->tree_entries -= removed;
-    im.tn_head[node] = -1;
-    im.tn_tail[node] = -1;
-    im.tn_child[node] = base;
+    // the node now holds only the survivors, below it; fix the counts on the path
+    const int removed = have - sm.tmp2;
+    for (int i = 0; i < sm.path_n; i++) { sm.path_cnt[i] -= removed; MN_ATOMIC_SUB(&im.tn[sm.path[i]].z, removed); }
+    sm.tree_entries -= removed;
+    im.tn[node] = make_int4(-1, -1, sm.tmp2, base);
+    const int root_cnt = sm.path_n > 0 ? sm.path_cnt[0] : sm.tmp2;
+    if (root_cnt <= 0) mn_root_clear(sm, root);
   }
   MN_SYNC();
 }
 
 // Find the first non-empty leaf in pop order; split it while it is too large.  Leaves the path
-// (ancestors, root first) in sm.path and returns the leaf, -1 when the tree is empty, or -2 when the
-// leaf needs a split that the caller did not allow.
+// (ancestors, root first, with their counts) in sm.path / sm.path_cnt, the leaf's node in sm.leaf_nd,
+// and returns the leaf, -1 when the tree is empty, or -2 when the leaf needs a split that the caller
+// did not allow.  The root bitmap is exact, so finding the root costs no memory access.
 MN_D int mn_top_leaf(const MnImage& im, MnSm& sm, int* root_out, bool allow_split) {
-  for (int guard = 0; guard < 64; guard++) {
+  for (int guard = 0; guard < 4096; guard++) {
     MN_SYNC();
     if (MN_T0) {
-      // highest non-empty root = first in pop order
       int root = -1;
       const int nsum = ((MN_NROOTS + 31) / 32 + 31) / 32;
       for (int s = nsum - 1; s >= 0 && root < 0; s--) {
         uint32_t sv = sm.root_sum[s];
-        while (sv && root < 0) {
-          int wb = 31 - MN_CLZ(sv);
-          int w = s * 32 + wb;
+        if (sv) {
+          int w = s * 32 + 31 - MN_CLZ(sv);
           uint32_t bits = sm.root_bits[w];
-          while (bits && root < 0) {
-            int b = 31 - MN_CLZ(bits);
-            int r = w * 32 + b;
-            if (im.tn_cnt[r] > 0) root = r;
-            else { bits &= ~(1u << b); sm.root_bits[w] = bits; }
-          }
-          if (root < 0) { sv &= ~(1u << wb); sm.root_sum[s] = sv; }
+          if (bits) root = w * 32 + 31 - MN_CLZ(bits);
+          else sm.root_sum[s] = sv & ~(1u << (w & 31));  // (stale summary bit)
+          if (root < 0) s++;                                // look at this summary word again
         }
       }
       sm.tmp0 = root;
       sm.path_n = 0;
-      int node = root, level = 0;
-      if (root >= 0) {
-        while (im.tn_child[node] >= 0) {
-          sm.path[sm.path_n++] = node;
-          int cb = im.tn_child[node], found = -1;
-          for (int d = 0; d < MN_TREE_FANOUT; d++)
-            if (im.tn_cnt[cb + d] > 0) { found = cb + d; break; }
-          if (found < 0) { mn_fail(im, MN_ERR_INTERNAL); break; }
-          node = found;
-          level++;
-        }
-      }
-      sm.tmp1 = node;
-      sm.tmp2 = level;
     }
     MN_SYNC();
-    int root = sm.tmp0, node = sm.tmp1, level = sm.tmp2;
+    const int root = sm.tmp0;
     if (root < 0) return -1;
+    int node = root, level = 0;
+    int4 nd = im.tn[node];
+    if (nd.z <= 0) {  // (defensive: a root bit without entries)
+      MN_SYNC();
+      if (MN_T0) mn_root_clear(sm, root);
+      continue;
+    }
+    bool bad = false;
+    while (nd.w >= 0) {  // descend: the 64 children of a split node are read by 64 threads at once
+      const int cb = nd.w;
+      MN_FOR(d, MN_TREE_FANOUT) sm.scan_nd[d] = im.tn[cb + d];
+      MN_SYNC();
+      if (MN_T0) {
+        int found = -1;
+        for (int d = 0; d < MN_TREE_FANOUT; d++)
+          if (sm.scan_nd[d].z > 0) { found = d; break; }
+        sm.path[sm.path_n] = node; sm.path_cnt[sm.path_n] = nd.z; sm.path_n++;
+        sm.tmp1 = found;
+      }
+      MN_SYNC();
+      const int found = sm.tmp1;
+      if (found < 0 || level > 16) { bad = true; break; }
+      nd = sm.scan_nd[found];
+      node = cb + found;
+      level++;
+      MN_SYNC();  // scan_nd is reused by the next level
+    }
+    if (bad) { mn_fail(im, MN_ERR_INTERNAL); return -1; }
     *root_out = root;
-    if (im.tn_cnt[node] <= MN_LEAFCAP || level >= mn_max_level(root)) return node;
+    if (nd.z <= MN_LEAFCAP || level >= mn_max_level(root)) {
+      MN_SYNC();
+      if (MN_T0) sm.leaf_nd = nd;
+      MN_SYNC();
+      return node;
+    }
     if (!allow_split) return -2;  // the caller's staging buffers are in use
     MN_TOC(MN_CY_REFILL);
-    mn_split_leaf(im, sm, root, node, level);
+    mn_split_leaf(im, sm, root, node, level, nd.z);
     MN_TOC(MN_CY_SPLIT);
-    if (im.ctl->status != MN_OK) return -1;
+    if (sm.failed) return -1;
   }
   mn_fail(im, MN_ERR_LIMIT);
   return -1;
 }
 
 // decode the i-th sorted initial entry
-MN_D void mn_decode_init(const MnImage& im, const MnMergeArgs& A, uint64_t key, float* mp, int* lo, int* hi, int* rec) {
+MN_D void mn_decode_init(const MnMergeArgs& A, uint64_t key, float* mp, int* lo, int* hi, int* rec) {
   uint32_t ord = (uint32_t)(key & ((1ull << MN_ORD_BITS) - 1));
   *mp = mn_u2f(~(uint32_t)(key >> MN_ORD_BITS));
   int l = (int)(ord / (uint32_t)A.K), rank = (int)(ord % (uint32_t)A.K);
@@ -448,34 +538,36 @@ MN_D void mn_decode_init(const MnImage& im, const MnMergeArgs& A, uint64_t key, 
   *rec = p * A.K + k;
 }
 
-// exclusive prefix sum of n 0/1 flags (all threads call it); returns the total
-MN_D int mn_exclusive_scan(MnSm& sm, const int* flags, int* out, int n) {
+// exclusive prefix sum of n non-negative ints (all threads call it); returns the total
+MN_D int mn_exclusive_scan(MnSm& sm, const int* vals, int* out, int n) {
   const int nt = MN_NT, t = MN_TID;
   const int per = (n + nt - 1) / nt;
   const int b = t * per, e = b + per < n ? b + per : n;
   int ssum = 0;
-  for (int i = b; i < e; i++) ssum += flags[i];
-  if (t < MN_SB) sm.ds_cnt[t] = ssum;
+  for (int i = b; i < e; i++) ssum += vals[i];
+  if (t < MN_SB) sm.w.ds.cnt[t] = ssum;
   MN_SYNC();
   if (MN_T0) {
     int acc = 0;
-    for (int k = 0; k < nt && k < MN_SB; k++) { int v = sm.ds_cnt[k]; sm.ds_cnt[k] = acc; acc += v; }
+    for (int k = 0; k < nt && k < MN_SB; k++) { int v = sm.w.ds.cnt[k]; sm.w.ds.cnt[k] = acc; acc += v; }
     sm.tmp3 = acc;
   }
   MN_SYNC();
-  int acc = t < MN_SB ? sm.ds_cnt[t] : 0;
-  for (int i = b; i < e; i++) { out[i] = acc; acc += flags[i]; }
+  int acc = t < MN_SB ? sm.w.ds.cnt[t] : 0;
+  for (int i = b; i < e; i++) { int v = vals[i]; out[i] = acc; acc += v; }
   MN_SYNC();
   return sm.tmp3;
 }
 
+MN_D void mn_hot_update(const MnImage& im, MnSm& sm, int cut);
+MN_D void mn_push_entry(MnSm& sm, float mp, int lo, int hi, int rec);
 // Refill the (empty) hot buffer.  Afterwards: hot holds every entry popping before-or-at `bound`.
 MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
   if (MN_T0) sm.st_refills++;
   for (int guard = 0; guard < (1 << 20); guard++) {
     MN_SYNC();
     mn_flush_ins(im, sm);  // (also on retries: a previous pass may have pushed leaf entries back)
-    if (im.ctl->status != MN_OK) return;
+    if (sm.failed) return;
     // ---- load + validate successive top leaves (each pops entirely before the next) until a
     //      useful number of entries is staged; their chunks are recycled ----
     int nleaf = 0;
@@ -486,49 +578,38 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
       int leaf = mn_top_leaf(im, sm, &root, nleaf == 0);  // splitting reuses the staging buffers
       if (nleaf == 0) { MN_SYNC(); if (MN_T0) sm.npr = 0; MN_SYNC(); }  // (a split used npr)
       if (leaf < 0) break;
-      if (im.ctl->status != MN_OK) return;
-      if (nleaf + im.tn_cnt[leaf] > MN_SB - MN_REFILL_STATIC_MIN) {  // keep room for initial entries
+      if (sm.failed) return;
+      const int have = sm.leaf_nd.z;
+      if (nleaf + have > MN_SB - MN_REFILL_STATIC_MIN) {  // keep room for initial entries
         if (nleaf == 0) mn_fail(im, MN_ERR_INTERNAL);  // an unsplittable leaf larger than the buffer
         break;
       }
-      if (MN_T0) sm.tmp1 = im.tn_head[leaf];
-      MN_SYNC();
-      int chunk = sm.tmp1;
-      while (chunk >= 0) {
-        MN_SYNC();
-        if (MN_T0) {
-          int c = chunk, nch = 0;
-          while (c >= 0 && nch < MN_CW) { sm.cw_chunk[nch++] = c; c = im.qc_next[c]; }
-          sm.tmp1 = c; sm.tmp3 = nch;
+      const int nch = (have + MN_QCH - 1) / MN_QCH;
+      if (nch > MN_CW) { mn_fail(im, MN_ERR_INTERNAL); break; }
+      mn_leaf_chunks(im, sm, leaf, 0, nch, -1);
+      MN_FOR(i, have) {
+        const int c = sm.cw_chunk[i / MN_QCH], s = i % MN_QCH;
+        if (c < 0) { mn_fail(im, MN_ERR_INTERNAL); continue; }
+        uint4 e = im.q_ent[(size_t)c * MN_QCH + s];
+        int rec = (int)e.y;
+        int2 lh = im.rec_lh[rec];
+        float4 v = im.rec_val[rec];
+        float emp = mn_u2f(e.x);
+        int st = mn_entry_state(emp, (int)e.z, (int)e.w, lh, v);
+        if (st == MN_K_UNGUARD) { v.z = -1.0f; im.rec_val[rec] = v; }
+        else if (st != MN_K_DROP) {
+          int p = MN_ATOMIC_ADD(&sm.npr, 1);
+          if (p < MN_SB) { sm.sb_mp[p] = emp; sm.sb_lo[p] = (int)e.z; sm.sb_hi[p] = (int)e.w; sm.sb_rec[p] = rec; }
         }
-        MN_SYNC();
-        int nch = sm.tmp3;
-        MN_FOR(i, nch * MN_QCH) {
-          int c = sm.cw_chunk[i / MN_QCH], s = i % MN_QCH;
-          if (s < im.qc_cnt[c]) {
-            uint4 e = im.q_ent[(size_t)c * MN_QCH + s];
-            int rec = (int)e.y;
-            int2 lh = im.rec_lh[rec];
-            float4 v = im.rec_val[rec];
-            if (lh.x == (int)e.z && lh.y == (int)e.w && mn_f2u(v.w) == e.x) {
-              int p = MN_ATOMIC_ADD(&sm.npr, 1);
-              if (p < MN_SB) { sm.sb_mp[p] = v.w; sm.sb_lo[p] = lh.x; sm.sb_hi[p] = lh.y; sm.sb_rec[p] = rec; }
-            }
-          }
-        }
-        MN_SYNC();
-        MN_FOR(i, nch) mn_qc_free(im, sm.cw_chunk[i]);
-        MN_SYNC();
-        chunk = sm.tmp1;
       }
       MN_SYNC();
+      MN_FOR(i, nch) if (sm.cw_chunk[i] >= 0) mn_qc_free(im, sm, sm.cw_chunk[i]);
       if (MN_T0) {
-        int removed = im.tn_cnt[leaf];
-        for (int i = 0; i < sm.path_n; i++) im.tn_cnt[sm.path[i]] -= removed;
-        im.tn_cnt[leaf] = 0;
-        im.tn_head[leaf] = -1;
-        im.tn_tail[leaf] = -1;
-        im.ctl->tree_entries -= removed;
+        for (int i = 0; i < sm.path_n; i++) MN_ATOMIC_SUB(&im.tn[sm.path[i]].z, have);
+        im.tn[leaf] = make_int4(-1, -1, 0, -1);
+        sm.tree_entries -= have;
+        const int root_cnt = sm.path_n > 0 ? sm.path_cnt[0] - have : 0;
+        if (root_cnt <= 0) mn_root_clear(sm, root);
         if (sm.npr > MN_SB) { mn_fail(im, MN_ERR_INTERNAL); sm.npr = MN_SB; }
       }
       MN_SYNC();
@@ -546,13 +627,13 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
     MN_SYNC();
     const int w = sm.tmp0;
     const float lmp = w >= 0 ? sm.sb_mp[w] : 0.f; const int llo = w >= 0 ? sm.sb_lo[w] : 0, lhi = w >= 0 ? sm.sb_hi[w] : 0;
-    const int sc = im.ctl->static_cursor, ninit = im.ctl->n_init;
+    const int sc = sm.static_cursor, ninit = sm.n_init;
     const int room = MN_HC - nleaf;
     int navail = ninit - sc; if (navail > room) navail = room;
     // count the initial entries (a prefix, they are sorted) that pop before the leaf's last entry
     MN_FOR(i, navail) {
       float mp; int lo, hi, rec;
-      mn_decode_init(im, A, im.init_keys[sc + i], &mp, &lo, &hi, &rec);
+      mn_decode_init(A, im.init_keys[sc + i], &mp, &lo, &hi, &rec);
       bool take = (w < 0) || mn_before(mp, lo, hi, lmp, llo, lhi);
       if (take) MN_ATOMIC_ADD(&sm.tmp2, 1);
     }
@@ -562,17 +643,18 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
     bool more_before = false;
     if (w >= 0 && ntake == navail && sc + navail < ninit) {
       float mp; int lo, hi, rec;
-      mn_decode_init(im, A, im.init_keys[sc + navail], &mp, &lo, &hi, &rec);
+      mn_decode_init(A, im.init_keys[sc + navail], &mp, &lo, &hi, &rec);
       more_before = mn_before(mp, lo, hi, lmp, llo, lhi);
     }
     MN_FOR(i, ntake) {
       float mp; int lo, hi, rec;
-      mn_decode_init(im, A, im.init_keys[sc + i], &mp, &lo, &hi, &rec);
+      mn_decode_init(A, im.init_keys[sc + i], &mp, &lo, &hi, &rec);
       int2 lh = im.rec_lh[rec];
       float4 v = im.rec_val[rec];
-      bool valid = (lh.x == lo && lh.y == hi && v.w == mp);
+      int st = mn_entry_state(mp, lo, hi, lh, v);
+      if (st == MN_K_UNGUARD) { v.z = -1.0f; im.rec_val[rec] = v; st = MN_K_DROP; }
       int p = nleaf + i;
-      sm.sb_mp[p] = valid ? mp : MN_NEG_INF; sm.sb_lo[p] = lo; sm.sb_hi[p] = hi; sm.sb_rec[p] = rec;
+      sm.sb_mp[p] = st != MN_K_DROP ? mp : MN_NEG_INF; sm.sb_lo[p] = lo; sm.sb_hi[p] = hi; sm.sb_rec[p] = rec;
     }
     MN_SYNC();
     // the bound
@@ -580,7 +662,7 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
       if (w < 0) {  // tree empty: the last taken initial entry bounds the rest of the array
         if (ntake > 0) {
           float mp; int lo, hi, rec;
-          mn_decode_init(im, A, im.init_keys[sc + ntake - 1], &mp, &lo, &hi, &rec);
+          mn_decode_init(A, im.init_keys[sc + ntake - 1], &mp, &lo, &hi, &rec);
           sm.b_mp = mp; sm.b_lo = lo; sm.b_hi = hi;
         }
         sm.cold_empty = (sc + ntake >= ninit) ? 1 : 0;
@@ -591,17 +673,43 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
         sm.cold_empty = 0;
       } else {  // hot is full of earlier initial entries: leaf entries after the last taken one stay cold
         float mp; int lo, hi, rec;
-        mn_decode_init(im, A, im.init_keys[sc + ntake - 1], &mp, &lo, &hi, &rec);
+        mn_decode_init(A, im.init_keys[sc + ntake - 1], &mp, &lo, &hi, &rec);
         sm.b_mp = mp; sm.b_lo = lo; sm.b_hi = hi;
         sm.cold_empty = 0;
       }
-      im.ctl->static_cursor = sc + ntake;
+      sm.static_cursor = sc + ntake;
+      sm.tmp1 = 0; sm.tmp0 = 0;
     }
     MN_SYNC();
+    // ---- guards in the batch (record re-stored lower since the entry was queued) are replaced by
+    //      their exact entry now, in bulk, instead of costing a window slot later ----
+    MN_FOR(i, nleaf + ntake) {
+      if (sm.sb_mp[i] > MN_NEG_INF) {
+        const int rec = sm.sb_rec[i];
+        const int2 lh = im.rec_lh[rec];
+        float4 v = im.rec_val[rec];
+        if (mn_entry_state(sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i], lh, v) == MN_K_REQUEUE) {
+          v.z = v.w;
+          im.rec_val[rec] = v;
+          MN_ATOMIC_ADD(&sm.tmp1, 1);
+          if (!sm.cold_empty && mn_before(sm.b_mp, sm.b_lo, sm.b_hi, v.w, lh.x, lh.y)) {  // cold
+            int p = MN_ATOMIC_ADD(&sm.nins, 1);
+            sm.ins_mp[p] = v.w; sm.ins_lo[p] = lh.x; sm.ins_hi[p] = lh.y; sm.ins_rec[p] = rec;
+            sm.sb_mp[i] = MN_NEG_INF;
+          } else {  // still hot-bound: re-key in place (an initial entry then breaks its sorted run)
+            sm.sb_mp[i] = v.w; sm.sb_lo[i] = lh.x; sm.sb_hi[i] = lh.y;
+            if (i >= nleaf) sm.tmp0 = 1;
+          }
+        }
+      }
+    }
+    MN_SYNC();
+    if (MN_T0) { sm.st_requeues += sm.tmp1; sm.tmp1 = 0; }
+    const bool init_unsorted = sm.tmp0 != 0;
     if (more_before) {
       // push the leaf entries that pop after the bound back to the insert buffer
       MN_FOR(i, nleaf) {
-        if (mn_before(sm.b_mp, sm.b_lo, sm.b_hi, sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i])) {
+        if (sm.sb_mp[i] > MN_NEG_INF && mn_before(sm.b_mp, sm.b_lo, sm.b_hi, sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i])) {
           int p = MN_ATOMIC_ADD(&sm.nins, 1);
           sm.ins_mp[p] = sm.sb_mp[i]; sm.ins_lo[p] = sm.sb_lo[i]; sm.ins_hi[p] = sm.sb_hi[i]; sm.ins_rec[p] = sm.sb_rec[i];
           sm.sb_mp[i] = MN_NEG_INF;
@@ -610,7 +718,7 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
       MN_SYNC();
     }
 #ifdef MN_EMUL_TRACE
-    fprintf(stderr, "refill: nleaf %d ntake %d more_before %d nins %d cold_empty %d bound %.9g %d %d sc %d ninit %d tree %d\n", nleaf, ntake, (int)more_before, sm.nins, sm.cold_empty, sm.b_mp, sm.b_lo, sm.b_hi, im.ctl->static_cursor, ninit, im.ctl->tree_entries);
+    fprintf(stderr, "refill: nleaf %d ntake %d more_before %d nins %d cold_empty %d bound %.9g %d %d sc %d ninit %d tree %d\n", nleaf, ntake, (int)more_before, sm.nins, sm.cold_empty, sm.b_mp, sm.b_lo, sm.b_hi, sm.static_cursor, ninit, sm.tree_entries);
 #endif
     const int n = nleaf + ntake;
     if (n == 0) {
@@ -618,7 +726,7 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
       MN_SYNC();
       return;  // nothing left anywhere (cold_empty set above)
     }
-    if (nleaf <= MN_RANK_MAX) {
+    if (nleaf <= MN_RANK_MAX && !init_unsorted) {
       // ---- fast path, no barrier-heavy sort: rank the (few) leaf entries by brute force, compact the
       //      already sorted initial entries with a scan, then merge the two runs by binary search.
       //      Duplicates of one record stay adjacent and are dropped when they are popped. ----
@@ -645,11 +753,11 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
         int p = sm.ne_pos[i];
         if (p >= 0) { sm.ne_mp[p] = sm.sb_mp[i]; sm.ne_lo[p] = sm.sb_lo[i]; sm.ne_hi[p] = sm.sb_hi[i]; sm.ne_rec[p] = sm.sb_rec[i]; }
       }
-      const int ns = mn_exclusive_scan(sm, sm.sb_node, sm.ds_el, ntake);
+      const int ns = mn_exclusive_scan(sm, sm.sb_node, sm.w.ds.el, ntake);
       const int cur = sm.hsel, dst = sm.hsel ^ 1;
       MN_FOR(i, ntake) {
         if (sm.sb_node[i]) {
-          int p = sm.ds_el[i], q = nleaf + i;
+          int p = sm.w.ds.el[i], q = nleaf + i;
           sm.hot_mp[cur][p] = sm.sb_mp[q]; sm.hot_lo[cur][p] = sm.sb_lo[q]; sm.hot_hi[cur][p] = sm.sb_hi[q]; sm.hot_rec[cur][p] = sm.sb_rec[q];
         }
       }
@@ -689,7 +797,7 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
       if (MN_T0) sm.nhot = sm.tmp0;
       MN_SYNC();
     }
-    if (sm.nhot > 0 || sm.cold_empty) return;
+    if (sm.nhot > 0 || (sm.cold_empty && sm.nins == 0)) return;
     // everything loaded was invalid: lower the bound again
   }
   mn_fail(im, MN_ERR_LIMIT);
@@ -731,9 +839,18 @@ MN_D void mn_clear_live(const MnImage& im, const MnMergeArgs& A, int r) {
   MN_ATOMIC_AND(&im.live_mask[p], ~(1u << k));
   MN_ATOMIC_AND(&im.live_mask[p + A.off.delta[k]], ~(1u << (16 + k)));
 }
+// live-mask bits of pixel `pix` that belong to record slot r (0 when r is not a slot of pix)
+MN_D uint32_t mn_own_bits(const MnMergeArgs& A, int pix, int r) {
+  int p = r / A.K, k = r - p * A.K;
+  uint32_t m = 0;
+  if (pix == p) m |= 1u << k;
+  if (pix == p + A.off.delta[k]) m |= 1u << (16 + k);
+  return m;
+}
 
 // queue a created entry (cc:564,697,705): hot-bound entries are staged in ne_*, colder ones go to ins
 MN_D void mn_push_entry(MnSm& sm, float mp, int lo, int hi, int rec) {
+  MN_WATCH(rec, "push mp %.9g key %d %d", mp, lo, hi);
   bool cold = !sm.cold_empty && mn_before(sm.b_mp, sm.b_lo, sm.b_hi, mp, lo, hi);
   if (cold) {
     int p = MN_ATOMIC_ADD(&sm.nins, 1);
@@ -743,34 +860,135 @@ MN_D void mn_push_entry(MnSm& sm, float mp, int lo, int hi, int rec) {
     sm.ne_mp[p] = mp; sm.ne_lo[p] = lo; sm.ne_hi[p] = hi; sm.ne_rec[p] = rec;
   }
 }
+// Store priority `mp` on a record whose guard priority is `q` (-1: no queued entry): queue an entry
+// unless an earlier-popping one already guards the record.  Returns the new guard priority.
+MN_D float mn_store_priority(MnSm& sm, float mp, float q, int lo, int hi, int rec) {
+  if (mp >= 0.0f && !(q > mp)) {
+    mn_push_entry(sm, mp, lo, hi, rec);
+    return mp;
+  }
+  return q;
+}
+
+// ---- hash bucket helpers on buckets already in registers ------------------------------------------
+MN_D void mn_load_bucket4(const MnImage& im, uint32_t b, uint32_t* out) {
+  const uint4* p = reinterpret_cast<const uint4*>(im.hash + (size_t)b * 8);
+  uint4 x = p[0], y = p[1];
+  out[0] = x.x; out[1] = x.y; out[2] = x.z; out[3] = x.w;
+  out[4] = y.x; out[5] = y.y; out[6] = y.z; out[7] = y.w;
+}
+// global slot index of value `val` in the two loaded buckets (-1: not there)
+MN_D int mn_bucket_find_val(const MnHashPos& p, const uint32_t* bk /*16*/, uint32_t val) {
+  for (int s = 0; s < 8; s++) if (bk[s] == val) return (int)(p.b1 * 8 + s);
+  for (int s = 0; s < 8; s++) if (bk[8 + s] == val) return (int)(p.b2 * 8 + s);
+  return -1;
+}
+// the (tiny) overflow area of the hash lives in shared memory: no memory access on a lookup miss
+MN_D int mn_ovf_find(const MnSm& sm, int n, int lo, int hi) {
+  for (int i = 0; i < n; i++)
+    if (sm.ovf_lo[i] == lo && sm.ovf_hi[i] == hi) return sm.ovf_rec[i];
+  return -1;
+}
+MN_D void mn_ovf_erase(MnSm& sm, int rec) {
+  const int n = sm.hash_ovf_n < MN_OVF ? sm.hash_ovf_n : MN_OVF;
+  for (int i = 0; i < n; i++)
+    if (sm.ovf_rec[i] == rec && sm.ovf_lo[i] >= 0) { sm.ovf_lo[i] = -1; sm.ovf_hi[i] = -1; return; }
+}
+// insert with a hint: `islot` was free when the buckets were read
+MN_D void mn_hash_insert_hint(const MnImage& im, MnSm& sm, int lo, int hi, int rec, int islot) {
+  MnHashPos p = mn_hash_pos(im.hash_nbuckets, lo, hi);
+  uint32_t val = (p.fp << MN_HASH_FP_SHIFT) | (uint32_t)(rec + 1);
+  if (islot >= 0 && MN_ATOMIC_CAS(&im.hash[islot], 0u, val) == 0u) return;
+  uint32_t* bk1 = im.hash + (size_t)p.b1 * 8;
+  uint32_t* bk2 = im.hash + (size_t)p.b2 * 8;
+  for (int w = 0; w < 2; w++) {
+    uint32_t* bk = w ? bk2 : bk1;
+    for (int s = 0; s < 8; s++)
+      if (bk[s] == 0 && MN_ATOMIC_CAS(&bk[s], 0u, val) == 0u) return;
+  }
+  int i = MN_ATOMIC_ADD(&sm.hash_ovf_n, 1);
+  if (i < MN_OVF) { sm.ovf_lo[i] = lo; sm.ovf_hi[i] = hi; sm.ovf_rec[i] = rec; }
+  else mn_fail(im, MN_ERR_HASH_FULL);
+}
 
 // ---- plan the pairs [p0, p1) (record t of candidate j's absorbed object), cc:650-707 -----------
+// Dependent round trips: record t -> {neighbour object, new-key buckets, old-key buckets} ->
+// partner record (+ the neighbour's class vector when classes differ).
 MN_D void mn_plan_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const float* c_clp, int p0, int p1) {
+  const int novf = sm.hash_ovf_n < MN_OVF ? sm.hash_ovf_n : MN_OVF;
   MN_FOR(ii, p1 - p0) {
     int i = p0 + ii;
-    int j = sm.pr_cand[i], t = sm.pr_t[i];
+    int j = sm.w.pr.cand[i], t = sm.w.pr.t[i];
     int a = sm.c_surv[j], b = sm.c_abs[j];
     int2 lh = im.rec_lh[t];
     float4 v = im.rec_val[t];
+    float tdiff = im.rec_diff[t];
     int x = lh.x == b ? lh.y : lh.x;
-    if (lh.x != b && lh.y != b) mn_fail(im, MN_ERR_INTERNAL);  // cc:665-668
-    if (x == a) mn_fail(im, MN_ERR_INTERNAL);                    // cc:670-673
-    int nlo = a < x ? a : x, nhi = a < x ? x : a;
-    int u = mn_hash_find(im, nlo, nhi);  // cc:685-686
-    float oml = v.x, same = v.y, diff = v.z;
-    if (u >= 0) {  // cc:690-692: that += this
-      float4 uv = im.rec_val[u];
-      oml = MN_FADD(uv.x, v.x); diff = MN_FADD(uv.z, v.z); same = MN_FADD(uv.y, v.y);
+    if ((lh.x != b && lh.y != b) || x == a || x < 0) {  // cc:665-673
+      mn_fail(im, MN_ERR_INTERNAL);
+      sm.w.pr.x[i] = a; sm.w.pr.u[i] = -1; sm.w.pr.mp[i] = -1.0f; sm.w.pr.eslot[i] = -1; sm.w.pr.islot[i] = -1;
+      sm.w.pr.lo[i] = 0; sm.w.pr.hi[i] = 0; sm.w.pr.oml[i] = 0; sm.w.pr.same[i] = 0; sm.w.pr.diff[i] = 0; sm.w.pr.q[i] = -1.0f;
+      continue;
     }
-    uint32_t xnc = im.obj_nc[x];
-    int nx = mn_nc_npix(xnc), cx = mn_nc_cls(xnc);
-    const float* clpa = c_clp + (size_t)j * A.C;
+    int nlo = a < x ? a : x, nhi = a < x ? x : a;
+    int olo = b < x ? b : x, ohi = b < x ? x : b;
+    MnHashPos pn = mn_hash_pos(im.hash_nbuckets, nlo, nhi);
+    MnHashPos po = mn_hash_pos(im.hash_nbuckets, olo, ohi);
+    uint32_t bn[16], bo[16];
+    mn_load_bucket4(im, pn.b1, bn); mn_load_bucket4(im, pn.b2, bn + 8);
+    mn_load_bucket4(im, po.b1, bo); mn_load_bucket4(im, po.b2, bo + 8);
+    uint4 ox = im.obj[x];
+    // partner record u = (a, x) if the survivor is already linked to x (cc:685-686)
+    int u = -1, islot = -1, f1 = 0, f2 = 0;
+    for (int s = 0; s < 8; s++) { f1 += bn[s] == 0; f2 += bn[8 + s] == 0; }
+    int c0 = -1, c1 = -1, srest = 16;
+    for (int s = 0; s < 16; s++) {
+      uint32_t hv = bn[s];
+      if (hv != 0 && (hv >> MN_HASH_FP_SHIFT) == pn.fp) {
+        int r = (int)(hv & ((1u << MN_HASH_FP_SHIFT) - 1)) - 1;
+        if (c0 < 0) c0 = r; else if (c1 < 0) c1 = r; else { srest = s; break; }
+      }
+    }
+    float4 uv = make_float4(0.f, 0.f, 0.f, 0.f); float ud = 0.f;
+    if (c0 >= 0) {  // fingerprint matches: key and values of (up to) two candidates in one round trip
+      int2 l0 = im.rec_lh[c0]; float4 v0 = im.rec_val[c0]; float d0 = im.rec_diff[c0];
+      int2 l1 = make_int2(-1, -1); float4 v1 = v0; float d1 = 0.f;
+      if (c1 >= 0) { l1 = im.rec_lh[c1]; v1 = im.rec_val[c1]; d1 = im.rec_diff[c1]; }
+      if (l0.x == nlo && l0.y == nhi) { u = c0; uv = v0; ud = d0; }
+      else if (c1 >= 0 && l1.x == nlo && l1.y == nhi) { u = c1; uv = v1; ud = d1; }
+    }
+    for (int s = srest; s < 16 && u < 0; s++) {  // (a third fingerprint match: practically never)
+      uint32_t hv = bn[s];
+      if (hv != 0 && (hv >> MN_HASH_FP_SHIFT) == pn.fp) {
+        int r = (int)(hv & ((1u << MN_HASH_FP_SHIFT) - 1)) - 1;
+        int2 l2 = im.rec_lh[r];
+        if (l2.x == nlo && l2.y == nhi) { u = r; uv = im.rec_val[r]; ud = im.rec_diff[r]; }
+      }
+    }
+    if (u < 0 && novf > 0) {
+      u = mn_ovf_find(sm, novf, nlo, nhi);
+      if (u >= 0) { uv = im.rec_val[u]; ud = im.rec_diff[u]; }
+    }
+    if (u < 0) {  // free slot for the re-keyed record: the emptier bucket first
+      int first = (f1 >= f2) ? 0 : 8;
+      for (int s = 0; s < 8 && islot < 0; s++) if (bn[first + s] == 0) islot = (int)((first ? pn.b2 : pn.b1) * 8 + s);
+      for (int s = 0; s < 8 && islot < 0; s++) if (bn[(8 - first) + s] == 0) islot = (int)((first ? pn.b1 : pn.b2) * 8 + s);
+    }
+    int eslot = mn_bucket_find_val(po, bo, (po.fp << MN_HASH_FP_SHIFT) | (uint32_t)(t + 1));
+    float oml = v.x, same = v.y, diff = tdiff, q = v.z;
+    if (u >= 0) {  // cc:690-692: that += this
+      oml = MN_FADD(uv.x, v.x); diff = MN_FADD(ud, tdiff); same = MN_FADD(uv.y, v.y);
+      q = uv.z;
+    }
+    int nx = mn_nc_npix(ox.x), cx = mn_nc_cls(ox.x);
+    const float* clpa = c_clp + (size_t)(j * 3 + 2) * A.C;
     const float* clpx = im.clp + (size_t)x * A.C;
     float mp;
     if (a < x) mp = mn_priority(oml, A.omf, A.mlb, A.C, sm.c_na[j], sm.c_merged[j], clpa, nx, cx, clpx, nullptr);
     else mp = mn_priority(oml, A.omf, A.mlb, A.C, nx, cx, clpx, sm.c_na[j], sm.c_merged[j], clpa, nullptr);
-    sm.pr_x[i] = x; sm.pr_u[i] = u; sm.pr_oml[i] = oml; sm.pr_same[i] = same; sm.pr_diff[i] = diff;
-    sm.pr_mp[i] = mp; sm.pr_lo[i] = nlo; sm.pr_hi[i] = nhi;
+    sm.w.pr.x[i] = x; sm.w.pr.u[i] = u; sm.w.pr.oml[i] = oml; sm.w.pr.same[i] = same; sm.w.pr.diff[i] = diff;
+    sm.w.pr.mp[i] = mp; sm.w.pr.lo[i] = nlo; sm.w.pr.hi[i] = nhi; sm.w.pr.q[i] = q;
+    sm.w.pr.eslot[i] = eslot; sm.w.pr.islot[i] = islot;
     if (mp >= 0.0f) MN_ATOMIC_MAX(&sm.c_maxnew[j], mn_f2u(mp) + 1u);
   }
 }
@@ -779,99 +997,39 @@ MN_D void mn_plan_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const
 MN_D void mn_commit_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, int p0, int p1) {
   MN_FOR(ii, p1 - p0) {
     int i = p0 + ii;
-    int j = sm.pr_cand[i];
+    int j = sm.w.pr.cand[i];
     if (!sm.c_accept[j]) continue;
-    int t = sm.pr_t[i], u = sm.pr_u[i], b = sm.c_abs[j], x = sm.pr_x[i];
-    int olo = b < x ? b : x, ohi = b < x ? x : b;
-    mn_hash_erase(im, olo, ohi, t);  // cc:680
-    float mp = sm.pr_mp[i];
-    if (u >= 0) {
-      im.rec_val[u] = make_float4(sm.pr_oml[i], sm.pr_same[i], sm.pr_diff[i], mp);  // cc:690-695
-      im.rec_lh[t] = make_int2(-1, -1);                                               // cc:694
+    int t = sm.w.pr.t[i], u = sm.w.pr.u[i];
+    if (sm.w.pr.eslot[i] >= 0) im.hash[sm.w.pr.eslot[i]] = 0;  // cc:680
+    else mn_ovf_erase(sm, t);
+    float mp = sm.w.pr.mp[i];
+    if (u >= 0) {  // cc:690-698: fold t into u, t dies
+      float q = mn_store_priority(sm, mp, sm.w.pr.q[i], sm.w.pr.lo[i], sm.w.pr.hi[i], u);
+      MN_WATCH(u, "fold-into mp %.9g q_old %.9g q_new %.9g key %d %d (t=%d)", mp, sm.w.pr.q[i], q, sm.w.pr.lo[i], sm.w.pr.hi[i], t);
+      MN_WATCH(t, "folded (dies) into %d", u);
+      im.rec_val[u] = make_float4(sm.w.pr.oml[i], sm.w.pr.same[i], q, mp);
+      im.rec_diff[u] = sm.w.pr.diff[i];
+      im.rec_lh[t] = make_int2(-1, -1);  // cc:694
       mn_clear_live(im, A, t);
-      if (mp >= 0.0f) mn_push_entry(sm, mp, sm.pr_lo[i], sm.pr_hi[i], u);             // cc:696-698
-    } else {
-      im.rec_lh[t] = make_int2(sm.pr_lo[i], sm.pr_hi[i]);                             // cc:659-664,677
-      im.rec_val[t] = make_float4(sm.pr_oml[i], sm.pr_same[i], sm.pr_diff[i], mp);    // cc:703
-      mn_hash_insert(im, sm.pr_lo[i], sm.pr_hi[i], t);                                // cc:700-702
-      if (mp >= 0.0f) mn_push_entry(sm, mp, sm.pr_lo[i], sm.pr_hi[i], t);             // cc:704-706
+    } else {  // cc:659-664,677,700-706: t is re-keyed to (survivor, x)
+      float q = mn_store_priority(sm, mp, sm.w.pr.q[i], sm.w.pr.lo[i], sm.w.pr.hi[i], t);
+      MN_WATCH(t, "adopt mp %.9g q_old %.9g q_new %.9g key %d %d", mp, sm.w.pr.q[i], q, sm.w.pr.lo[i], sm.w.pr.hi[i]);
+      im.rec_lh[t] = make_int2(sm.w.pr.lo[i], sm.w.pr.hi[i]);
+      im.rec_val[t] = make_float4(sm.w.pr.oml[i], sm.w.pr.same[i], q, mp);
+      mn_hash_insert_hint(im, sm, sm.w.pr.lo[i], sm.w.pr.hi[i], t, sm.w.pr.islot[i]);
     }
   }
 }
 
-// pixel-list chunk from the per-round cache (filled by thread 0 before the commit phase)
-MN_D int mn_plc_take(const MnImage& im, MnSm& sm) {
-  int i = MN_ATOMIC_ADD(&sm.plcache_used, 1);
-  if (i >= sm.plcache_n) { mn_fail(im, MN_ERR_PL_POOL); return -1; }
-  return sm.plcache[i];
-}
-MN_D void mn_plc_free(const MnImage& im, int c) {
-  int t = MN_ATOMIC_ADD(&im.ctl->plc_free_top, 1);
-  im.plc_free[t] = c;
-}
-MN_D void mn_plc_cache_fill(const MnImage& im, MnSm& sm) {  // thread 0, between phases
-  int keep = 0;
-  for (int i = sm.plcache_used; i < sm.plcache_n; i++) sm.plcache[keep++] = sm.plcache[i];
-  while (keep < MN_PLCACHE) {
-    int c;
-    if (im.ctl->plc_free_top > 0) c = im.plc_free[--im.ctl->plc_free_top];
-    else if (im.ctl->plc_bump < im.plc_cap) c = im.ctl->plc_bump++;
-    else break;
-    sm.plcache[keep++] = c;
-  }
-  sm.plcache_n = keep;
-  sm.plcache_used = 0;
-}
-
-// append pixel `pix` to object a's pixel list
-MN_D void mn_pl_append(const MnImage& im, MnSm& sm, int a, int pix) {
-  int tail = im.pl_tail[a];
-  if (tail < 0 || im.plc_cnt[tail] >= MN_PLC) {
-    int c = mn_plc_take(im, sm);
-    if (c < 0) return;
-    im.plc_next[c] = -1;
-    im.plc_cnt[c] = 0;
-    if (tail >= 0) im.plc_next[tail] = c; else im.pl_head[a] = c;
-    im.pl_tail[a] = c;
-    tail = c;
-  }
-  im.plc_pix[(size_t)tail * MN_PLC + im.plc_cnt[tail]] = pix;
-  im.plc_cnt[tail]++;
-}
-
-// cc:635-647 for candidate j: object-level part of Merge (one thread)
+// cc:635-647 for accepted merge candidate j: object-level part of Merge (one thread)
 MN_D void mn_commit_merge_object(const MnImage& im, MnSm& sm, const MnMergeArgs& A, int j) {
   int a = sm.c_surv[j], b = sm.c_abs[j], r = sm.c_rec[j];
-  int nb = mn_nc_npix(im.obj_nc[b]);
-  im.obj_nc[a] = mn_pack_nc(sm.c_na[j], sm.c_merged[j]);                                  // cc:635-639
-  im.obj_same[a] = MN_FADD(im.obj_same[a], MN_FADD(sm.c_rsame[j], im.obj_same[b]));       // cc:641-642
-  im.parent[b] = a;                                                                       // cc:724-725
-  mn_hash_erase(im, sm.c_lo[j], sm.c_hi[j], r);                                           // cc:645-647
-  im.rec_lh[r] = make_int2(-1, -1);                                                       // cc:726
+  im.obj[a] = make_uint4(mn_pack_nc(sm.c_na[j], sm.c_merged[j]), mn_f2u(sm.c_same[j]), (uint32_t)sm.c_newptr[j], 0u);  // cc:635-642
+  im.parent[b] = a;                                                                                                 // cc:724-725
+  if (sm.c_eslot[j] >= 0) im.hash[sm.c_eslot[j]] = 0;                                                               // cc:645-647
+  else mn_ovf_erase(sm, r);
+  im.rec_lh[r] = make_int2(-1, -1);                                                                                 // cc:726
   mn_clear_live(im, A, r);
-  // pixel-set union (cc:636-639): b's root pixel and its chunks join a's list
-  int bh = im.pl_head[b];
-  int at = im.pl_tail[a];
-  int room = at >= 0 ? MN_PLC - im.plc_cnt[at] : 0;
-  if (bh < 0) {
-    mn_pl_append(im, sm, a, b);
-  } else if (nb <= room || (nb <= MN_PLC && nb <= 8)) {
-    // small object: copy its pixels, recycle its chunks
-    mn_pl_append(im, sm, a, b);
-    for (int c = bh; c >= 0;) {
-      int n = im.plc_cnt[c];
-      for (int s = 0; s < n; s++) mn_pl_append(im, sm, a, im.plc_pix[(size_t)c * MN_PLC + s]);
-      int nx = im.plc_next[c];
-      mn_plc_free(im, c);
-      c = nx;
-    }
-  } else {
-    mn_pl_append(im, sm, b, b);  // b's own root pixel goes to the end of b's list
-    if (at >= 0) im.plc_next[at] = im.pl_head[b]; else im.pl_head[a] = im.pl_head[b];
-    im.pl_tail[a] = im.pl_tail[b];
-  }
-  im.pl_head[b] = -1;
-  im.pl_tail[b] = -1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -947,141 +1105,230 @@ MN_D void mn_hot_update(const MnImage& im, MnSm& sm, int cut) {
 // ------------------------------------------------------------------------------------------------
 // round phases
 
-// Phase 1: validate + classify candidate j (cc:554-561).  One thread per candidate.
-MN_D void mn_classify(const MnImage& im, MnSm& sm, const MnMergeArgs& A, int j) {
-  float mp = HOT_MP(j); int lo = HOT_LO(j), hi = HOT_HI(j), rec = HOT_REC(j);
-  sm.c_rec[j] = rec; sm.c_key[j] = mp; sm.c_lo[j] = lo; sm.c_hi[j] = hi;
-  sm.c_kind[j] = 0; sm.c_npairs[j] = 0; sm.c_pfill[j] = 0; sm.c_maxnew[j] = 0; sm.c_conflict[j] = 0;
-  sm.c_npix[j] = 0; sm.c_accept[j] = 0;
-  int2 lh = im.rec_lh[rec];
-  float4 v = im.rec_val[rec];
-  bool valid = (lh.x == lo && lh.y == hi && v.w == mp);
-  if (j > 0 && HOT_REC(j - 1) == rec && HOT_MP(j - 1) == mp && HOT_LO(j - 1) == lo && HOT_HI(j - 1) == hi) valid = false;
-  if (!valid) return;
-  uint32_t nc1 = im.obj_nc[lo], nc2 = im.obj_nc[hi];
-  int n1 = mn_nc_npix(nc1), n2 = mn_nc_npix(nc2), cl1 = mn_nc_cls(nc1), cl2 = mn_nc_cls(nc2);
+// Stage everything the classification of the first n hot entries needs: one dependent round trip.
+// c_clp holds per candidate [lo vector | hi vector | merged vector], C floats each.
+MN_D void mn_stage_candidates(const MnImage& im, MnSm& sm, const MnMergeArgs& A, float* c_clp, int n) {
+  MN_FOR(w, n * 8) {
+    const int j = w >> 3, role = w & 7;
+    const int rec = HOT_REC(j), lo = HOT_LO(j), hi = HOT_HI(j);
+    if (role == 0) {
+      sm.c_val[j] = im.rec_val[rec];
+      sm.c_rec[j] = rec; sm.c_key[j] = HOT_MP(j); sm.c_lo[j] = lo; sm.c_hi[j] = hi;
+      sm.c_kind[j] = MN_K_DROP; sm.c_npairs[j] = 0; sm.c_pfill[j] = 0; sm.c_maxnew[j] = 0; sm.c_conflict[j] = 0;
+      sm.c_nb[j] = 0; sm.c_accept[j] = 0; sm.c_cpbase[j] = -1;
+    } else if (role == 1) {
+      sm.c_lh[j] = im.rec_lh[rec];
+      sm.c_rdiff[j] = im.rec_diff[rec];
+    } else if (role == 2) sm.c_obj[j][0] = im.obj[lo];
+    else if (role == 3) sm.c_obj[j][1] = im.obj[hi];
+    else if (role == 4) {
+      sm.c_lm[j][0] = im.live_mask[lo];
+      // duplicates of an earlier window entry: bit 0 same record and priority, bit 1 also the same key
+      const float mp = HOT_MP(j);
+      int d = 0;
+      for (int i = 0; i < j; i++) {
+        const bool same = HOT_REC(i) == rec && HOT_MP(i) == mp;
+        d |= same ? (1 | ((HOT_LO(i) == lo && HOT_HI(i) == hi) ? 2 : 0)) : 0;
+      }
+      sm.c_dup[j] = d;
+    }
+    else if (role == 5) sm.c_lm[j][1] = im.live_mask[hi];
+    else {
+      MnHashPos p = mn_hash_pos(im.hash_nbuckets, lo, hi);
+      mn_load_bucket4(im, role == 6 ? p.b1 : p.b2, &sm.c_hb[j][role == 6 ? 0 : 8]);
+    }
+  }
+  const int C = A.C;
+  const int total = n * 2 * C;
+  for (int w0 = MN_TID; w0 < total; w0 += 4 * MN_NT) {  // loads first, then stores: one round trip
+    float v[4]; int dst[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int w = w0 + q * MN_NT;
+      dst[q] = -1;
+      if (w < total) {
+        const int j = w / (2 * C), rem = w - j * 2 * C;
+        const int side = rem / C, c = rem - side * C;
+        const int o = side ? HOT_HI(j) : HOT_LO(j);
+        v[q] = im.clp[(size_t)o * C + c];
+        dst[q] = (j * 3 + side) * C + c;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) if (dst[q] >= 0) c_clp[dst[q]] = v[q];
+  }
+}
+
+// Classify candidate j from the staged data (cc:554-561).  One thread per candidate.
+MN_D void mn_classify(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const float* c_clp, int j) {
+  const float mp = sm.c_key[j]; const int lo = sm.c_lo[j], hi = sm.c_hi[j], rec = sm.c_rec[j];
+  const int2 lh = sm.c_lh[j];
+  const float4 v = sm.c_val[j];
+  int st = mn_entry_state(mp, lo, hi, lh, v);
+  // a duplicate of an earlier window entry (same record, same priority; same key if exact)?
+  if (st != MN_K_DROP && (sm.c_dup[j] & (st == MN_K_RESTORE ? 2 : 1))) st = MN_K_DROP;
+  if (st != MN_K_RESTORE) {
+    sm.c_kind[j] = st;
+    if (st == MN_K_REQUEUE) sm.c_maxnew[j] = mn_f2u(v.w) + 1u;
+    // a guard touches its record, whose endpoints may have moved since the entry was queued
+    if (st != MN_K_DROP) { sm.c_lo[j] = lh.x; sm.c_hi[j] = lh.y; }
+    return;
+  }
+  const uint4 o1 = sm.c_obj[j][0], o2 = sm.c_obj[j][1];
+  const int n1 = mn_nc_npix(o1.x), n2 = mn_nc_npix(o2.x), cl1 = mn_nc_cls(o1.x), cl2 = mn_nc_cls(o2.x);
   int merged;
-  float nmp = mn_priority(v.x, A.omf, A.mlb, A.C, n1, cl1, im.clp + (size_t)lo * A.C, n2, cl2,
-                          im.clp + (size_t)hi * A.C, &merged);  // cc:560
+  const float nmp = mn_priority(v.x, A.omf, A.mlb, A.C, n1, cl1, c_clp + (size_t)(j * 3) * A.C, n2, cl2,
+                                c_clp + (size_t)(j * 3 + 1) * A.C, &merged);  // cc:560
   sm.c_newmp[j] = nmp;
   sm.c_merged[j] = merged;
   if (nmp == mp) {  // cc:561-562 -> Merge; cc:612-616: the larger object survives, lower id on ties
-    sm.c_kind[j] = 2;
-    int a = lo, b = hi;
-    if (n1 < n2) { a = hi; b = lo; }
-    sm.c_surv[j] = a; sm.c_abs[j] = b; sm.c_na[j] = n1 + n2;
-    sm.c_npix[j] = (a == lo) ? n2 : n1;
-    sm.c_rsame[j] = v.y;
+    sm.c_kind[j] = MN_K_MERGE;
+    const bool swap = n1 < n2;
+    sm.c_surv[j] = swap ? hi : lo; sm.c_abs[j] = swap ? lo : hi;
+    sm.c_na[j] = n1 + n2; sm.c_nb[j] = swap ? n1 : n2;
+    const uint4 oa = swap ? o2 : o1, ob = swap ? o1 : o2;
+    sm.c_ptra[j] = (int)oa.z; sm.c_ptrb[j] = (int)ob.z;
+    sm.c_same[j] = MN_FADD(mn_u2f(oa.y), MN_FADD(v.y, mn_u2f(ob.y)));  // cc:641-642
+    MnHashPos p = mn_hash_pos(im.hash_nbuckets, lo, hi);
+    sm.c_eslot[j] = mn_bucket_find_val(p, sm.c_hb[j], (p.fp << MN_HASH_FP_SHIFT) | (uint32_t)(rec + 1));
   } else {  // cc:563-565
-    sm.c_kind[j] = 1;
+    sm.c_kind[j] = MN_K_RESTORE;
     if (nmp >= 0.0f) sm.c_maxnew[j] = mn_f2u(nmp) + 1u;
   }
 }
 
-// expand the pixel-list chunks [c0..] of candidate j's absorbed object into pw (root pixel first)
-MN_D void mn_expand_pixels(const MnImage& im, MnSm& sm, int ncw) {
-  MN_FOR(i, ncw * MN_PLC) {
-    int w = i / MN_PLC, s = i - w * MN_PLC;
-    int c = sm.cw_chunk[w];
-    if (s < im.plc_cnt[c]) {
-      int p = MN_ATOMIC_ADD(&sm.npw, 1);
-      if (p < MN_PW) { sm.pw_cand[p] = sm.cw_cand[w]; sm.pw_pix[p] = im.plc_pix[(size_t)c * MN_PLC + s]; }
+// merged class vector of the merging candidates [0, n) (cc:640: this += other)
+MN_D void mn_stage_merged_clp(MnSm& sm, const MnMergeArgs& A, float* c_clp, int n) {
+  const int C = A.C;
+  MN_FOR(w, n * C) {
+    const int j = w / C, c = w - j * C;
+    if (sm.c_kind[j] == MN_K_MERGE) {
+      const int sa = sm.c_surv[j] == sm.c_lo[j] ? 0 : 1;
+      c_clp[(size_t)(j * 3 + 2) * C + c] = MN_FADD(c_clp[(size_t)(j * 3 + sa) * C + c], c_clp[(size_t)(j * 3 + 1 - sa) * C + c]);
     }
   }
 }
 
-// live records of pixel p other than the merging record itself
-MN_D uint32_t mn_live_bits(const MnImage& im, const MnMergeArgs& A, int p, int skip_rec) {
-  uint32_t m = im.live_mask[p];
-  uint32_t out = m;
-  while (m) {
-    int bit = 31 - MN_CLZ(m);
-    m &= ~(1u << bit);
-    if (mn_rec_of_bit(A, p, bit) == skip_rec) out &= ~(1u << bit);
-  }
-  return out;
-}
-MN_D int mn_popc(uint32_t x) { int c = 0; while (x) { x &= x - 1; c++; } return c; }
-
-// write the pair list entries of pixel work items [w0, w1)
-MN_D void mn_fill_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, int w0, int w1) {
-  MN_FOR(ii, w1 - w0) {
-    int i = w0 + ii;
-    int j = sm.pw_cand[i], p = sm.pw_pix[i];
-    uint32_t m = mn_live_bits(im, A, p, sm.c_rec[j]);
-    while (m) {
-      int bit = 31 - MN_CLZ(m);
-      m &= ~(1u << bit);
-      int slot = sm.c_pbase[j] + MN_ATOMIC_ADD(&sm.c_pfill[j], 1);
-      if (slot < MN_WL) { sm.pr_cand[slot] = j; sm.pr_t[slot] = mn_rec_of_bit(A, p, bit); }
-    }
+// pixels [i0, i0 + n) of candidate j's absorbed object -> pw slots [s0, s0 + n): pixel, live mask
+// without the merging record's own bits, pair count (one more dependent round trip: array -> masks)
+MN_D void mn_load_pixels(const MnImage& im, MnSm& sm, const MnMergeArgs& A, int j, int i0, int s0, int n) {
+  MN_FOR(k, n) {
+    const int b = sm.c_abs[j];
+    int pix; uint32_t m;
+    if (sm.c_nb[j] == 1) { pix = b; m = sm.c_lm[j][b == sm.c_lo[j] ? 0 : 1]; }
+    else { pix = im.pix_pool[sm.c_ptrb[j] + i0 + k]; m = im.live_mask[pix]; }
+    m &= ~mn_own_bits(A, pix, sm.c_rec[j]);
+    const int cnt = MN_POPC(m);
+    sm.pw_pix[s0 + k] = pix; sm.pw_mask[s0 + k] = m; sm.pw_cand[s0 + k] = j; sm.pw_cnt[s0 + k] = cnt;
+    if (cnt) MN_ATOMIC_ADD(&sm.c_npairs[j], cnt);
   }
 }
 
-// post-merge class vector of candidate j's survivor (cc:640: this += other)
-MN_D void mn_stage_clp(const MnImage& im, MnSm& sm, const MnMergeArgs& A, float* c_clp, int j0, int j1) {
-  MN_FOR(i, (j1 - j0) * A.C) {
-    int j = j0 + i / A.C, c = i % A.C;
-    if (sm.c_kind[j] == 2)
-      c_clp[(size_t)j * A.C + c] = MN_FADD(im.clp[(size_t)sm.c_surv[j] * A.C + c], im.clp[(size_t)sm.c_abs[j] * A.C + c]);
+// survivor pixel arrays of the accepted merges: copy the arrays that move, append the absorbed pixels
+MN_D void mn_commit_pixels(const MnImage& im, MnSm& sm, int npw) {
+  const int ncp = sm.ncp;
+  const int ncopy = sm.cp_base[ncp];
+  MN_FOR(i, ncopy) {
+    int e = 0;
+    while (e + 1 < ncp && sm.cp_base[e + 1] <= i) e++;
+    const int j = sm.cp_list[e], idx = i - sm.cp_base[e];
+    const int n_a = sm.c_na[j] - sm.c_nb[j];
+    const int src = n_a == 1 ? sm.c_surv[j] : im.pix_pool[sm.c_ptra[j] + idx];
+    im.pix_pool[sm.c_newptr[j] + idx] = src;
+  }
+  MN_FOR(i, npw) {
+    const int j = sm.pw_cand[i];
+    if (!sm.c_accept[j]) continue;
+    const int n_a = sm.c_na[j] - sm.c_nb[j];
+    im.pix_pool[sm.c_newptr[j] + n_a + (i - sm.c_pwbase[j])] = sm.pw_pix[i];
   }
 }
 
-// Solo mode: the first valid candidate f is a merge whose absorbed object does not fit the work
+// pixel array of the survivor of merge candidate j (thread 0): keep it when the merged object still
+// fits its capacity class, otherwise take a fresh array and schedule the copy
+MN_D void mn_alloc_pixels(const MnImage& im, MnSm& sm, int j) {
+  const int na = sm.c_na[j], n_a = na - sm.c_nb[j];
+  const int capn = mn_pix_cap(na), capo = mn_pix_cap(n_a);
+  if (capn != capo) {
+    int ptr = sm.pix_bump;
+    if (ptr + capn > im.pix_cap) { mn_fail(im, MN_ERR_PL_POOL); ptr = 0; }
+    else sm.pix_bump = ptr + capn;
+    sm.c_newptr[j] = ptr;
+    sm.cp_list[sm.ncp] = j; sm.cp_base[sm.ncp + 1] = sm.cp_base[sm.ncp] + n_a; sm.ncp++;
+  } else {
+    sm.c_newptr[j] = sm.c_ptra[j];
+  }
+}
+
+// Solo mode: the first live candidate f is a merge whose absorbed object does not fit the work
 // lists.  It is the next event of the sequential order whatever else is queued, so it is planned
 // and committed in slices, alone.
 MN_D void mn_solo_merge(const MnImage& im, MnSm& sm, const MnMergeArgs& A, float* c_clp, int f) {
-  // candidate f becomes candidate 0 of a one-member round
   MN_SYNC();
-  if (MN_T0) {
-    sm.c_rec[0] = sm.c_rec[f]; sm.c_key[0] = sm.c_key[f]; sm.c_lo[0] = sm.c_lo[f]; sm.c_hi[0] = sm.c_hi[f];
-    sm.c_kind[0] = 2; sm.c_newmp[0] = sm.c_newmp[f]; sm.c_merged[0] = sm.c_merged[f];
-    sm.c_surv[0] = sm.c_surv[f]; sm.c_abs[0] = sm.c_abs[f]; sm.c_na[0] = sm.c_na[f];
-    sm.c_rsame[0] = sm.c_rsame[f]; sm.c_npix[0] = sm.c_npix[f]; sm.c_accept[0] = 1;
-    sm.c_maxnew[0] = 0; sm.c_pbase[0] = 0;
-    sm.st_solo++; sm.st_events++; sm.st_merges++;
-    sm.nne = 0;
+  const int C = A.C;
+  // candidate f becomes candidate 0 of a one-member round
+  if (f != 0) {
+    MN_FOR(c, 3 * C) c_clp[c] = c_clp[(size_t)f * 3 * C + c];
+    if (MN_T0) {
+      sm.c_rec[0] = sm.c_rec[f]; sm.c_key[0] = sm.c_key[f]; sm.c_lo[0] = sm.c_lo[f]; sm.c_hi[0] = sm.c_hi[f];
+      sm.c_newmp[0] = sm.c_newmp[f]; sm.c_merged[0] = sm.c_merged[f];
+      sm.c_surv[0] = sm.c_surv[f]; sm.c_abs[0] = sm.c_abs[f]; sm.c_na[0] = sm.c_na[f]; sm.c_nb[0] = sm.c_nb[f];
+      sm.c_ptra[0] = sm.c_ptra[f]; sm.c_ptrb[0] = sm.c_ptrb[f]; sm.c_same[0] = sm.c_same[f]; sm.c_eslot[0] = sm.c_eslot[f];
+      sm.c_lm[0][0] = sm.c_lm[f][0]; sm.c_lm[0][1] = sm.c_lm[f][1];
+    }
   }
   MN_SYNC();
-  mn_hot_update(im, sm, f + 1);  // drop the consumed prefix (invalid entries and f itself)
-  mn_stage_clp(im, sm, A, c_clp, 0, 1);
+  if (MN_T0) {
+    sm.c_kind[0] = MN_K_MERGE; sm.c_accept[0] = 1; sm.c_maxnew[0] = 0; sm.c_pbase[0] = 0; sm.c_pwbase[0] = 0;
+    // entries of the consumed prefix that forget their guard
+    sm.st_solo++; sm.st_events++; sm.st_merges++; sm.st_rounds++;
+    sm.nne = 0;
+    sm.ncp = 0; sm.cp_base[0] = 0;
+    mn_alloc_pixels(im, sm, 0);
+  }
   MN_SYNC();
-  const int b = sm.c_abs[0];
-  int chunk = im.pl_head[b];
-  bool first = true;
-  for (int guard = 0; guard < (1 << 26); guard++) {
+  mn_hot_update(im, sm, f + 1);  // drop the consumed prefix (stale entries and f itself)
+  {  // move the survivor's pixel array if it must grow
+    const int ncopy = sm.cp_base[sm.ncp];
+    const int n_a = sm.c_na[0] - sm.c_nb[0];
+    MN_FOR(i, ncopy) im.pix_pool[sm.c_newptr[0] + i] = n_a == 1 ? sm.c_surv[0] : im.pix_pool[sm.c_ptra[0] + i];
+  }
+  MN_SYNC();
+  const int nb = sm.c_nb[0];
+  const int n_a = sm.c_na[0] - nb;
+  for (int base = 0; base < nb; base += MN_PW) {
+    const int cnt = nb - base < MN_PW ? nb - base : MN_PW;
+    if (MN_T0) sm.c_npairs[0] = 0;
     MN_SYNC();
-    // ---- next slice of pixels: up to MN_PW / MN_PLC - 1 chunks (+ the root pixel once) ----
-    if (MN_T0) {
-      sm.npw = 0; sm.ncw = 0;
-      if (first) { sm.pw_cand[0] = 0; sm.pw_pix[0] = b; sm.npw = 1; }
-      int c = chunk;
-      while (c >= 0 && sm.ncw < MN_PW / MN_PLC - 1) { sm.cw_cand[sm.ncw] = 0; sm.cw_chunk[sm.ncw] = c; sm.ncw++; c = im.plc_next[c]; }
-      sm.tmp1 = c;
-    }
+    mn_load_pixels(im, sm, A, 0, base, 0, cnt);
     MN_SYNC();
-    chunk = sm.tmp1;
-    first = false;
-    mn_expand_pixels(im, sm, sm.ncw);
-    MN_SYNC();
-    const int npw = sm.npw;
-    if (npw == 0) break;
-    // ---- sub-slices of at most MN_WL pairs ----
+    MN_FOR(i, cnt) im.pix_pool[sm.c_newptr[0] + n_a + base + i] = sm.pw_pix[i];
+    mn_exclusive_scan(sm, sm.pw_cnt, sm.pw_off, cnt);
+    // sub-slices of at most MN_WL pairs
     int w0 = 0;
-    while (w0 < npw) {
+    while (w0 < cnt) {
       MN_SYNC();
       if (MN_T0) {
-        int tot = 0, w = w0;
-        while (w < npw) {
-          int c = mn_popc(mn_live_bits(im, A, sm.pw_pix[w], sm.c_rec[0]));
-          if (tot + c > MN_WL) break;
-          tot += c; w++;
-        }
-        sm.tmp2 = w; sm.tmp3 = tot; sm.c_pfill[0] = 0;
+        const int o0 = sm.pw_off[w0];
+        int a = w0, bnd = cnt;  // last w with off[w] + cnt[w] - o0 <= MN_WL
+        while (a < bnd) { int mid = (a + bnd) >> 1; if (sm.pw_off[mid] + sm.pw_cnt[mid] - o0 <= MN_WL) a = mid + 1; else bnd = mid; }
+        sm.tmp2 = a; sm.tmp3 = (a < cnt ? sm.pw_off[a] : sm.pw_off[cnt - 1] + sm.pw_cnt[cnt - 1]) - o0;
       }
       MN_SYNC();
       const int w1 = sm.tmp2, npr = sm.tmp3;
-      mn_fill_pairs(im, sm, A, w0, w1);
+      if (w1 == w0) { mn_fail(im, MN_ERR_INTERNAL); return; }
+      const int o0 = sm.pw_off[w0];
+      MN_FOR(ii, w1 - w0) {
+        const int i = w0 + ii;
+        uint32_t m = sm.pw_mask[i];
+        int slot = sm.pw_off[i] - o0;
+        while (m) {
+          int bit = 31 - MN_CLZ(m);
+          m &= ~(1u << bit);
+          sm.w.pr.cand[slot] = 0; sm.w.pr.t[slot] = mn_rec_of_bit(A, sm.pw_pix[i], bit);
+          slot++;
+        }
+      }
       MN_SYNC();
       mn_plan_pairs(im, sm, A, c_clp, 0, npr);
       MN_SYNC();
@@ -1090,36 +1337,222 @@ MN_D void mn_solo_merge(const MnImage& im, MnSm& sm, const MnMergeArgs& A, float
       if (MN_T0) sm.st_pairs += npr;
       mn_hot_update(im, sm, 0);
       if (sm.nins > MN_IC - MN_NE - 64) mn_flush_ins(im, sm);
-      if (im.ctl->status != MN_OK) return;
+      if (sm.failed) return;
       w0 = w1;
     }
-    if (chunk < 0) break;
+    MN_SYNC();
   }
   MN_SYNC();
-  if (MN_T0) {
-    mn_plc_cache_fill(im, sm);
-    mn_commit_merge_object(im, sm, A, 0);
-  }
-  MN_FOR(c, A.C) im.clp[(size_t)sm.c_surv[0] * A.C + c] = c_clp[c];
+  if (MN_T0) mn_commit_merge_object(im, sm, A, 0);
+  MN_FOR(c, C) im.clp[(size_t)sm.c_surv[0] * C + c] = c_clp[(size_t)2 * C + c];
   MN_SYNC();
 }
 
-// The scheduler for one image.  c_clp: MN_H * C floats of shared memory.
+// consume the non-event entries of the window prefix [0, n): forget guards of dormant records
+MN_D void mn_consume_unguard(const MnImage& im, MnSm& sm, int n) {
+  MN_FOR(j, n) {
+    if (sm.c_kind[j] == MN_K_UNGUARD) {
+      float4 v = sm.c_val[j];
+      v.z = -1.0f;
+      im.rec_val[sm.c_rec[j]] = v;
+    }
+  }
+}
+
+// ---- the three scans over the (<= 32) candidates of a round --------------------------------------
+// On the device they run on warp 0 with one lane per candidate (ballots and shuffles: a thread-0
+// loop over shared memory costs ~30 cycles per access); on the host they are plain loops.
+#if defined(__CUDA_ARCH__)
+MN_D int mn_wscan_incl(int v, int lane) {
+  for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += o; }
+  return v;
+}
+MN_D uint32_t mn_wscan_max_excl(uint32_t v, int lane) {  // exclusive prefix maximum
+  for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d && o > v) v = o; }
+  uint32_t e = __shfl_up_sync(0xffffffffu, v, 1);
+  return lane == 0 ? 0u : e;
+}
+#endif
+
+// Capacity cut of the window [0, n0) by pixels (vals = c_nb) or by pairs (vals = c_npairs) of its
+// merging members: members that do not fit `cap` wait for a later round.  When the first event does not
+// fit on its own it is merged alone, in slices ("solo") -- unless a requeue ahead of it may put
+// another record in front, in which case this round only consumes that prefix.
+// Writes: base[j] per merging member, sm.ncand, sm.solo, and returns nothing; with `pixels` also the
+// list of merging members (m_list, m_base), sm.first, sm.npw; otherwise sm.npr.
+MN_D void mn_pass_capacity(MnSm& sm, int n0, const int* vals, int* base, int cap, bool pixels) {
+#if defined(__CUDA_ARCH__)
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  const int k = lane < n0 ? sm.c_kind[lane] : MN_K_DROP;
+  const bool isM = k == MN_K_MERGE;
+  const int v = isM ? vals[lane] : 0;
+  const int incl = mn_wscan_incl(v, lane);
+  const uint32_t evm = __ballot_sync(0xffffffffu, k == MN_K_RESTORE || k == MN_K_MERGE);
+  const uint32_t rqm = __ballot_sync(0xffffffffu, k == MN_K_REQUEUE);
+  const uint32_t mm = __ballot_sync(0xffffffffu, isM);
+  const uint32_t om = __ballot_sync(0xffffffffu, isM && incl > cap);
+  const int f = pixels ? (evm ? __ffs(evm) - 1 : -1) : sm.first;
+  int n = n0, solo = 0;
+  if (om) {
+    const int jo = __ffs(om) - 1;
+    n = jo;
+    const int nrq = __popc(rqm & ((1u << jo) - 1u));
+    solo = (jo == f && nrq == 0) ? 1 : 0;
+  }
+  const uint32_t below = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+  const int tot = n > 0 ? __shfl_sync(0xffffffffu, incl, n - 1) : 0;
+  if (isM && lane < n) {
+    base[lane] = incl - v;
+    if (pixels) { const int mi = __popc(mm & ((1u << lane) - 1u)); sm.m_list[mi] = lane; sm.m_base[mi] = incl - v; }
+  }
+  if (lane == 0) {
+    if (pixels) {
+      const int nm = __popc(mm & below);
+      sm.m_base[nm] = tot; sm.nm = nm; sm.first = f; sm.npw = tot; sm.npr = 0;
+    } else {
+      if (n < n0) sm.st_cut_cap++;
+      sm.npr = tot;
+    }
+    sm.ncand = n; sm.solo = solo;
+  }
+#else
+  int tot = 0, n = 0, f = pixels ? -1 : sm.first, solo = 0, nm = 0, nrq = 0;
+  for (int j = 0; j < n0; j++) {
+    const int k = sm.c_kind[j];
+    if (pixels && (k == MN_K_RESTORE || k == MN_K_MERGE) && f < 0) f = j;
+    if (k == MN_K_REQUEUE) nrq++;
+    if (k == MN_K_MERGE) {
+      if (tot + vals[j] > cap) { if (j == f && nrq == 0) solo = 1; break; }
+      base[j] = tot;
+      if (pixels) { sm.m_list[nm] = j; sm.m_base[nm] = tot; nm++; }
+      tot += vals[j];
+    }
+    n = j + 1;
+  }
+  if (pixels) { sm.m_base[nm] = tot; sm.nm = nm; sm.first = f; sm.npw = tot; sm.npr = 0; }
+  else { if (n < n0) sm.st_cut_cap++; sm.npr = tot; }
+  sm.ncand = n; sm.solo = solo;
+#endif
+}
+
+// Accept the longest provably sequential prefix of the window [0, ncand) (rules (a) and (b) of the
+// header) and give every accepted merge the pixel array of its survivor: the old one when the merged
+// object still fits its capacity class, else a fresh one (cp_list / cp_base schedule the copies).
+MN_D void mn_pass_accept(const MnImage& im, MnSm& sm, int ncand, int npr) {
+#if defined(__CUDA_ARCH__)
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  const int k = lane < ncand ? sm.c_kind[lane] : MN_K_DROP;
+  const bool member = k != MN_K_DROP;
+  const bool event = k == MN_K_RESTORE || k == MN_K_MERGE;
+  const uint32_t memm = __ballot_sync(0xffffffffu, member);
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t exmax = mn_wscan_max_excl(member ? sm.c_maxnew[lane] : 0u, lane);
+  const bool before = (memm & lt) != 0;
+  const bool cconf = member && before && sm.c_conflict[lane] != 0;
+  const bool ccasc = member && before && !cconf && event && exmax != 0 && exmax - 1u >= mn_f2u(sm.c_key[lane]);
+  const uint32_t cm = __ballot_sync(0xffffffffu, cconf || ccasc);
+  const int cut = cm ? __ffs(cm) - 1 : ncand;
+  const bool acc = member && lane < cut;
+  if (lane < ncand) sm.c_accept[lane] = acc ? 1 : 0;
+  const uint32_t below = cut >= 32 ? 0xffffffffu : ((1u << cut) - 1u);
+  const uint32_t accm = memm & below;
+  const uint32_t mergem = __ballot_sync(0xffffffffu, acc && k == MN_K_MERGE);
+  const uint32_t restm = __ballot_sync(0xffffffffu, acc && k == MN_K_RESTORE);
+  const uint32_t reqm = __ballot_sync(0xffffffffu, acc && k == MN_K_REQUEUE);
+  const uint32_t ungm = __ballot_sync(0xffffffffu, acc && k == MN_K_UNGUARD);
+  const uint32_t dropm = __ballot_sync(0xffffffffu, lane < cut && lane < ncand && k == MN_K_DROP);
+  const uint32_t confcut = __ballot_sync(0xffffffffu, cconf && lane == cut);
+  // pixel arrays
+  int need = 0, n_a = 0;
+  if (acc && k == MN_K_MERGE) {
+    const int na = sm.c_na[lane];
+    n_a = na - sm.c_nb[lane];
+    const int capn = mn_pix_cap(na), capo = mn_pix_cap(n_a);
+    if (capn != capo) need = capn;
+  }
+  const int need_incl = mn_wscan_incl(need, lane);
+  const int cp_incl = mn_wscan_incl(need ? n_a : 0, lane);
+  const uint32_t needm = __ballot_sync(0xffffffffu, need != 0);
+  const int total_need = __shfl_sync(0xffffffffu, need_incl, 31);
+  const int total_cp = __shfl_sync(0xffffffffu, cp_incl, 31);
+  const int bump = sm.pix_bump;
+  const bool fits = bump + total_need <= im.pix_cap;
+  if (acc && k == MN_K_MERGE) {
+    if (need) {
+      const int ci = __popc(needm & lt);
+      sm.c_newptr[lane] = fits ? bump + need_incl - need : 0;
+      sm.cp_list[ci] = lane; sm.cp_base[ci] = cp_incl - n_a;
+    } else {
+      sm.c_newptr[lane] = sm.c_ptra[lane];
+    }
+  }
+  if (lane == 0) {
+    const int ncp = __popc(needm);
+    sm.ncp = ncp; sm.cp_base[ncp] = total_cp;
+    if (fits) sm.pix_bump = bump + total_need; else mn_fail(im, MN_ERR_PL_POOL);
+    sm.cutpos = cut; sm.nacc = __popc(accm);
+    sm.st_merges += __popc(mergem); sm.st_restores += __popc(restm); sm.st_requeues += __popc(reqm);
+    sm.st_events += __popc(mergem) + __popc(restm);
+    sm.st_invalid += __popc(ungm) + __popc(dropm);
+    if (cm) { if (confcut) sm.st_cut_conf++; else sm.st_cut_casc++; }
+    sm.st_rounds++; sm.st_pairs += npr;
+  }
+#else
+  uint32_t runmax = 0;  // bits+1 of the largest priority stored by an accepted member
+  int cut = ncand, nacc = 0;
+  sm.ncp = 0; sm.cp_base[0] = 0;
+  for (int j = 0; j < ncand; j++) {
+    const int k = sm.c_kind[j];
+    if (k == MN_K_DROP) { sm.st_invalid++; continue; }
+    const bool event = (k == MN_K_RESTORE || k == MN_K_MERGE);
+    if (sm.c_conflict[j] && nacc > 0) { cut = j; sm.st_cut_conf++; break; }
+    if (event && runmax != 0 && runmax - 1u >= mn_f2u(sm.c_key[j]) && nacc > 0) { cut = j; sm.st_cut_casc++; break; }
+    sm.c_accept[j] = 1;
+    nacc++;
+    if (sm.c_maxnew[j] > runmax) runmax = sm.c_maxnew[j];
+    if (k == MN_K_MERGE) { sm.st_merges++; sm.st_events++; mn_alloc_pixels(im, sm, j); }
+    else if (k == MN_K_RESTORE) { sm.st_restores++; sm.st_events++; }
+    else if (k == MN_K_REQUEUE) sm.st_requeues++;
+    else sm.st_invalid++;
+  }
+  sm.cutpos = cut; sm.nacc = nacc;
+  sm.st_rounds++; sm.st_pairs += npr;
+#endif
+}
+
+// The scheduler for one image.  c_clp: MN_H * 3 * C floats of shared memory.
 MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, float* c_clp) {
   // ---- init ----
   if (MN_T0) {
-    sm.hsel = 0; sm.nhot = 0; sm.nins = 0; sm.nne = 0; sm.cold_empty = 0; sm.plcache_n = 0; sm.plcache_used = 0;
-    sm.b_mp = 0; sm.b_lo = 0; sm.b_hi = 0; sm.path_n = 0;
+    sm.hsel = 0; sm.nhot = 0; sm.nins = 0; sm.nne = 0; sm.cold_empty = 0;
+    sm.b_mp = 0; sm.b_lo = 0; sm.b_hi = 0; sm.path_n = 0; sm.failed = 0;
+    sm.pix_bump = 0; sm.hash_ovf_n = im.ctl->hash_ovf_n;
+    sm.qc_free_top = 0; sm.qc_bump = 0; sm.tn_bump = MN_NROOTS; sm.tree_entries = 0; sm.peak_entries = 0; sm.peak_chunks = 0;
     sm.st_rounds = sm.st_events = sm.st_merges = sm.st_restores = sm.st_invalid = sm.st_solo = 0;
     sm.st_refills = sm.st_flushes = sm.st_splits = sm.st_pairs = sm.st_cut_conf = sm.st_cut_casc = sm.st_cut_cap = 0;
+    sm.st_requeues = 0;
     for (int i = 0; i < MN_NCYC; i++) sm.cyc[i] = 0;
     sm.cyc_t0 = 0;
     // number of real (non-sentinel) initial entries: first index whose key is the sentinel
     long long E = (long long)A.N * A.K;
     long long a = 0, b = E;
     while (a < b) { long long mid = (a + b) >> 1; if (im.init_keys[mid] == ~0ull) b = mid; else a = mid + 1; }
-    im.ctl->n_init = (int)a;
-    im.ctl->static_cursor = 0;
+    sm.n_init = (int)a;
+    sm.static_cursor = 0;
+    if (im.ctl->status != MN_OK) sm.failed = 1;
+  }
+  MN_SYNC();
+  {  // the records record-init could not place in a bucket
+    const int n = sm.hash_ovf_n;
+    if (n > MN_OVF || (uint32_t)n > im.hash_ovf_cap) { if (MN_T0) mn_fail(im, MN_ERR_HASH_FULL); }
+    else MN_FOR(i, n) {
+      const int rec = (int)im.hash_ovf[i] - 1;
+      int2 lh = make_int2(-1, -1);
+      if (rec >= 0) lh = im.rec_lh[rec];
+      sm.ovf_lo[i] = lh.x; sm.ovf_hi[i] = lh.y; sm.ovf_rec[i] = rec;
+    }
   }
   MN_FOR(i, (int)((MN_NROOTS + 31) / 32)) sm.root_bits[i] = 0;
   MN_FOR(i, (int)(((MN_NROOTS + 31) / 32 + 31) / 32)) sm.root_sum[i] = 0;
@@ -1127,174 +1560,149 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
 
   for (long long round = 0;; round++) {
     MN_SYNC();
-    if (im.ctl->status != MN_OK) break;
+    if (sm.failed) break;
     if (A.max_rounds > 0 && round >= A.max_rounds) { if (MN_T0) mn_fail(im, MN_ERR_LIMIT); break; }
     MN_TIC();
     if (sm.nins > MN_IC - MN_NE - 64) { mn_flush_ins(im, sm); MN_TOC(MN_CY_FLUSH); }
     if (sm.nhot == 0) {
       mn_refill(im, sm, A);
       MN_TOC(MN_CY_REFILL);
-      if (im.ctl->status != MN_OK) break;
+      if (sm.failed) break;
       if (sm.nhot == 0) break;  // queue empty: cc:542
     }
-    const int ncand0 = sm.nhot < MN_H ? sm.nhot : MN_H;
-    // ---- phase 1: classify ----
+    const int ncand0 = sm.nhot < A.H ? sm.nhot : A.H;
+    // ---- phase 1: stage (one round trip), classify ----
+    mn_stage_candidates(im, sm, A, c_clp, ncand0);
     MN_FOR(i, MN_CT) { sm.ct_obj[i] = -1; sm.ct_w[i] = INT_MAX; sm.ct_r[i] = INT_MAX; }
-    MN_FOR(j, ncand0) mn_classify(im, sm, A, j);
     MN_SYNC();
-    // ---- phase 2: capacity cut by pixels; chunk lists of the absorbed objects ----
-    if (MN_T0) {
-      int tot = 0, n = 0, f = -1, solo = 0;
-      for (int j = 0; j < ncand0; j++) {
-        if (sm.c_kind[j] != 0 && f < 0) f = j;
-        if (sm.c_kind[j] == 2) {
-          if (tot + sm.c_npix[j] > MN_PW) { if (j == f) solo = 1; break; }
-          tot += sm.c_npix[j];
-        }
-        n = j + 1;
-      }
-      sm.ncand = n; sm.solo = solo; sm.tmp0 = f; sm.ncw = 0; sm.npw = 0; sm.npr = 0;
+    MN_FOR(j, ncand0) mn_classify(im, sm, A, c_clp, j);
+    MN_SYNC();
+    // ---- phase 2: merged class vectors; capacity cut by pixels ----
+    mn_stage_merged_clp(sm, A, c_clp, ncand0);
+    mn_pass_capacity(sm, ncand0, sm.c_nb, sm.c_pwbase, MN_PW, true);
+    MN_SYNC();
+    if (sm.solo) {
+      const int f = sm.first;
+      mn_consume_unguard(im, sm, f);
+      mn_solo_merge(im, sm, A, c_clp, f);
+      MN_TOC(MN_CY_SOLO);
+      continue;
     }
-    MN_SYNC();
-    if (sm.solo) { mn_solo_merge(im, sm, A, c_clp, sm.tmp0); if (MN_T0) sm.st_rounds++; MN_TOC(MN_CY_SOLO); continue; }
-    MN_FOR(j, sm.ncand) {
-      if (sm.c_kind[j] == 2) {
-        int p = MN_ATOMIC_ADD(&sm.npw, 1);
-        sm.pw_cand[p] = j; sm.pw_pix[p] = sm.c_abs[j];
-        for (int c = im.pl_head[sm.c_abs[j]]; c >= 0; c = im.plc_next[c]) {
-          int w = MN_ATOMIC_ADD(&sm.ncw, 1);
-          if (w < MN_CW) { sm.cw_cand[w] = j; sm.cw_chunk[w] = c; }
-        }
-      }
-    }
-    MN_SYNC();
-    if (sm.ncw > MN_CW) {
-      // sparsely filled chunk chains overflowed the chunk work list: shrink the round to its first
-      // valid member (a merge goes through the sliced solo path, which has no such limit)
-      const int f = sm.tmp0;
-      MN_SYNC();
-      if (sm.c_kind[f] == 2) { mn_solo_merge(im, sm, A, c_clp, f); if (MN_T0) sm.st_rounds++; continue; }
-      if (MN_T0) { sm.ncand = f + 1; sm.ncw = 0; sm.npw = 0; sm.st_cut_cap++; }
-      MN_SYNC();
-    }
-    mn_expand_pixels(im, sm, sm.ncw);
-    MN_SYNC();
-    // ---- phase 3: count pairs, capacity cut by pairs ----
-    MN_FOR(i, sm.npw) {
-      int j = sm.pw_cand[i];
-      int c = mn_popc(mn_live_bits(im, A, sm.pw_pix[i], sm.c_rec[j]));
-      if (c) MN_ATOMIC_ADD(&sm.c_npairs[j], c);
-    }
-    MN_SYNC();
-    if (MN_T0) {
-      int tot = 0, n = 0, f = sm.tmp0, solo = 0;
-      for (int j = 0; j < sm.ncand; j++) {
-        if (sm.c_kind[j] == 2) {
-          if (tot + sm.c_npairs[j] > MN_WL) { if (j == f) solo = 1; break; }
-          sm.c_pbase[j] = tot;
-          tot += sm.c_npairs[j];
-        }
-        n = j + 1;
-      }
-      if (n < sm.ncand) sm.st_cut_cap++;
-      sm.ncand = n; sm.npr = tot; sm.solo = solo;
-    }
-    MN_SYNC();
-    if (sm.solo) { mn_solo_merge(im, sm, A, c_clp, sm.tmp0); if (MN_T0) sm.st_rounds++; MN_TOC(MN_CY_SOLO); continue; }
-    const int ncand = sm.ncand, npr = sm.npr;
-    // ---- phase 4: pair lists + staged class vectors ----
+    // ---- phase 3: pixels of the absorbed objects, their live masks, pair counts ----
     {
-      // only pixels of candidates inside the cut contribute
-      MN_FOR(ii, sm.npw) {
-        int j = sm.pw_cand[ii];
-        if (j >= ncand) continue;
-        int p = sm.pw_pix[ii];
-        uint32_t m = mn_live_bits(im, A, p, sm.c_rec[j]);
-        while (m) {
-          int bit = 31 - MN_CLZ(m);
-          m &= ~(1u << bit);
-          int slot = sm.c_pbase[j] + MN_ATOMIC_ADD(&sm.c_pfill[j], 1);
-          if (slot < MN_WL) { sm.pr_cand[slot] = j; sm.pr_t[slot] = mn_rec_of_bit(A, p, bit); }
-        }
+      const int npw = sm.npw, nm = sm.nm;
+      MN_FOR(i, npw) {
+        int a = 0, bnd = nm;  // last e with m_base[e] <= i
+        while (a + 1 < bnd) { int mid = (a + bnd) >> 1; if (sm.m_base[mid] <= i) a = mid; else bnd = mid; }
+        const int j = sm.m_list[a], idx = i - sm.m_base[a];
+        const int b = sm.c_abs[j];
+        int pix; uint32_t m;
+        if (sm.c_nb[j] == 1) { pix = b; m = sm.c_lm[j][b == sm.c_lo[j] ? 0 : 1]; }
+        else { pix = im.pix_pool[sm.c_ptrb[j] + idx]; m = im.live_mask[pix]; }
+        m &= ~mn_own_bits(A, pix, sm.c_rec[j]);
+        const int cnt = MN_POPC(m);
+        sm.pw_pix[i] = pix; sm.pw_mask[i] = m; sm.pw_cand[i] = j; sm.pw_cnt[i] = cnt;
+        if (cnt) MN_ATOMIC_ADD(&sm.c_npairs[j], cnt);
       }
     }
-    mn_stage_clp(im, sm, A, c_clp, 0, ncand);
+    MN_SYNC();
+    mn_pass_capacity(sm, sm.ncand, sm.c_npairs, sm.c_pbase, MN_WL, false);  // capacity cut by pairs
+    MN_SYNC();
+    if (sm.solo) {
+      const int f = sm.first;
+      mn_consume_unguard(im, sm, f);
+      mn_solo_merge(im, sm, A, c_clp, f);
+      MN_TOC(MN_CY_SOLO);
+      continue;
+    }
+    const int ncand = sm.ncand, npr = sm.npr, npw = sm.npw;
+    MN_FOR(i, npw) {
+      const int j = sm.pw_cand[i];
+      if (j >= ncand) continue;
+      uint32_t m = sm.pw_mask[i];
+      const int cnt = sm.pw_cnt[i];
+      if (!cnt) continue;
+      int slot = sm.c_pbase[j] + MN_ATOMIC_ADD(&sm.c_pfill[j], cnt);
+      while (m) {
+        int bit = 31 - MN_CLZ(m);
+        m &= ~(1u << bit);
+        sm.w.pr.cand[slot] = j; sm.w.pr.t[slot] = mn_rec_of_bit(A, sm.pw_pix[i], bit);
+        slot++;
+      }
+    }
     MN_SYNC();
     MN_TOC(MN_CY_SELECT);
-    // ---- phase 5: plan ----
+    // ---- phase 4: plan ----
     mn_plan_pairs(im, sm, A, c_clp, 0, npr);
     MN_SYNC();
     MN_TOC(MN_CY_PLAN);
-    // ---- phase 6: footprints into the conflict table ----
+    // ---- phase 5: footprints into the conflict table ----
     MN_FOR(j, ncand) {
-      if (sm.c_kind[j] == 0) continue;
+      const int k = sm.c_kind[j];
+      if (k == MN_K_DROP) continue;
       int s1 = mn_ct_slot(sm, sm.c_lo[j]), s2 = mn_ct_slot(sm, sm.c_hi[j]);
       if (s1 < 0 || s2 < 0) { sm.c_conflict[j] = 1; continue; }
-      if (sm.c_kind[j] == 2) { MN_ATOMIC_MIN(&sm.ct_w[s1], j); MN_ATOMIC_MIN(&sm.ct_w[s2], j); }
+      if (k == MN_K_MERGE) { MN_ATOMIC_MIN(&sm.ct_w[s1], j); MN_ATOMIC_MIN(&sm.ct_w[s2], j); }
       else { MN_ATOMIC_MIN(&sm.ct_r[s1], j); MN_ATOMIC_MIN(&sm.ct_r[s2], j); }
     }
     MN_FOR(i, npr) {
-      int s = mn_ct_slot(sm, sm.pr_x[i]);
-      if (s < 0) sm.c_conflict[sm.pr_cand[i]] = 1; else MN_ATOMIC_MIN(&sm.ct_r[s], sm.pr_cand[i]);
+      int s = mn_ct_slot(sm, sm.w.pr.x[i]);
+      if (s < 0) sm.c_conflict[sm.w.pr.cand[i]] = 1; else MN_ATOMIC_MIN(&sm.ct_r[s], sm.w.pr.cand[i]);
     }
     MN_SYNC();
     MN_FOR(j, ncand) {
-      if (sm.c_kind[j] == 0) continue;
+      const int k = sm.c_kind[j];
+      if (k == MN_K_DROP) continue;
       int s1 = mn_ct_find(sm, sm.c_lo[j]), s2 = mn_ct_find(sm, sm.c_hi[j]);
       bool cf = false;
-      if (s1 >= 0) cf = cf || sm.ct_w[s1] < j || (sm.c_kind[j] == 2 && sm.ct_r[s1] < j);
-      if (s2 >= 0) cf = cf || sm.ct_w[s2] < j || (sm.c_kind[j] == 2 && sm.ct_r[s2] < j);
+      if (s1 >= 0) cf = cf || sm.ct_w[s1] < j || (k == MN_K_MERGE && sm.ct_r[s1] < j);
+      if (s2 >= 0) cf = cf || sm.ct_w[s2] < j || (k == MN_K_MERGE && sm.ct_r[s2] < j);
       if (cf) sm.c_conflict[j] = 1;
     }
     MN_FOR(i, npr) {
-      int s = mn_ct_find(sm, sm.pr_x[i]);
-      if (s >= 0 && sm.ct_w[s] < sm.pr_cand[i]) sm.c_conflict[sm.pr_cand[i]] = 1;
+      int s = mn_ct_find(sm, sm.w.pr.x[i]);
+      if (s >= 0 && sm.ct_w[s] < sm.w.pr.cand[i]) sm.c_conflict[sm.w.pr.cand[i]] = 1;
     }
     MN_SYNC();
-    // ---- phase 7: accept the longest provably sequential prefix ----
-    if (MN_T0) {
-      uint32_t runmax = 0;  // bits+1 of the largest priority created by an accepted member
-      int cut = ncand, nacc = 0;
-      for (int j = 0; j < ncand; j++) {
-        if (sm.c_kind[j] == 0) { sm.st_invalid++; continue; }
-        if (sm.c_conflict[j] && nacc > 0) { cut = j; sm.st_cut_conf++; break; }
-        if (runmax != 0 && runmax - 1u >= mn_f2u(sm.c_key[j]) && nacc > 0) { cut = j; sm.st_cut_casc++; break; }
-        sm.c_accept[j] = 1;
-        nacc++;
-        if (sm.c_maxnew[j] > runmax) runmax = sm.c_maxnew[j];
-        if (sm.c_kind[j] == 2) sm.st_merges++; else sm.st_restores++;
-      }
-      // invalid entries counted past the cut were not consumed
-      sm.cutpos = cut; sm.nacc = nacc;
-      sm.st_events += nacc; sm.st_rounds++; sm.st_pairs += npr;
-      mn_plc_cache_fill(im, sm);
-    }
+    // ---- phase 6: accept the longest provably sequential prefix ----
+    mn_pass_accept(im, sm, ncand, npr);
     MN_SYNC();
 #ifdef MN_EMUL_TRACE
     fprintf(stderr, "round: ncand %d nacc %d cut %d nhot %d nins %d npr %d cold_empty %d key0 %.9g\n", ncand, sm.nacc, sm.cutpos, sm.nhot, sm.nins, npr, sm.cold_empty, sm.c_key[0]);
 #endif
     MN_TOC(MN_CY_ACCEPT);
-    // ---- phase 8: commit ----
+    // ---- phase 7: commit ----
     MN_FOR(j, ncand) {
       if (!sm.c_accept[j]) continue;
-      if (sm.c_kind[j] == 1) {  // cc:563-565
-        int rec = sm.c_rec[j];
-        float4 v = im.rec_val[rec];
+      const int k = sm.c_kind[j];
+      const int rec = sm.c_rec[j];
+      MN_WATCH(rec, "commit cand j=%d kind %d key %.9g (%d,%d) val mp %.9g q %.9g newmp %.9g", j, k, sm.c_key[j], sm.c_lo[j], sm.c_hi[j], sm.c_val[j].w, sm.c_val[j].z, sm.c_newmp[j]);
+      if (k == MN_K_RESTORE) {  // cc:563-565: the consumed entry was the record's guard
+        float4 v = sm.c_val[j];
         v.w = sm.c_newmp[j];
+        v.z = mn_store_priority(sm, v.w, -1.0f, sm.c_lo[j], sm.c_hi[j], rec);
         im.rec_val[rec] = v;
-        if (v.w >= 0.0f) mn_push_entry(sm, v.w, sm.c_lo[j], sm.c_hi[j], rec);
-      } else {
+      } else if (k == MN_K_MERGE) {
         mn_commit_merge_object(im, sm, A, j);
+      } else if (k == MN_K_REQUEUE) {
+        float4 v = sm.c_val[j];
+        v.z = mn_store_priority(sm, v.w, -1.0f, sm.c_lh[j].x, sm.c_lh[j].y, rec);
+        im.rec_val[rec] = v;
+      } else if (k == MN_K_UNGUARD) {
+        float4 v = sm.c_val[j];
+        v.z = -1.0f;
+        im.rec_val[rec] = v;
       }
     }
     MN_FOR(i, ncand * A.C) {
       int j = i / A.C, c = i % A.C;
-      if (sm.c_accept[j] && sm.c_kind[j] == 2) im.clp[(size_t)sm.c_surv[j] * A.C + c] = c_clp[(size_t)j * A.C + c];
+      if (sm.c_accept[j] && sm.c_kind[j] == MN_K_MERGE) im.clp[(size_t)sm.c_surv[j] * A.C + c] = c_clp[(size_t)(j * 3 + 2) * A.C + c];
     }
+    mn_commit_pixels(im, sm, npw);
     mn_commit_pairs(im, sm, A, 0, npr);
     MN_SYNC();
     MN_TOC(MN_CY_COMMIT);
-    // ---- phase 9: queue maintenance ----
+    // ---- phase 8: queue maintenance ----
     mn_hot_update(im, sm, sm.cutpos);
     MN_TOC(MN_CY_HOT);
   }
@@ -1305,6 +1713,11 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     c->invalid_pops = sm.st_invalid; c->solo_events = sm.st_solo; c->refills = sm.st_refills;
     c->flushes = sm.st_flushes; c->splits = sm.st_splits; c->pairs = sm.st_pairs;
     c->cuts_conflict = sm.st_cut_conf; c->cuts_cascade = sm.st_cut_casc; c->cuts_capacity = sm.st_cut_cap;
+    c->requeues = sm.st_requeues;
+    c->pix_bump = sm.pix_bump; c->hash_ovf_n = sm.hash_ovf_n;
+    c->qc_bump = sm.qc_bump; c->qc_free_top = sm.qc_free_top; c->tn_bump = sm.tn_bump; c->tree_entries = sm.tree_entries;
+    c->static_cursor = sm.static_cursor; c->n_init = sm.n_init;
+    c->peak_entries = sm.peak_entries; c->peak_chunks = sm.peak_chunks;
     for (int i = 0; i < MN_NCYC; i++) c->cyc[i] = sm.cyc[i];
   }
   MN_SYNC();

@@ -114,6 +114,50 @@ void mno_host_log1m_table(uint32_t lo_bits, uint32_t n, float* out) {
     out[i] = (float)log(1.0 - (double)x);
   }
 }
+/* glibc / ARM optimized-routines expf (|x| < 88), the restatement the CUDA kernel uses; the x86-64
+ * libm runs its FMA build, hence the three explicit fma() steps.  Pinned to expf() by the CPU suite. */
+static const uint64_t MNO_EXP2F_TAB[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+float mno_expf_recipe(float x) {
+  const double InvLn2N = 0x1.71547652b82fep+0 * 32.0, SHIFT = 0x1.8p+52;
+  const double C0 = 0x1.c6af84b912394p-5 / 32768.0, C1 = 0x1.ebfce50fac4f3p-3 / 1024.0, C2 = 0x1.62e42ff0c52d6p-1 / 32.0;
+  double z = InvLn2N * (double)x;
+  double kd = z + SHIFT;
+  uint64_t ki;
+  memcpy(&ki, &kd, 8);
+  kd -= SHIFT;
+  double r = z - kd;
+  uint64_t t = MNO_EXP2F_TAB[ki & 31] + (ki << 47);
+  double s;
+  memcpy(&s, &t, 8);
+  z = fma(C0, r, C1);
+  double r2 = r * r;
+  double y = fma(C2, r, 1.0);
+  y = fma(z, r2, y);
+  y = y * s;
+  return (float)y;
+}
+/* mismatches of the recipe against the host expf over +-[2^-20 .. 2^6.3] sampled with `stride` */
+long long mno_expf_recipe_mismatches(uint32_t stride) {
+  long long bad = 0;
+  for (uint32_t b = 0x35800000u; b < 0x42a00000u; b += stride) {
+    float x;
+    memcpy(&x, &b, 4);
+    for (int sg = 0; sg < 2; sg++) {
+      float v = sg ? -x : x;
+      float a = expf(v), c = mno_expf_recipe(v);
+      if (memcmp(&a, &c, 4) != 0) bad++;
+    }
+  }
+  return bad;
+}
 /* same_different_bias transform, cc:183-195 */
 static float mno_bias_sameness(float s, float sdb) {
   float logit = (float)((double)logf(s) - log(1.0 - (double)s) + (double)sdb);

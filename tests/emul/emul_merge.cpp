@@ -28,41 +28,33 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   memset(&im, 0, sizeof(im));
   im.clp = zalloc<float>((size_t)N * C);
   im.cls = zalloc<int>(N);
-  im.obj_nc = zalloc<uint32_t>(N);
-  im.obj_same = zalloc<float>(N);
+  im.obj = zalloc<uint4>(N);
   im.parent = zalloc<int>(N);
   im.live_mask = zalloc<uint32_t>(N);
-  im.pl_head = zalloc<int>(N);
-  im.pl_tail = zalloc<int>(N);
-  im.plc_cap = N / 2 + 1024;
-  im.plc_next = zalloc<int>(im.plc_cap);
-  im.plc_cnt = zalloc<int>(im.plc_cap);
-  im.plc_pix = zalloc<int>((size_t)im.plc_cap * MN_PLC);
-  im.plc_free = zalloc<int>(im.plc_cap);
+  im.pix_cap = 16 * N + 4096;
+  im.pix_pool = zalloc<int>(im.pix_cap);
   im.rec_lh = zalloc<int2>(E);
   im.rec_val = zalloc<float4>(E);
+  im.rec_diff = zalloc<float>(E);
   im.hash_nbuckets = (uint32_t)(E * 16 / 10 / 8 + 64);
   im.hash = zalloc<uint32_t>((size_t)im.hash_nbuckets * 8);
   im.hash_ovf_cap = 4096;
   im.hash_ovf = zalloc<uint32_t>(im.hash_ovf_cap);
   im.init_keys = zalloc<uint64_t>(E);
-  im.qc_cap = (int)(E / MN_QCH) + 65536 + MN_NROOTS;
+  im.qc_cap = (int)(E / MN_QCH * 2) + 4 * MN_NROOTS + 4096;
   im.q_ent = zalloc<uint4>((size_t)im.qc_cap * MN_QCH);
   im.qc_next = zalloc<int>(im.qc_cap);
-  im.qc_cnt = zalloc<int>(im.qc_cap);
   im.qc_free = zalloc<int>(im.qc_cap);
-  im.tn_cap = MN_NROOTS + MN_TREE_FANOUT * 8192;
-  im.tn_head = zalloc<int>(im.tn_cap);
-  im.tn_tail = zalloc<int>(im.tn_cap);
-  im.tn_cnt = zalloc<int>(im.tn_cap);
-  im.tn_child = zalloc<int>(im.tn_cap);
+  im.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)(8192 + E / 256);
+  im.tn = zalloc<int4>(im.tn_cap);
+  im.tn_dir = zalloc<int>((size_t)im.tn_cap * 8);
   im.ctl = zalloc<MnCtl>(1);
-  for (int i = 0; i < im.tn_cap; i++) { im.tn_head[i] = -1; im.tn_tail[i] = -1; im.tn_child[i] = -1; }
+  for (int i = 0; i < im.tn_cap; i++) im.tn[i] = make_int4(-1, -1, 0, -1);
   im.ctl->tn_bump = MN_NROOTS;
 
   MnMergeArgs A;
   memset(&A, 0, sizeof(A));
-  A.C = C; A.K = K; A.N = N; A.W = W; A.omf = omf; A.mlb = mlb; A.max_rounds = 0;
+  A.C = C; A.K = K; A.N = N; A.W = W; A.omf = omf; A.mlb = mlb; A.max_rounds = 0; A.H = MN_H;
   A.off.K = K;
   std::vector<std::pair<int, int>> mag;
   for (int k = 0; k < K; k++) {
@@ -82,8 +74,8 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
       if (c == 0 || v > best) { best = v; bc = c; }
     }
     im.cls[p] = bc;
-    im.obj_nc[p] = mn_pack_nc(1, bc);
-    im.parent[p] = p; im.pl_head[p] = -1; im.pl_tail[p] = -1;
+    im.obj[p] = make_uint4(mn_pack_nc(1, bc), 0u, 0xffffffffu, 0u);
+    im.parent[p] = p;
   }
   for (int p = 0; p < N; p++) {
     int row = p / W, col = p % W;
@@ -106,7 +98,8 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
         float mp = mn_priority(oml, omf, mlb, C, 1, im.cls[lo], im.clp + (size_t)lo * C, 1, im.cls[hi],
                                im.clp + (size_t)hi * C, nullptr);
         im.rec_lh[r] = make_int2(lo, hi);
-        im.rec_val[r] = make_float4(oml, same, diff, mp);
+        im.rec_val[r] = make_float4(oml, same, mp >= 0.0f ? mp : -1.0f, mp);
+        im.rec_diff[r] = diff;
         mn_hash_insert(im, lo, hi, (int)r);
         if (mp >= 0.0f) {
           uint32_t ord = (uint32_t)lo * (uint32_t)K + (uint32_t)rank_of_k[k];
@@ -114,7 +107,7 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
         }
       } else {
         im.rec_lh[r] = make_int2(-1, -1);
-        im.rec_val[r] = make_float4(0, 0, 0, -1.0f);
+        im.rec_val[r] = make_float4(0, 0, -1.0f, -1.0f);
       }
       im.init_keys[r] = key;
     }
@@ -122,7 +115,7 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   std::sort(im.init_keys, im.init_keys + E);
 
   MnSm* sm = (MnSm*)calloc(1, sizeof(MnSm));
-  float* c_clp = zalloc<float>((size_t)MN_H * C);
+  float* c_clp = zalloc<float>((size_t)MN_H * 3 * C);
   mn_merge_image(im, *sm, A, c_clp);
 
   // labels (cc:491-517): ascending surviving id, class-0 objects -> 0
@@ -131,7 +124,7 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   int k = 1;
   for (int o = 0; o < N; o++) {
     if (im.parent[o] != o) continue;
-    int cls = mn_nc_cls(im.obj_nc[o]);
+    int cls = mn_nc_cls(im.obj[o].x);
     if (cls == 0) continue;
     object_class[k - 1] = cls;
     label[o] = k++;
@@ -145,14 +138,14 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   if (getenv("EMUL_DEBUG")) {
     for (size_t r = 0; r < E; r++) if (im.rec_lh[r].x >= 0 && im.rec_val[r].w >= 0.0f)
       fprintf(stderr, "LEFTOVER rec %zu lo %d hi %d mp %.9g (bits %08x) root %d\n", r, im.rec_lh[r].x, im.rec_lh[r].y, im.rec_val[r].w, mn_f2u(im.rec_val[r].w), mn_root_of(im.rec_val[r].w));
-    fprintf(stderr, "status %d fail_line %d\n", im.ctl->status, im.ctl->fail_line);
+    fprintf(stderr, "status %d fail_line %d hash_ovf_n %d peak_entries %d peak_chunks %d (E %zu) tn_bump %d qc_bump %d pix_bump %d\n", im.ctl->status, im.ctl->fail_line, im.ctl->hash_ovf_n, im.ctl->peak_entries, im.ctl->peak_chunks, E, im.ctl->tn_bump, im.ctl->qc_bump, im.ctl->pix_bump);
     fprintf(stderr, "tree_entries %d static_cursor %d n_init %d nins %d nhot %d cold_empty %d\n", im.ctl->tree_entries, im.ctl->static_cursor, im.ctl->n_init, sm->nins, sm->nhot, sm->cold_empty);
   }
   if (stats) {
     MnCtl* c = im.ctl;
     long long v[16] = {c->rounds, c->events, c->merges, c->restores, c->invalid_pops, c->solo_events,
                        c->refills, c->flushes, c->splits, c->pairs, c->cuts_conflict, c->cuts_cascade,
-                       c->cuts_capacity, (long long)c->qc_bump, (long long)c->plc_bump, (long long)c->tn_bump};
+                       c->cuts_capacity, (long long)c->qc_bump, (long long)c->pix_bump, (long long)c->tn_bump};
     memcpy(stats, v, sizeof(v));
   }
   // (leaks on purpose: short-lived test process helper)

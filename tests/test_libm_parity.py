@@ -16,6 +16,14 @@ def test_logf_recipe_equals_libm_exhaustive(oracle_mod):
     assert bad == 0
 
 
+def test_expf_recipe_equals_libm_sampled(oracle_mod):
+    """The same_different_bias path (segment.cc:189-191) needs expf; the recipe must be the host's expf."""
+    L = oracle_mod.oracle_lib()
+    L.mno_expf_recipe_mismatches.restype = ctypes.c_longlong
+    L.mno_expf_recipe_mismatches.argtypes = [ctypes.c_uint32]
+    assert L.mno_expf_recipe_mismatches(7) == 0
+
+
 def _device_vs_host(oracle_mod, lib_mod, which, host_fn, stride_chunks=1, bias=0.0):
     L = lib_mod.lib()
     F = ctypes.POINTER(ctypes.c_float)
