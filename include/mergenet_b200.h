@@ -73,7 +73,7 @@ typedef struct {
   /* SM cycles of the image's CTA: total, and by phase (select, plan, accept, commit, hot-queue update,
    * flush, refill, split, solo merges, gc) */
   long long cycles_total;
-  long long cycles[10];
+  long long cycles[16]; /* ... + refill leaves / init / sort, select stage / classify / pixels */
 } mn_image_stats;
 
 /* Device time of the phases of the last batch (CUDA events on the plan's stream), milliseconds. */

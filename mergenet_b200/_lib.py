@@ -45,7 +45,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "mn_api.cu")]
+    extra = os.environ.get("MN_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB_PATH, os.path.join(CSRC, "mn_api.cu")]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
@@ -58,9 +59,10 @@ class ImageStats(ctypes.Structure):
                     "rounds", "events", "merges", "restores", "invalid_pops", "solo_events", "refills",
                     "flushes", "splits", "pairs", "cuts_conflict", "cuts_cascade", "cuts_capacity",
                     "queue_chunks_used", "pixel_pool_used", "tree_nodes_used", "requeues", "hash_overflow", "cycles_total")] + [
-        ("cycles", ctypes.c_longlong * 10)]
+        ("cycles", ctypes.c_longlong * 16)]
 
-    CYCLE_NAMES = ("select", "plan", "accept", "commit", "hot", "flush", "refill", "split", "solo", "gc")
+    CYCLE_NAMES = ("select", "plan", "accept", "commit", "hot", "flush", "refill", "split", "solo", "gc",
+                   "rf_leaves", "rf_init", "rf_sort", "sel_stage", "sel_class", "sel_pix")
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_ if n != "cycles"}

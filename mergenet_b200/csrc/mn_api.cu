@@ -59,7 +59,8 @@ extern "C" int mn_device_count(void) {
 
 // ------------------------------------------------------------------------------------------------
 // kernels of this file
-__global__ void __launch_bounds__(256, 1) mn_merge_kernel(const MnImage* imgs, int nimg, MnMergeArgs A) {
+#define MN_MERGE_THREADS 512
+__global__ void __launch_bounds__(MN_MERGE_THREADS, 1) mn_merge_kernel(const MnImage* imgs, int nimg, MnMergeArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   MnSm& sm = *reinterpret_cast<MnSm*>(smem_raw);
   float* c_clp = reinterpret_cast<float*>(smem_raw + ((sizeof(MnSm) + 15) / 16) * 16);
@@ -104,7 +105,7 @@ __global__ void mn_label_write_kernel(const MnImage* imgs, int nimg, int N, int*
   for (int b = blockIdx.y; b < nimg; b += gridDim.y) {
     const MnImage im = imgs[b];
     const int* flags = im.cls;
-    const int* excl = (const int*)im.live_mask;  // exclusive scan of flags (the live masks are dead by now)
+    const int* excl = im.pix_pool;  // exclusive scan of flags (the pixel arrays are dead by now)
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
       int r = p;
       for (int g = 0; g < (1 << 26); g++) {
@@ -169,7 +170,7 @@ struct mn_plan {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t clp, cls, obj, parent, live_mask, pix_pool, rec_lh, rec_val, rec_same, rec_diff, hash, hash_ovf,
+  size_t clp, cls, obj, parent, pix_pool, rec, rec_sd, hash, hash_ovf,
       init_keys, qc_next, qc_free, tn, tn_dir, ctl, total;
   int pix_cap, qc_cap, tn_cap;
   uint32_t hash_nbuckets, hash_ovf_cap;
@@ -180,22 +181,19 @@ static WsLayout ws_layout(int H, int W, int C, int K) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
   L.pix_cap = (int)(16 * N + 4096);
-  // queue entry pool: 16-byte entries in chunks of MN_QCH; it aliases rec_same (4*E bytes, dead after
-  // record init) and extends past it: one chunk per live tree leaf plus the pending entries.
+  // queue entry pool: 16-byte entries in chunks of MN_QCH; it aliases rec_same | rec_diff (8*E bytes,
+  // dead after record init) and extends past them: one chunk per live tree leaf plus the entries.
   L.qc_cap = (int)(E * 3 / 4 / MN_QCH + 4 * MN_NROOTS + 4096);  // measured peak: 0.6 E entries
-  L.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)std::max<size_t>(2048, E / 1024);
+  L.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)std::max<size_t>(16384, E / 128);
   L.hash_nbuckets = (uint32_t)(E * 18 / 10 / 8 + 64);
   L.hash_ovf_cap = 16384;
   L.clp = take(N * C * 4);
   L.cls = take(N * 4);
   L.obj = take(N * 16);
   L.parent = take(N * 4);
-  L.live_mask = take(N * 4);
   L.pix_pool = take((size_t)L.pix_cap * 4);
-  L.rec_lh = take(E * 8);
-  L.rec_val = take(E * 16);
-  L.rec_diff = take(E * 4);
-  L.rec_same = take(std::max(E * 4, (size_t)L.qc_cap * MN_QCH * 16));  // rec_same, then q_ent
+  L.rec = take(E * 32);
+  L.rec_sd = take(std::max(E * 8, (size_t)L.qc_cap * MN_QCH * 16));  // rec_same | rec_diff, then q_ent
   L.hash = take((size_t)L.hash_nbuckets * 8 * 4);
   L.hash_ovf = take((size_t)L.hash_ovf_cap * 4);
   L.init_keys = take(E * 8);
@@ -296,14 +294,14 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
     memset(&im, 0, sizeof(im));
     im.clp = (float*)(base + L.clp); im.cls = (int*)(base + L.cls);
     im.obj = (uint4*)(base + L.obj);
-    im.parent = (int*)(base + L.parent); im.live_mask = (uint32_t*)(base + L.live_mask);
+    im.parent = (int*)(base + L.parent);
     im.pix_pool = (int*)(base + L.pix_pool);
-    im.rec_lh = (int2*)(base + L.rec_lh); im.rec_val = (float4*)(base + L.rec_val);
-    im.rec_same = (float*)(base + L.rec_same); im.rec_diff = (float*)(base + L.rec_diff);
+    im.rec = (uint4*)(base + L.rec);
+    im.rec_same = (float*)(base + L.rec_sd); im.rec_diff = im.rec_same + p->E;
     im.hash = (uint32_t*)(base + L.hash); im.hash_ovf = (uint32_t*)(base + L.hash_ovf);
     im.hash_nbuckets = L.hash_nbuckets; im.hash_ovf_cap = L.hash_ovf_cap;
     im.init_keys = (uint64_t*)(base + L.init_keys);
-    im.q_ent = (uint4*)(base + L.rec_same);
+    im.q_ent = (uint4*)(base + L.rec_sd);
     im.qc_next = (int*)(base + L.qc_next); im.qc_free = (int*)(base + L.qc_free);
     im.tn = (int4*)(base + L.tn); im.tn_dir = (int*)(base + L.tn_dir);
     im.pix_cap = L.pix_cap; im.qc_cap = L.qc_cap; im.tn_cap = L.tn_cap;
@@ -401,7 +399,7 @@ extern "C" int mn_segment_batch_device(mn_plan* p, int B, const float* d_class, 
   memset(&A, 0, sizeof(A));
   A.C = p->C; A.K = p->K; A.N = N; A.W = p->W; A.omf = omf; A.mlb = mlb; A.off = p->off; A.H = p->merge_H; A.max_rounds = 40ll * N + 100000;  // guard: rounds <= events, a few per pixel
   int grid = std::min(B, p->num_sms);
-  mn_merge_kernel<<<grid, 256, p->merge_smem, s>>>(p->d_imgs, B, A);
+  mn_merge_kernel<<<grid, MN_MERGE_THREADS, p->merge_smem, s>>>(p->d_imgs, B, A);
   p->timings.other_launches++;
   MN_CUDA_OK(cudaEventRecord(p->ev[4], s));
   // labels
@@ -410,7 +408,7 @@ extern "C" int mn_segment_batch_device(mn_plan* p, int B, const float* d_class, 
     mn_label_flags_kernel<<<g, 256, 0, s>>>(p->d_imgs, B, N);
     for (int b = 0; b < B; b++) {
       size_t tb = p->cub_temp_bytes;
-      MN_CUDA_OK(cub::DeviceScan::ExclusiveSum(p->d_cub_temp, tb, (const int*)p->h_imgs[b].cls, (int*)p->h_imgs[b].live_mask, N, s));
+      MN_CUDA_OK(cub::DeviceScan::ExclusiveSum(p->d_cub_temp, tb, (const int*)p->h_imgs[b].cls, p->h_imgs[b].pix_pool, N, s));
     }
     MN_CUDA_OK(cudaMemsetAsync(d_object_class, 0xFF, (size_t)B * N * 4, s));
     mn_label_write_kernel<<<g, 256, 0, s>>>(p->d_imgs, B, N, d_mask, d_object_class, d_ninst);
@@ -491,7 +489,7 @@ extern "C" int mn_plan_image_stats(mn_plan* p, int image, mn_image_stats* o) {
   o->invalid_pops = c.invalid_pops; o->solo_events = c.solo_events; o->refills = c.refills;
   o->flushes = c.flushes; o->splits = c.splits; o->pairs = c.pairs; o->cuts_conflict = c.cuts_conflict;
   o->cuts_cascade = c.cuts_cascade; o->cuts_capacity = c.cuts_capacity;
-  for (int i = 0; i < 10; i++) o->cycles[i] = c.cyc[i];
+  for (int i = 0; i < 16; i++) o->cycles[i] = c.cyc[i];
   o->cycles_total = c.cycles_total;
   o->queue_chunks_used = c.qc_bump; o->pixel_pool_used = c.pix_bump; o->tree_nodes_used = c.tn_bump;
   o->requeues = c.requeues; o->hash_overflow = c.hash_ovf_n;
@@ -559,21 +557,20 @@ extern "C" int mn_debug_edge_dump(int H, int W, int C, int K, const int* offset_
   cudaMemcpyAsync(p->d_in_adj, h_adj, (size_t)K * N * 4, cudaMemcpyHostToDevice, s);
   rc = run_front(p, 1, p->d_in_class, p->d_in_adj, 0, sdb, omf, mlb, s, false);
   if (rc) return done(rc);
-  std::vector<int2> lh(E);
-  std::vector<float4> val(E);
-  std::vector<float> dif(E);
+  std::vector<uint4> rec(2 * E);
   const MnImage& im = p->h_imgs[0];
   cudaMemcpyAsync(clp, im.clp, N * C * 4, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(cls, im.cls, N * 4, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(lh.data(), im.rec_lh, E * 8, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(val.data(), im.rec_val, E * 16, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(dif.data(), im.rec_diff, E * 4, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(rec.data(), im.rec, E * 32, cudaMemcpyDeviceToHost, s);
   if (sdb != 0.0f) cudaMemcpyAsync(h_adj, p->d_in_adj, (size_t)K * N * 4, cudaMemcpyDeviceToHost, s);
   if (cudaStreamSynchronize(s) != cudaSuccess) return done(MN_STATUS_CUDA);
   for (size_t r = 0; r < E; r++) {
-    lo[r] = lh[r].x; hi[r] = lh[r].y;
-    bool v = lh[r].x >= 0;
-    oml[r] = v ? val[r].x : 0.f; same[r] = v ? val[r].y : 0.f; diff[r] = v ? dif[r] : 0.f; mp[r] = v ? val[r].w : 0.f;
+    const uint4 a = rec[2 * r];
+    const float4 b = *reinterpret_cast<const float4*>(&rec[2 * r + 1]);
+    lo[r] = (int)a.x; hi[r] = (int)a.y;
+    bool v = lo[r] >= 0;
+    if (!v) { lo[r] = -1; hi[r] = -1; }
+    oml[r] = v ? b.x : 0.f; same[r] = v ? b.y : 0.f; diff[r] = v ? mn_u2f(a.w) : 0.f; mp[r] = v ? b.w : 0.f;
   }
   return done(MN_STATUS_OK);
 }

@@ -291,9 +291,8 @@ __global__ void __launch_bounds__(256) mn_record_init_kernel(MnRecInitParams P) 
         c2 = col - P.off_c[kk];
         if (r2 >= 0 && r2 < P.H && c2 >= 0 && c2 < P.W) m |= 1u << (16 + kk);
       }
-      im.live_mask[p] = m;
       im.parent[p] = p;
-      im.obj[p] = make_uint4(mn_pack_nc(1, im.cls[p]), 0u /* sameness sum 0.0f */, 0xffffffffu /* no pixel array */, 0u);
+      im.obj[p] = make_uint4(mn_pack_nc(1, im.cls[p]), 0u /* sameness sum 0.0f */, 0xffffffffu /* no pixel array */, m);
     }
     const int r2 = row + P.off_r[k], c2 = col + P.off_c[k];
     uint64_t key = ~0ull;
@@ -305,16 +304,17 @@ __global__ void __launch_bounds__(256) mn_record_init_kernel(MnRecInitParams P) 
       const int cl = im.cls[lo], ch = im.cls[hi];
       const float mp = mn_priority(oml, P.omf, P.mlb, P.C, 1, cl, im.clp + (size_t)lo * P.C, 1, ch,
                                    im.clp + (size_t)hi * P.C, nullptr);  // cc:45
-      im.rec_lh[r] = make_int2(lo, hi);
-      im.rec_val[r] = make_float4(oml, same, mp >= 0.0f ? mp : -1.0f, mp);  // rec_diff[r] already holds diff
-      mn_hash_insert(im, lo, hi, r);
+      MN_REC_LH(im, r) = make_int2(lo, hi);  // (the hash verifies keys through the record)
+      const int hslot = mn_hash_insert(im, lo, hi, r);
+      MN_REC_A(im, r) = make_uint4((uint32_t)lo, (uint32_t)hi, (uint32_t)hslot, mn_f2u(diff));
+      MN_REC_B(im, r) = make_float4(oml, same, mp >= 0.0f ? mp : -1.0f, mp);
       if (mp >= 0.0f) {  // cc:225-227
         uint32_t ord = (uint32_t)lo * (uint32_t)P.K + (uint32_t)P.rank_of_k[k];
         key = ((uint64_t)(~mn_f2u(mp == 0.0f ? 0.0f : mp)) << MN_ORD_BITS) | ord;
       }
     } else {
-      im.rec_lh[r] = make_int2(-1, -1);
-      im.rec_val[r] = make_float4(0.f, 0.f, -1.0f, -1.0f);
+      MN_REC_A(im, r) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
+      MN_REC_B(im, r) = make_float4(0.f, 0.f, -1.0f, -1.0f);
     }
     P.keys_out[r] = key;
   }

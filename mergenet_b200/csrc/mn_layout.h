@@ -5,7 +5,7 @@
 //   objects   clp[N*C] f32 | obj[N] uint4 (npix | cls<<24, sameness sum, pixel-array offset, -) |
 //             parent[N] | live_mask[N] | pix_pool: one contiguous pixel array per multi-pixel
 //             object, capacity = next power of two >= npix (>= 4)          (Object, h:85-137)
-//   records   rec_lh[E] int2 (lo,hi; lo=-1 = dead) | rec_val[E] float4 (oml,same,diff,mp)
+//   records   rec[E] 32 B: (lo, hi, hash slot, diff | oml, same, qmp, mp); lo = -1 = dead
 //             (AdjacencyRecord, h:175-232)
 //   hash      2-choice, 8-slot buckets of u32 (fingerprint<<26 | rec+1): (lo,hi) -> record
 //             (replaces the per-object unordered_map lookups of cc:685-688)
@@ -69,7 +69,9 @@ template <typename T> static inline T mn_h_cas(T* p, T c, T v) { T o = *p; if (o
 #define MN_ORD_BITS 25       // initial-entry tie-break ordinal lo*K + rank  (N*K <= 2^25)
 #define MN_QCH 64            // queue entries per tree chunk (16 B each)
 #define MN_HASH_FP_SHIFT 26  // slot = fingerprint(6) << 26 | (rec + 1)
-#define MN_TREE_FANOUT 64    // children per split (6-bit digits)
+#define MN_TREE_BITS 3       // digit width of the queue tree below a root
+#define MN_TREE_FANOUT (1 << MN_TREE_BITS)  // children per split: small, so that the children of a split
+                                            // leaf (> MN_LEAFCAP entries) are still worth a load each
 
 // queue tree roots: one per 2^15 float-bit patterns over [MN_ROOT_LO, MN_ROOT_HI)
 #define MN_ROOT_SHIFT 15
@@ -107,22 +109,24 @@ struct MnCtl {
   long long refills, flushes, splits, pairs, cuts_conflict, cuts_cascade, cuts_capacity;
   long long cycles_total;
   long long requeues;
-  long long cyc[10];   // cycle buckets (MN_CY_*)
+  long long cyc[16];   // cycle buckets (MN_CY_*)
 };
 
 struct MnImage {
   // objects
   float* clp;
   int* cls;  // argmax class per pixel from the edge pass (consumed by record init)
-  uint4* obj;  // x = npix | cls << 24, y = bits of the object's sameness sum (h:131), z = pixel array offset (-1: single pixel)
+  uint4* obj;  // x = npix | cls << 24, y = bits of the object's sameness sum (h:131), z = pixel array offset
+               // (-1: single pixel); w = LIVE MASK OF PIXEL p (bit k: record slot p*K+k alive, bit 16+k: the
+               // slot of the record arriving through offset k) -- per pixel, whatever object owns it
   int* parent;
-  uint32_t* live_mask;
   int* pix_pool;
   // records
-  int2* rec_lh;
-  float4* rec_val;  // (oml, sameness sum, qmp = priority of the record's earliest queued entry or -1, mp)
-  float* rec_same;  // edge-pass output; dead after record init, then aliased by q_ent
-  float* rec_diff;  // edge-pass output, then the record's differentness sum (h:196-199)
+  uint4* rec;       // one 32-byte sector per record slot r: rec[2r] = (lo, hi, hash slot, differentness sum),
+                    // rec[2r+1] = (oml, sameness sum, qmp = priority of the record's earliest queued entry
+                    // or -1, mp); lo = -1: dead                                         (h:175-232)
+  float* rec_same;  // edge-pass outputs; dead after record init, then aliased by q_ent
+  float* rec_diff;
   // hash
   uint32_t* hash;
   uint32_t* hash_ovf;  // small linear overflow area of rec+1 values
@@ -142,6 +146,9 @@ struct MnImage {
   MnCtl* ctl;
 };
 
+#define MN_REC_A(im, r) ((im).rec[2 * (size_t)(r)])
+#define MN_REC_B(im, r) (reinterpret_cast<float4*>((im).rec)[2 * (size_t)(r) + 1])
+#define MN_REC_LH(im, r) (*reinterpret_cast<int2*>(&(im).rec[2 * (size_t)(r)]))
 MN_HD uint32_t mn_pack_nc(int npix, int cls) { return (uint32_t)npix | ((uint32_t)cls << 24); }
 MN_HD int mn_nc_npix(uint32_t nc) { return (int)(nc & 0xFFFFFFu); }
 MN_HD int mn_nc_cls(uint32_t nc) { return (int)(nc >> 24); }
@@ -184,7 +191,7 @@ MN_HD int mn_hash_find(const MnImage& im, int lo, int hi) {
       uint32_t v = bk[s];
       if (v != 0 && (v >> MN_HASH_FP_SHIFT) == p.fp) {
         int r = (int)(v & ((1u << MN_HASH_FP_SHIFT) - 1)) - 1;
-        int2 lh = im.rec_lh[r];
+        int2 lh = MN_REC_LH(im, r);
         if (lh.x == lo && lh.y == hi) return r;
       }
     }
@@ -194,15 +201,16 @@ MN_HD int mn_hash_find(const MnImage& im, int lo, int hi) {
     uint32_t v = im.hash_ovf[i];
     if (v != 0) {
       int r = (int)v - 1;
-      int2 lh = im.rec_lh[r];
+      int2 lh = MN_REC_LH(im, r);
       if (lh.x == lo && lh.y == hi) return r;
     }
   }
   return -1;
 }
-// rec_lh[rec] must already hold (lo,hi).  Safe against concurrent inserts/erases of other keys.
-// Two-choice placement: the emptier of the two candidate buckets first.
-MN_HD void mn_hash_insert(const MnImage& im, int lo, int hi, int rec) {
+// Safe against concurrent inserts/erases of other keys.  Two-choice placement: the emptier of the two
+// candidate buckets first.  Returns the global slot index, or -1 when the record went to the overflow
+// area (the caller stores it in the record: erasing then needs no lookup).
+MN_HD int mn_hash_insert(const MnImage& im, int lo, int hi, int rec) {
   MnHashPos p = mn_hash_pos(im.hash_nbuckets, lo, hi);
   uint32_t val = (p.fp << MN_HASH_FP_SHIFT) | (uint32_t)(rec + 1);
   uint32_t* bk1 = im.hash + (size_t)p.b1 * 8;
@@ -212,7 +220,7 @@ MN_HD void mn_hash_insert(const MnImage& im, int lo, int hi, int rec) {
   for (int w = 0; w < 2; w++) {
     uint32_t* bk = ((w == 0) == (f1 >= f2)) ? bk1 : bk2;
     for (int s = 0; s < 8; s++) {
-      if (bk[s] == 0 && MN_ATOMIC_CAS(&bk[s], 0u, val) == 0u) return;
+      if (bk[s] == 0 && MN_ATOMIC_CAS(&bk[s], 0u, val) == 0u) return (int)(bk - im.hash) + s;
     }
   }
   int i = MN_ATOMIC_ADD(&im.ctl->hash_ovf_n, 1);
@@ -221,6 +229,7 @@ MN_HD void mn_hash_insert(const MnImage& im, int lo, int hi, int rec) {
   } else {
     im.ctl->status = MN_ERR_HASH_FULL;
   }
+  return -1;
 }
 MN_HD void mn_hash_erase(const MnImage& im, int lo, int hi, int rec) {
   MnHashPos p = mn_hash_pos(im.hash_nbuckets, lo, hi);

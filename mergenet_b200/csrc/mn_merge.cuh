@@ -26,7 +26,7 @@
 // later, a lazily split radix tree of unsorted chunks keyed by (mp bits, lo, hi).  The queue is lazy
 // in two ways.  Like the reference's heap, an entry that no longer describes its record is dropped
 // when it surfaces (cc:554-559).  Unlike it, a record whose priority is re-stored LATER in pop order
-// than an entry it already has gets no new entry: rec_val.z (`qmp`) remembers the priority of the
+// than an entry it already has gets no new entry: rec[2r+1].z (`qmp`) remembers the priority of the
 // record's earliest queued entry (the "guard"); when the guard surfaces and the stored priority is
 // lower, an exact entry is queued then ("requeue").  Invariant: every live record with stored
 // mp >= 0 has a queued entry popping before-or-at its true position, so no pop can be missed, and
@@ -56,7 +56,7 @@
 #define MN_NEG_INF (-3.0e38f)
 #define MN_RANK_MAX 256  // up to this many entries are ordered by brute-force ranking (no barriers)
 // cycle accounting buckets (thread 0, clock64)
-#define MN_NCYC 10
+#define MN_NCYC 16
 #define MN_CY_SELECT 0   // stage + classify + work lists
 #define MN_CY_PLAN 1
 #define MN_CY_ACCEPT 2
@@ -67,6 +67,12 @@
 #define MN_CY_SPLIT 7
 #define MN_CY_SOLO 8
 #define MN_CY_GC 9
+#define MN_CY_RF_LEAVES 10  // refill: tree leaves
+#define MN_CY_RF_INIT 11    // refill: initial entries, bound, bulk requeue
+#define MN_CY_RF_SORT 12    // refill: ordering + merge into hot
+#define MN_CY_SEL_STAGE 13  // select: staging loads
+#define MN_CY_SEL_CLASS 14  // select: classify, merged vectors, pixel capacity
+#define MN_CY_SEL_PIX 15    // select: pixels, masks, pair lists
 
 // candidate kinds
 #define MN_K_DROP 0      // stale entry: dropped when consumed
@@ -92,12 +98,12 @@ struct MnSm {
   uint32_t root_bits[(MN_NROOTS + 31) / 32];
   uint32_t root_sum[((MN_NROOTS + 31) / 32 + 31) / 32];
   int cw_chunk[MN_CW];
-  int4 scan_nd[MN_TREE_FANOUT]; int4 leaf_nd; int path_cnt[20];
+  int4 scan_nd[MN_TREE_FANOUT]; int4 leaf_nd; int path_cnt[32];
   int qc_free_top, qc_bump, tn_bump, tree_entries, static_cursor, n_init;  // mirrors of MnCtl
   int peak_entries, peak_chunks;
   // candidates: staged loads
   int c_rec[MN_H]; float c_key[MN_H]; int c_lo[MN_H]; int c_hi[MN_H]; int c_kind[MN_H];
-  float4 c_val[MN_H]; int2 c_lh[MN_H]; uint4 c_obj[MN_H][2]; uint32_t c_lm[MN_H][2]; uint32_t c_hb[MN_H][16];
+  float4 c_val[MN_H]; int2 c_lh[MN_H]; uint4 c_obj[MN_H][2];
   float c_rdiff[MN_H]; int c_dup[MN_H];
   // candidates: classification
   float c_newmp[MN_H]; int c_merged[MN_H]; int c_surv[MN_H]; int c_abs[MN_H]; int c_na[MN_H]; int c_nb[MN_H];
@@ -134,7 +140,7 @@ struct MnSm {
   int failed;               // sticky copy of ctl->status != 0
   int cold_empty;  // 1: nothing outside `hot` -> every new entry goes to hot
   float b_mp; int b_lo; int b_hi;  // bound: entries popping strictly after it are cold
-  int path[20]; int path_n;
+  int path[32]; int path_n;
   long long cyc[MN_NCYC]; long long cyc_t0;
   long long st_rounds, st_events, st_merges, st_restores, st_invalid, st_solo, st_refills,
       st_flushes, st_splits, st_pairs, st_cut_conf, st_cut_casc, st_cut_cap, st_requeues;
@@ -211,17 +217,17 @@ MN_D int mn_root_of(float mp) {
   if (b >= MN_ROOT_HI_BITS) return MN_NROOTS - 1;
   return (int)((b - MN_ROOT_LO_BITS) >> MN_ROOT_SHIFT) + 1;
 }
-// 6-bit digit `level` (1-based, below the root) of the 80-bit pop-order key [~mpbits:32][lo:24][hi:24].
+// MN_TREE_BITS-bit digit `level` (1-based, below the root) of the 80-bit pop-order key [~mpbits:32][lo:24][hi:24].
 // Regular roots fix the top 32 - MN_ROOT_SHIFT key bits, where their digits start; the two open-ended roots
 // start at bit 0.  Smaller digit = pops first.
 MN_D int mn_digit(int root, int level, float mp, int lo, int hi) {
   int start = (root == 0 || root == MN_NROOTS - 1) ? 0 : 32 - MN_ROOT_SHIFT;
-  int pos = start + 6 * (level - 1);  // bit offset from the top of the 80-bit key
+  int pos = start + MN_TREE_BITS * (level - 1);  // bit offset from the top of the 80-bit key
   unsigned long long hi64 = ((unsigned long long)(~mn_f2u(mp)) << 32) | ((unsigned long long)(uint32_t)lo << 8) |
                             ((unsigned long long)(uint32_t)hi >> 16);
   unsigned long long lo16 = (unsigned long long)((uint32_t)hi & 0xFFFFu);
   int d = 0;
-  for (int b = 0; b < 6; b++) {
+  for (int b = 0; b < MN_TREE_BITS; b++) {
     int p = pos + b;
     int bit;
     if (p < 64) bit = (int)((hi64 >> (63 - p)) & 1ull);
@@ -231,7 +237,10 @@ MN_D int mn_digit(int root, int level, float mp, int lo, int hi) {
   }
   return d;
 }
-MN_D int mn_max_level(int root) { return (root == 0 || root == MN_NROOTS - 1) ? 14 : (80 - (32 - MN_ROOT_SHIFT) + 5) / 6; }
+MN_D int mn_max_level(int root) {
+  const int start = (root == 0 || root == MN_NROOTS - 1) ? 0 : 32 - MN_ROOT_SHIFT;
+  return (80 - start + MN_TREE_BITS - 1) / MN_TREE_BITS;
+}
 
 MN_D int mn_qc_alloc(const MnImage& im, MnSm& sm) {  // called only from phases that never free
   int t = MN_ATOMIC_SUB(&sm.qc_free_top, 1);
@@ -359,7 +368,7 @@ MN_D void mn_flush_ins(const MnImage& im, MnSm& sm) {
   MN_SYNC();
 }
 
-// What a queue entry (emp, elo, ehi) is against its record (rec_lh, rec_val = oml, same, qmp, mp):
+// What a queue entry (emp, elo, ehi) is against its record (key lh, values v = oml, same, qmp, mp):
 //   DROP     the record is dead, or another entry guards it (emp != qmp), or it was re-keyed at the
 //            same priority (a fresh entry was queued then);
 //   exact    emp == qmp == mp and the key matches: the reference's valid pop (cc:554-559);
@@ -423,11 +432,11 @@ MN_D void mn_split_leaf(const MnImage& im, MnSm& sm, int root, int node, int lev
       if (c < 0) { mn_fail(im, MN_ERR_INTERNAL); continue; }
       uint4 e = im.q_ent[(size_t)c * MN_QCH + s];
       int rec = (int)e.y;
-      int2 lh = im.rec_lh[rec];
-      float4 v = im.rec_val[rec];
+      int2 lh = MN_REC_LH(im, rec);
+      float4 v = MN_REC_B(im, rec);
       float emp = mn_u2f(e.x);
       int st = mn_entry_state(emp, (int)e.z, (int)e.w, lh, v);
-      if (st == MN_K_UNGUARD) { v.z = -1.0f; im.rec_val[rec] = v; }
+      if (st == MN_K_UNGUARD) { v.z = -1.0f; MN_REC_B(im, rec) = v; }
       else if (st != MN_K_DROP) {  // the entry keeps its own key (a guard stays where it is)
         int p = MN_ATOMIC_ADD(&sm.npr, 1);
         sm.sb_mp[p] = emp; sm.sb_lo[p] = (int)e.z; sm.sb_hi[p] = (int)e.w; sm.sb_rec[p] = rec;
@@ -501,7 +510,7 @@ MN_D int mn_top_leaf(const MnImage& im, MnSm& sm, int* root_out, bool allow_spli
       }
       MN_SYNC();
       const int found = sm.tmp1;
-      if (found < 0 || level > 16) { bad = true; break; }
+      if (found < 0 || level > 30) { bad = true; break; }
       nd = sm.scan_nd[found];
       node = cb + found;
       level++;
@@ -567,6 +576,7 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
   for (int guard = 0; guard < (1 << 20); guard++) {
     MN_SYNC();
     mn_flush_ins(im, sm);  // (also on retries: a previous pass may have pushed leaf entries back)
+    MN_TOC(MN_CY_FLUSH);
     if (sm.failed) return;
     // ---- load + validate successive top leaves (each pops entirely before the next) until a
     //      useful number of entries is staged; their chunks are recycled ----
@@ -592,11 +602,11 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
         if (c < 0) { mn_fail(im, MN_ERR_INTERNAL); continue; }
         uint4 e = im.q_ent[(size_t)c * MN_QCH + s];
         int rec = (int)e.y;
-        int2 lh = im.rec_lh[rec];
-        float4 v = im.rec_val[rec];
+        int2 lh = MN_REC_LH(im, rec);
+        float4 v = MN_REC_B(im, rec);
         float emp = mn_u2f(e.x);
         int st = mn_entry_state(emp, (int)e.z, (int)e.w, lh, v);
-        if (st == MN_K_UNGUARD) { v.z = -1.0f; im.rec_val[rec] = v; }
+        if (st == MN_K_UNGUARD) { v.z = -1.0f; MN_REC_B(im, rec) = v; }
         else if (st != MN_K_DROP) {
           int p = MN_ATOMIC_ADD(&sm.npr, 1);
           if (p < MN_SB) { sm.sb_mp[p] = emp; sm.sb_lo[p] = (int)e.z; sm.sb_hi[p] = (int)e.w; sm.sb_rec[p] = rec; }
@@ -615,6 +625,7 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
       MN_SYNC();
       nleaf = sm.npr;
     }
+    MN_TOC(MN_CY_RF_LEAVES);
     // ---- the leaf's last entry in pop order bounds what may be taken from the sorted initial
     //      entries: everything else in the tree pops after it ----
     if (MN_T0) {
@@ -649,10 +660,10 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
     MN_FOR(i, ntake) {
       float mp; int lo, hi, rec;
       mn_decode_init(A, im.init_keys[sc + i], &mp, &lo, &hi, &rec);
-      int2 lh = im.rec_lh[rec];
-      float4 v = im.rec_val[rec];
+      int2 lh = MN_REC_LH(im, rec);
+      float4 v = MN_REC_B(im, rec);
       int st = mn_entry_state(mp, lo, hi, lh, v);
-      if (st == MN_K_UNGUARD) { v.z = -1.0f; im.rec_val[rec] = v; st = MN_K_DROP; }
+      if (st == MN_K_UNGUARD) { v.z = -1.0f; MN_REC_B(im, rec) = v; st = MN_K_DROP; }
       int p = nleaf + i;
       sm.sb_mp[p] = st != MN_K_DROP ? mp : MN_NEG_INF; sm.sb_lo[p] = lo; sm.sb_hi[p] = hi; sm.sb_rec[p] = rec;
     }
@@ -686,11 +697,11 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
     MN_FOR(i, nleaf + ntake) {
       if (sm.sb_mp[i] > MN_NEG_INF) {
         const int rec = sm.sb_rec[i];
-        const int2 lh = im.rec_lh[rec];
-        float4 v = im.rec_val[rec];
+        const int2 lh = MN_REC_LH(im, rec);
+        float4 v = MN_REC_B(im, rec);
         if (mn_entry_state(sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i], lh, v) == MN_K_REQUEUE) {
           v.z = v.w;
-          im.rec_val[rec] = v;
+          MN_REC_B(im, rec) = v;
           MN_ATOMIC_ADD(&sm.tmp1, 1);
           if (!sm.cold_empty && mn_before(sm.b_mp, sm.b_lo, sm.b_hi, v.w, lh.x, lh.y)) {  // cold
             int p = MN_ATOMIC_ADD(&sm.nins, 1);
@@ -720,39 +731,20 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
 #ifdef MN_EMUL_TRACE
     fprintf(stderr, "refill: nleaf %d ntake %d more_before %d nins %d cold_empty %d bound %.9g %d %d sc %d ninit %d tree %d\n", nleaf, ntake, (int)more_before, sm.nins, sm.cold_empty, sm.b_mp, sm.b_lo, sm.b_hi, sm.static_cursor, ninit, sm.tree_entries);
 #endif
+    MN_TOC(MN_CY_RF_INIT);
     const int n = nleaf + ntake;
     if (n == 0) {
       if (MN_T0) sm.nhot = 0;
       MN_SYNC();
       return;  // nothing left anywhere (cold_empty set above)
     }
-    if (nleaf <= MN_RANK_MAX && !init_unsorted) {
-      // ---- fast path, no barrier-heavy sort: rank the (few) leaf entries by brute force, compact the
-      //      already sorted initial entries with a scan, then merge the two runs by binary search.
-      //      Duplicates of one record stay adjacent and are dropped when they are popped. ----
-      if (MN_T0) sm.tmp0 = 0;
-      MN_SYNC();
-      MN_FOR(i, nleaf) {
-        int rk = -1;
-        if (sm.sb_mp[i] > MN_NEG_INF) {
-          rk = 0;
-          for (int q = 0; q < nleaf; q++) {
-            if (q == i || !(sm.sb_mp[q] > MN_NEG_INF)) continue;
-            bool qb = mn_before(sm.sb_mp[q], sm.sb_lo[q], sm.sb_hi[q], sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i]);
-            bool ib = mn_before(sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i], sm.sb_mp[q], sm.sb_lo[q], sm.sb_hi[q]);
-            if (qb || (!ib && q < i)) rk++;
-          }
-          MN_ATOMIC_ADD(&sm.tmp0, 1);
-        }
-        sm.ne_pos[i] = rk;
-      }
+    if (!init_unsorted) {
+      // ---- order the leaf entries only (the initial entries are a sorted run already): compact the
+      //      initial run with a scan, sort the leaf part (brute-force ranks when small, else bitonic),
+      //      then merge the two runs by binary search.  Duplicates of one record stay adjacent and are
+      //      dropped when they are popped. ----
       MN_FOR(i, ntake) sm.sb_node[i] = sm.sb_mp[nleaf + i] > MN_NEG_INF ? 1 : 0;
       MN_SYNC();
-      const int nl = sm.tmp0;
-      MN_FOR(i, nleaf) {
-        int p = sm.ne_pos[i];
-        if (p >= 0) { sm.ne_mp[p] = sm.sb_mp[i]; sm.ne_lo[p] = sm.sb_lo[i]; sm.ne_hi[p] = sm.sb_hi[i]; sm.ne_rec[p] = sm.sb_rec[i]; }
-      }
       const int ns = mn_exclusive_scan(sm, sm.sb_node, sm.w.ds.el, ntake);
       const int cur = sm.hsel, dst = sm.hsel ^ 1;
       MN_FOR(i, ntake) {
@@ -761,18 +753,51 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
           sm.hot_mp[cur][p] = sm.sb_mp[q]; sm.hot_lo[cur][p] = sm.sb_lo[q]; sm.hot_hi[cur][p] = sm.sb_hi[q]; sm.hot_rec[cur][p] = sm.sb_rec[q];
         }
       }
+      if (MN_T0) sm.tmp0 = 0;
       MN_SYNC();
+      const bool use_rank = nleaf <= MN_RANK_MAX;
+      if (use_rank) {
+        MN_FOR(i, nleaf) {
+          int rk = -1;
+          if (sm.sb_mp[i] > MN_NEG_INF) {
+            rk = 0;
+            for (int q = 0; q < nleaf; q++) {
+              if (q == i || !(sm.sb_mp[q] > MN_NEG_INF)) continue;
+              bool qb = mn_before(sm.sb_mp[q], sm.sb_lo[q], sm.sb_hi[q], sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i]);
+              bool ib = mn_before(sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i], sm.sb_mp[q], sm.sb_lo[q], sm.sb_hi[q]);
+              if (qb || (!ib && q < i)) rk++;
+            }
+            MN_ATOMIC_ADD(&sm.tmp0, 1);
+          }
+          sm.ne_pos[i] = rk;
+        }
+        MN_SYNC();
+        MN_FOR(i, nleaf) {
+          int p = sm.ne_pos[i];
+          if (p >= 0) { sm.ne_mp[p] = sm.sb_mp[i]; sm.ne_lo[p] = sm.sb_lo[i]; sm.ne_hi[p] = sm.sb_hi[i]; sm.ne_rec[p] = sm.sb_rec[i]; }
+        }
+      } else {
+        const int n2 = mn_pow2_ge(nleaf);
+        MN_FOR(i, n2 - nleaf) { sm.sb_mp[nleaf + i] = MN_NEG_INF; sm.sb_lo[nleaf + i] = INT_MAX; sm.sb_hi[nleaf + i] = INT_MAX; sm.sb_rec[nleaf + i] = -1; }
+        MN_FOR(i, nleaf) if (sm.sb_mp[i] > MN_NEG_INF) MN_ATOMIC_ADD(&sm.tmp0, 1);
+        MN_SYNC();
+        mn_sort_sb(sm, n2);  // valid entries first: pads / invalid sort last
+      }
+      MN_SYNC();
+      const int nl = sm.tmp0;
+      const float* Lmp = use_rank ? sm.ne_mp : sm.sb_mp; const int* Llo = use_rank ? sm.ne_lo : sm.sb_lo;
+      const int* Lhi = use_rank ? sm.ne_hi : sm.sb_hi; const int* Lrec = use_rank ? sm.ne_rec : sm.sb_rec;
       MN_FOR(i, nl) {  // leaf entry i -> i + #initial entries popping before-or-equal it
-        float mp = sm.ne_mp[i]; int lo = sm.ne_lo[i], hi = sm.ne_hi[i];
+        float mp = Lmp[i]; int lo = Llo[i], hi = Lhi[i];
         int a = 0, bnd = ns;
         while (a < bnd) { int mid = (a + bnd) >> 1; if (mn_before(mp, lo, hi, sm.hot_mp[cur][mid], sm.hot_lo[cur][mid], sm.hot_hi[cur][mid])) bnd = mid; else a = mid + 1; }
         int p = i + a;
-        sm.hot_mp[dst][p] = mp; sm.hot_lo[dst][p] = lo; sm.hot_hi[dst][p] = hi; sm.hot_rec[dst][p] = sm.ne_rec[i];
+        sm.hot_mp[dst][p] = mp; sm.hot_lo[dst][p] = lo; sm.hot_hi[dst][p] = hi; sm.hot_rec[dst][p] = Lrec[i];
       }
       MN_FOR(j, ns) {  // initial entry j -> j + #leaf entries popping strictly before it
         float mp = sm.hot_mp[cur][j]; int lo = sm.hot_lo[cur][j], hi = sm.hot_hi[cur][j];
         int a = 0, bnd = nl;
-        while (a < bnd) { int mid = (a + bnd) >> 1; if (mn_before(sm.ne_mp[mid], sm.ne_lo[mid], sm.ne_hi[mid], mp, lo, hi)) a = mid + 1; else bnd = mid; }
+        while (a < bnd) { int mid = (a + bnd) >> 1; if (mn_before(Lmp[mid], Llo[mid], Lhi[mid], mp, lo, hi)) a = mid + 1; else bnd = mid; }
         int p = j + a;
         sm.hot_mp[dst][p] = mp; sm.hot_lo[dst][p] = lo; sm.hot_hi[dst][p] = hi; sm.hot_rec[dst][p] = sm.hot_rec[cur][j];
       }
@@ -797,6 +822,7 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
       if (MN_T0) sm.nhot = sm.tmp0;
       MN_SYNC();
     }
+    MN_TOC(MN_CY_RF_SORT);
     if (sm.nhot > 0 || (sm.cold_empty && sm.nins == 0)) return;
     // everything loaded was invalid: lower the bound again
   }
@@ -836,8 +862,8 @@ MN_D int mn_rec_of_bit(const MnMergeArgs& A, int p, int bit) {
 // clear the two live-mask bits of record slot r
 MN_D void mn_clear_live(const MnImage& im, const MnMergeArgs& A, int r) {
   int p = r / A.K, k = r - p * A.K;
-  MN_ATOMIC_AND(&im.live_mask[p], ~(1u << k));
-  MN_ATOMIC_AND(&im.live_mask[p + A.off.delta[k]], ~(1u << (16 + k)));
+  MN_ATOMIC_AND(&im.obj[p].w, ~(1u << k));
+  MN_ATOMIC_AND(&im.obj[p + A.off.delta[k]].w, ~(1u << (16 + k)));
 }
 // live-mask bits of pixel `pix` that belong to record slot r (0 when r is not a slot of pix)
 MN_D uint32_t mn_own_bits(const MnMergeArgs& A, int pix, int r) {
@@ -894,21 +920,22 @@ MN_D void mn_ovf_erase(MnSm& sm, int rec) {
   for (int i = 0; i < n; i++)
     if (sm.ovf_rec[i] == rec && sm.ovf_lo[i] >= 0) { sm.ovf_lo[i] = -1; sm.ovf_hi[i] = -1; return; }
 }
-// insert with a hint: `islot` was free when the buckets were read
-MN_D void mn_hash_insert_hint(const MnImage& im, MnSm& sm, int lo, int hi, int rec, int islot) {
+// insert with a hint: `islot` was free when the buckets were read.  Returns the slot taken (-1: overflow)
+MN_D int mn_hash_insert_hint(const MnImage& im, MnSm& sm, int lo, int hi, int rec, int islot) {
   MnHashPos p = mn_hash_pos(im.hash_nbuckets, lo, hi);
   uint32_t val = (p.fp << MN_HASH_FP_SHIFT) | (uint32_t)(rec + 1);
-  if (islot >= 0 && MN_ATOMIC_CAS(&im.hash[islot], 0u, val) == 0u) return;
+  if (islot >= 0 && MN_ATOMIC_CAS(&im.hash[islot], 0u, val) == 0u) return islot;
   uint32_t* bk1 = im.hash + (size_t)p.b1 * 8;
   uint32_t* bk2 = im.hash + (size_t)p.b2 * 8;
   for (int w = 0; w < 2; w++) {
     uint32_t* bk = w ? bk2 : bk1;
     for (int s = 0; s < 8; s++)
-      if (bk[s] == 0 && MN_ATOMIC_CAS(&bk[s], 0u, val) == 0u) return;
+      if (bk[s] == 0 && MN_ATOMIC_CAS(&bk[s], 0u, val) == 0u) return (int)(bk - im.hash) + s;
   }
   int i = MN_ATOMIC_ADD(&sm.hash_ovf_n, 1);
   if (i < MN_OVF) { sm.ovf_lo[i] = lo; sm.ovf_hi[i] = hi; sm.ovf_rec[i] = rec; }
   else mn_fail(im, MN_ERR_HASH_FULL);
+  return -1;
 }
 
 // ---- plan the pairs [p0, p1) (record t of candidate j's absorbed object), cc:650-707 -----------
@@ -920,9 +947,10 @@ MN_D void mn_plan_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const
     int i = p0 + ii;
     int j = sm.w.pr.cand[i], t = sm.w.pr.t[i];
     int a = sm.c_surv[j], b = sm.c_abs[j];
-    int2 lh = im.rec_lh[t];
-    float4 v = im.rec_val[t];
-    float tdiff = im.rec_diff[t];
+    const uint4 ta = MN_REC_A(im, t);  // one 32-byte sector: key, hash slot, sums, priorities
+    const float4 v = MN_REC_B(im, t);
+    const int2 lh = make_int2((int)ta.x, (int)ta.y);
+    const float tdiff = mn_u2f(ta.w);
     int x = lh.x == b ? lh.y : lh.x;
     if ((lh.x != b && lh.y != b) || x == a || x < 0) {  // cc:665-673
       mn_fail(im, MN_ERR_INTERNAL);
@@ -931,12 +959,9 @@ MN_D void mn_plan_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const
       continue;
     }
     int nlo = a < x ? a : x, nhi = a < x ? x : a;
-    int olo = b < x ? b : x, ohi = b < x ? x : b;
     MnHashPos pn = mn_hash_pos(im.hash_nbuckets, nlo, nhi);
-    MnHashPos po = mn_hash_pos(im.hash_nbuckets, olo, ohi);
-    uint32_t bn[16], bo[16];
+    uint32_t bn[16];
     mn_load_bucket4(im, pn.b1, bn); mn_load_bucket4(im, pn.b2, bn + 8);
-    mn_load_bucket4(im, po.b1, bo); mn_load_bucket4(im, po.b2, bo + 8);
     uint4 ox = im.obj[x];
     // partner record u = (a, x) if the survivor is already linked to x (cc:685-686)
     int u = -1, islot = -1, f1 = 0, f2 = 0;
@@ -951,30 +976,29 @@ MN_D void mn_plan_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const
     }
     float4 uv = make_float4(0.f, 0.f, 0.f, 0.f); float ud = 0.f;
     if (c0 >= 0) {  // fingerprint matches: key and values of (up to) two candidates in one round trip
-      int2 l0 = im.rec_lh[c0]; float4 v0 = im.rec_val[c0]; float d0 = im.rec_diff[c0];
-      int2 l1 = make_int2(-1, -1); float4 v1 = v0; float d1 = 0.f;
-      if (c1 >= 0) { l1 = im.rec_lh[c1]; v1 = im.rec_val[c1]; d1 = im.rec_diff[c1]; }
-      if (l0.x == nlo && l0.y == nhi) { u = c0; uv = v0; ud = d0; }
-      else if (c1 >= 0 && l1.x == nlo && l1.y == nhi) { u = c1; uv = v1; ud = d1; }
+      uint4 a0 = MN_REC_A(im, c0); float4 v0 = MN_REC_B(im, c0);
+      uint4 a1 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u); float4 v1 = v0;
+      if (c1 >= 0) { a1 = MN_REC_A(im, c1); v1 = MN_REC_B(im, c1); }
+      if ((int)a0.x == nlo && (int)a0.y == nhi) { u = c0; uv = v0; ud = mn_u2f(a0.w); }
+      else if (c1 >= 0 && (int)a1.x == nlo && (int)a1.y == nhi) { u = c1; uv = v1; ud = mn_u2f(a1.w); }
     }
     for (int s = srest; s < 16 && u < 0; s++) {  // (a third fingerprint match: practically never)
       uint32_t hv = bn[s];
       if (hv != 0 && (hv >> MN_HASH_FP_SHIFT) == pn.fp) {
         int r = (int)(hv & ((1u << MN_HASH_FP_SHIFT) - 1)) - 1;
-        int2 l2 = im.rec_lh[r];
-        if (l2.x == nlo && l2.y == nhi) { u = r; uv = im.rec_val[r]; ud = im.rec_diff[r]; }
+        uint4 a2 = MN_REC_A(im, r);
+        if ((int)a2.x == nlo && (int)a2.y == nhi) { u = r; uv = MN_REC_B(im, r); ud = mn_u2f(a2.w); }
       }
     }
     if (u < 0 && novf > 0) {
       u = mn_ovf_find(sm, novf, nlo, nhi);
-      if (u >= 0) { uv = im.rec_val[u]; ud = im.rec_diff[u]; }
+      if (u >= 0) { uv = MN_REC_B(im, u); ud = mn_u2f(MN_REC_A(im, u).w); }
     }
     if (u < 0) {  // free slot for the re-keyed record: the emptier bucket first
       int first = (f1 >= f2) ? 0 : 8;
       for (int s = 0; s < 8 && islot < 0; s++) if (bn[first + s] == 0) islot = (int)((first ? pn.b2 : pn.b1) * 8 + s);
       for (int s = 0; s < 8 && islot < 0; s++) if (bn[(8 - first) + s] == 0) islot = (int)((first ? pn.b1 : pn.b2) * 8 + s);
     }
-    int eslot = mn_bucket_find_val(po, bo, (po.fp << MN_HASH_FP_SHIFT) | (uint32_t)(t + 1));
     float oml = v.x, same = v.y, diff = tdiff, q = v.z;
     if (u >= 0) {  // cc:690-692: that += this
       oml = MN_FADD(uv.x, v.x); diff = MN_FADD(ud, tdiff); same = MN_FADD(uv.y, v.y);
@@ -988,7 +1012,7 @@ MN_D void mn_plan_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const
     else mp = mn_priority(oml, A.omf, A.mlb, A.C, nx, cx, clpx, sm.c_na[j], sm.c_merged[j], clpa, nullptr);
     sm.w.pr.x[i] = x; sm.w.pr.u[i] = u; sm.w.pr.oml[i] = oml; sm.w.pr.same[i] = same; sm.w.pr.diff[i] = diff;
     sm.w.pr.mp[i] = mp; sm.w.pr.lo[i] = nlo; sm.w.pr.hi[i] = nhi; sm.w.pr.q[i] = q;
-    sm.w.pr.eslot[i] = eslot; sm.w.pr.islot[i] = islot;
+    sm.w.pr.eslot[i] = (int)ta.z; sm.w.pr.islot[i] = islot;
     if (mp >= 0.0f) MN_ATOMIC_MAX(&sm.c_maxnew[j], mn_f2u(mp) + 1u);
   }
 }
@@ -1007,16 +1031,17 @@ MN_D void mn_commit_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, int
       float q = mn_store_priority(sm, mp, sm.w.pr.q[i], sm.w.pr.lo[i], sm.w.pr.hi[i], u);
       MN_WATCH(u, "fold-into mp %.9g q_old %.9g q_new %.9g key %d %d (t=%d)", mp, sm.w.pr.q[i], q, sm.w.pr.lo[i], sm.w.pr.hi[i], t);
       MN_WATCH(t, "folded (dies) into %d", u);
-      im.rec_val[u] = make_float4(sm.w.pr.oml[i], sm.w.pr.same[i], q, mp);
-      im.rec_diff[u] = sm.w.pr.diff[i];
-      im.rec_lh[t] = make_int2(-1, -1);  // cc:694
+      MN_REC_B(im, u) = make_float4(sm.w.pr.oml[i], sm.w.pr.same[i], q, mp);
+      reinterpret_cast<float*>(&MN_REC_A(im, u))[3] = sm.w.pr.diff[i];
+      MN_REC_LH(im, t) = make_int2(-1, -1);  // cc:694
       mn_clear_live(im, A, t);
     } else {  // cc:659-664,677,700-706: t is re-keyed to (survivor, x)
       float q = mn_store_priority(sm, mp, sm.w.pr.q[i], sm.w.pr.lo[i], sm.w.pr.hi[i], t);
       MN_WATCH(t, "adopt mp %.9g q_old %.9g q_new %.9g key %d %d", mp, sm.w.pr.q[i], q, sm.w.pr.lo[i], sm.w.pr.hi[i]);
-      im.rec_lh[t] = make_int2(sm.w.pr.lo[i], sm.w.pr.hi[i]);
-      im.rec_val[t] = make_float4(sm.w.pr.oml[i], sm.w.pr.same[i], q, mp);
-      mn_hash_insert_hint(im, sm, sm.w.pr.lo[i], sm.w.pr.hi[i], t, sm.w.pr.islot[i]);
+      MN_REC_LH(im, t) = make_int2(sm.w.pr.lo[i], sm.w.pr.hi[i]);  // (the hash verifies keys through the record)
+      const int hs = mn_hash_insert_hint(im, sm, sm.w.pr.lo[i], sm.w.pr.hi[i], t, sm.w.pr.islot[i]);
+      MN_REC_A(im, t) = make_uint4((uint32_t)sm.w.pr.lo[i], (uint32_t)sm.w.pr.hi[i], (uint32_t)hs, mn_f2u(sm.w.pr.diff[i]));
+      MN_REC_B(im, t) = make_float4(sm.w.pr.oml[i], sm.w.pr.same[i], q, mp);
     }
   }
 }
@@ -1024,11 +1049,13 @@ MN_D void mn_commit_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, int
 // cc:635-647 for accepted merge candidate j: object-level part of Merge (one thread)
 MN_D void mn_commit_merge_object(const MnImage& im, MnSm& sm, const MnMergeArgs& A, int j) {
   int a = sm.c_surv[j], b = sm.c_abs[j], r = sm.c_rec[j];
-  im.obj[a] = make_uint4(mn_pack_nc(sm.c_na[j], sm.c_merged[j]), mn_f2u(sm.c_same[j]), (uint32_t)sm.c_newptr[j], 0u);  // cc:635-642
-  im.parent[b] = a;                                                                                                 // cc:724-725
-  if (sm.c_eslot[j] >= 0) im.hash[sm.c_eslot[j]] = 0;                                                               // cc:645-647
+  // cc:635-642 (obj.w, the live mask of pixel a, is updated concurrently by atomics: leave it alone)
+  *reinterpret_cast<uint2*>(&im.obj[a]) = make_uint2(mn_pack_nc(sm.c_na[j], sm.c_merged[j]), mn_f2u(sm.c_same[j]));
+  im.obj[a].z = (uint32_t)sm.c_newptr[j];
+  im.parent[b] = a;                                        // cc:724-725
+  if (sm.c_eslot[j] >= 0) im.hash[sm.c_eslot[j]] = 0;      // cc:645-647
   else mn_ovf_erase(sm, r);
-  im.rec_lh[r] = make_int2(-1, -1);                                                                                 // cc:726
+  MN_REC_LH(im, r) = make_int2(-1, -1);                    // cc:726
   mn_clear_live(im, A, r);
 }
 
@@ -1108,21 +1135,19 @@ MN_D void mn_hot_update(const MnImage& im, MnSm& sm, int cut) {
 // Stage everything the classification of the first n hot entries needs: one dependent round trip.
 // c_clp holds per candidate [lo vector | hi vector | merged vector], C floats each.
 MN_D void mn_stage_candidates(const MnImage& im, MnSm& sm, const MnMergeArgs& A, float* c_clp, int n) {
-  MN_FOR(w, n * 8) {
-    const int j = w >> 3, role = w & 7;
+  MN_FOR(w, n * 4) {
+    const int j = w >> 2, role = w & 3;
     const int rec = HOT_REC(j), lo = HOT_LO(j), hi = HOT_HI(j);
-    if (role == 0) {
-      sm.c_val[j] = im.rec_val[rec];
+    if (role == 0) {  // the record: one 32-byte sector
+      const uint4 ra = MN_REC_A(im, rec);
+      sm.c_val[j] = MN_REC_B(im, rec);
+      sm.c_lh[j] = make_int2((int)ra.x, (int)ra.y); sm.c_eslot[j] = (int)ra.z; sm.c_rdiff[j] = mn_u2f(ra.w);
       sm.c_rec[j] = rec; sm.c_key[j] = HOT_MP(j); sm.c_lo[j] = lo; sm.c_hi[j] = hi;
       sm.c_kind[j] = MN_K_DROP; sm.c_npairs[j] = 0; sm.c_pfill[j] = 0; sm.c_maxnew[j] = 0; sm.c_conflict[j] = 0;
       sm.c_nb[j] = 0; sm.c_accept[j] = 0; sm.c_cpbase[j] = -1;
-    } else if (role == 1) {
-      sm.c_lh[j] = im.rec_lh[rec];
-      sm.c_rdiff[j] = im.rec_diff[rec];
-    } else if (role == 2) sm.c_obj[j][0] = im.obj[lo];
-    else if (role == 3) sm.c_obj[j][1] = im.obj[hi];
-    else if (role == 4) {
-      sm.c_lm[j][0] = im.live_mask[lo];
+    } else if (role == 1) sm.c_obj[j][0] = im.obj[lo];
+    else if (role == 2) sm.c_obj[j][1] = im.obj[hi];
+    else {
       // duplicates of an earlier window entry: bit 0 same record and priority, bit 1 also the same key
       const float mp = HOT_MP(j);
       int d = 0;
@@ -1131,11 +1156,6 @@ MN_D void mn_stage_candidates(const MnImage& im, MnSm& sm, const MnMergeArgs& A,
         d |= same ? (1 | ((HOT_LO(i) == lo && HOT_HI(i) == hi) ? 2 : 0)) : 0;
       }
       sm.c_dup[j] = d;
-    }
-    else if (role == 5) sm.c_lm[j][1] = im.live_mask[hi];
-    else {
-      MnHashPos p = mn_hash_pos(im.hash_nbuckets, lo, hi);
-      mn_load_bucket4(im, role == 6 ? p.b1 : p.b2, &sm.c_hb[j][role == 6 ? 0 : 8]);
     }
   }
   const int C = A.C;
@@ -1189,8 +1209,6 @@ MN_D void mn_classify(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const f
     const uint4 oa = swap ? o2 : o1, ob = swap ? o1 : o2;
     sm.c_ptra[j] = (int)oa.z; sm.c_ptrb[j] = (int)ob.z;
     sm.c_same[j] = MN_FADD(mn_u2f(oa.y), MN_FADD(v.y, mn_u2f(ob.y)));  // cc:641-642
-    MnHashPos p = mn_hash_pos(im.hash_nbuckets, lo, hi);
-    sm.c_eslot[j] = mn_bucket_find_val(p, sm.c_hb[j], (p.fp << MN_HASH_FP_SHIFT) | (uint32_t)(rec + 1));
   } else {  // cc:563-565
     sm.c_kind[j] = MN_K_RESTORE;
     if (nmp >= 0.0f) sm.c_maxnew[j] = mn_f2u(nmp) + 1u;
@@ -1215,8 +1233,8 @@ MN_D void mn_load_pixels(const MnImage& im, MnSm& sm, const MnMergeArgs& A, int 
   MN_FOR(k, n) {
     const int b = sm.c_abs[j];
     int pix; uint32_t m;
-    if (sm.c_nb[j] == 1) { pix = b; m = sm.c_lm[j][b == sm.c_lo[j] ? 0 : 1]; }
-    else { pix = im.pix_pool[sm.c_ptrb[j] + i0 + k]; m = im.live_mask[pix]; }
+    if (sm.c_nb[j] == 1) { pix = b; m = sm.c_obj[j][b == sm.c_lo[j] ? 0 : 1].w; }
+    else { pix = im.pix_pool[sm.c_ptrb[j] + i0 + k]; m = im.obj[pix].w; }
     m &= ~mn_own_bits(A, pix, sm.c_rec[j]);
     const int cnt = MN_POPC(m);
     sm.pw_pix[s0 + k] = pix; sm.pw_mask[s0 + k] = m; sm.pw_cand[s0 + k] = j; sm.pw_cnt[s0 + k] = cnt;
@@ -1274,7 +1292,6 @@ MN_D void mn_solo_merge(const MnImage& im, MnSm& sm, const MnMergeArgs& A, float
       sm.c_newmp[0] = sm.c_newmp[f]; sm.c_merged[0] = sm.c_merged[f];
       sm.c_surv[0] = sm.c_surv[f]; sm.c_abs[0] = sm.c_abs[f]; sm.c_na[0] = sm.c_na[f]; sm.c_nb[0] = sm.c_nb[f];
       sm.c_ptra[0] = sm.c_ptra[f]; sm.c_ptrb[0] = sm.c_ptrb[f]; sm.c_same[0] = sm.c_same[f]; sm.c_eslot[0] = sm.c_eslot[f];
-      sm.c_lm[0][0] = sm.c_lm[f][0]; sm.c_lm[0][1] = sm.c_lm[f][1];
     }
   }
   MN_SYNC();
@@ -1354,7 +1371,7 @@ MN_D void mn_consume_unguard(const MnImage& im, MnSm& sm, int n) {
     if (sm.c_kind[j] == MN_K_UNGUARD) {
       float4 v = sm.c_val[j];
       v.z = -1.0f;
-      im.rec_val[sm.c_rec[j]] = v;
+      MN_REC_B(im, sm.c_rec[j]) = v;
     }
   }
 }
@@ -1550,7 +1567,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     else MN_FOR(i, n) {
       const int rec = (int)im.hash_ovf[i] - 1;
       int2 lh = make_int2(-1, -1);
-      if (rec >= 0) lh = im.rec_lh[rec];
+      if (rec >= 0) lh = MN_REC_LH(im, rec);
       sm.ovf_lo[i] = lh.x; sm.ovf_hi[i] = lh.y; sm.ovf_rec[i] = rec;
     }
   }
@@ -1558,6 +1575,29 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
   MN_FOR(i, (int)(((MN_NROOTS + 31) / 32 + 31) / 32)) sm.root_sum[i] = 0;
   MN_SYNC();
 
+#if defined(__CUDA_ARCH__) && defined(MN_CALIBRATE)
+  {  // latency calibration (debug builds only): cyc[GC] = 64 dependent random loads by thread 0, then
+     // cyc[REFILL] = 16 x (one random load per thread + barrier)
+    const long long E = (long long)A.N * A.K;
+    if (MN_T0) {
+      long long t0 = clock64();
+      unsigned idx = 12345u;
+      for (int i = 0; i < 64; i++) { int2 v = MN_REC_LH(im, idx % (unsigned)E); idx = idx * 1664525u + 1013904223u + (unsigned)v.x; }
+      sm.cyc[MN_CY_GC] = clock64() - t0 + (idx == 7u ? 1 : 0);
+    }
+    MN_SYNC();
+    long long t0 = clock64();
+    unsigned idx = 777u * (MN_TID + 1);
+    for (int i = 0; i < 16; i++) {
+      int2 v = MN_REC_LH(im, idx % (unsigned)E);
+      idx = idx * 1664525u + 1013904223u + (unsigned)v.x;
+      sm.ct_obj[MN_TID % MN_CT] = (int)idx;
+      MN_SYNC();
+    }
+    if (MN_T0) sm.cyc[MN_CY_REFILL] = clock64() - t0;
+    MN_SYNC();
+  }
+#endif
   for (long long round = 0;; round++) {
     MN_SYNC();
     if (sm.failed) break;
@@ -1575,6 +1615,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     mn_stage_candidates(im, sm, A, c_clp, ncand0);
     MN_FOR(i, MN_CT) { sm.ct_obj[i] = -1; sm.ct_w[i] = INT_MAX; sm.ct_r[i] = INT_MAX; }
     MN_SYNC();
+    MN_TOC(MN_CY_SEL_STAGE);
     MN_FOR(j, ncand0) mn_classify(im, sm, A, c_clp, j);
     MN_SYNC();
     // ---- phase 2: merged class vectors; capacity cut by pixels ----
@@ -1588,6 +1629,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
       MN_TOC(MN_CY_SOLO);
       continue;
     }
+    MN_TOC(MN_CY_SEL_CLASS);
     // ---- phase 3: pixels of the absorbed objects, their live masks, pair counts ----
     {
       const int npw = sm.npw, nm = sm.nm;
@@ -1597,8 +1639,8 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
         const int j = sm.m_list[a], idx = i - sm.m_base[a];
         const int b = sm.c_abs[j];
         int pix; uint32_t m;
-        if (sm.c_nb[j] == 1) { pix = b; m = sm.c_lm[j][b == sm.c_lo[j] ? 0 : 1]; }
-        else { pix = im.pix_pool[sm.c_ptrb[j] + idx]; m = im.live_mask[pix]; }
+        if (sm.c_nb[j] == 1) { pix = b; m = sm.c_obj[j][b == sm.c_lo[j] ? 0 : 1].w; }
+        else { pix = im.pix_pool[sm.c_ptrb[j] + idx]; m = im.obj[pix].w; }
         m &= ~mn_own_bits(A, pix, sm.c_rec[j]);
         const int cnt = MN_POPC(m);
         sm.pw_pix[i] = pix; sm.pw_mask[i] = m; sm.pw_cand[i] = j; sm.pw_cnt[i] = cnt;
@@ -1631,7 +1673,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
       }
     }
     MN_SYNC();
-    MN_TOC(MN_CY_SELECT);
+    MN_TOC(MN_CY_SEL_PIX);
     // ---- phase 4: plan ----
     mn_plan_pairs(im, sm, A, c_clp, 0, npr);
     MN_SYNC();
@@ -1681,17 +1723,17 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
         float4 v = sm.c_val[j];
         v.w = sm.c_newmp[j];
         v.z = mn_store_priority(sm, v.w, -1.0f, sm.c_lo[j], sm.c_hi[j], rec);
-        im.rec_val[rec] = v;
+        MN_REC_B(im, rec) = v;
       } else if (k == MN_K_MERGE) {
         mn_commit_merge_object(im, sm, A, j);
       } else if (k == MN_K_REQUEUE) {
         float4 v = sm.c_val[j];
         v.z = mn_store_priority(sm, v.w, -1.0f, sm.c_lh[j].x, sm.c_lh[j].y, rec);
-        im.rec_val[rec] = v;
+        MN_REC_B(im, rec) = v;
       } else if (k == MN_K_UNGUARD) {
         float4 v = sm.c_val[j];
         v.z = -1.0f;
-        im.rec_val[rec] = v;
+        MN_REC_B(im, rec) = v;
       }
     }
     MN_FOR(i, ncand * A.C) {

@@ -30,12 +30,9 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   im.cls = zalloc<int>(N);
   im.obj = zalloc<uint4>(N);
   im.parent = zalloc<int>(N);
-  im.live_mask = zalloc<uint32_t>(N);
   im.pix_cap = 16 * N + 4096;
   im.pix_pool = zalloc<int>(im.pix_cap);
-  im.rec_lh = zalloc<int2>(E);
-  im.rec_val = zalloc<float4>(E);
-  im.rec_diff = zalloc<float>(E);
+  im.rec = zalloc<uint4>(2 * E);
   im.hash_nbuckets = (uint32_t)(E * 16 / 10 / 8 + 64);
   im.hash = zalloc<uint32_t>((size_t)im.hash_nbuckets * 8);
   im.hash_ovf_cap = 4096;
@@ -45,7 +42,7 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   im.q_ent = zalloc<uint4>((size_t)im.qc_cap * MN_QCH);
   im.qc_next = zalloc<int>(im.qc_cap);
   im.qc_free = zalloc<int>(im.qc_cap);
-  im.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)(8192 + E / 256);
+  im.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)(16384 + E / 128);
   im.tn = zalloc<int4>(im.tn_cap);
   im.tn_dir = zalloc<int>((size_t)im.tn_cap * 8);
   im.ctl = zalloc<MnCtl>(1);
@@ -86,7 +83,7 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
       r2 = row - offsets[2 * k]; c2 = col - offsets[2 * k + 1];
       if (r2 >= 0 && r2 < H && c2 >= 0 && c2 < W) m |= 1u << (16 + k);
     }
-    im.live_mask[p] = m;
+    im.obj[p].w = m;
     for (int k = 0; k < K; k++) {
       size_t r = (size_t)p * K + k;
       int r2 = row + offsets[2 * k], c2 = col + offsets[2 * k + 1];
@@ -97,17 +94,17 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
         float diff = (float)log(1.0 - (double)s), same = logf(s), oml = same - diff;
         float mp = mn_priority(oml, omf, mlb, C, 1, im.cls[lo], im.clp + (size_t)lo * C, 1, im.cls[hi],
                                im.clp + (size_t)hi * C, nullptr);
-        im.rec_lh[r] = make_int2(lo, hi);
-        im.rec_val[r] = make_float4(oml, same, mp >= 0.0f ? mp : -1.0f, mp);
-        im.rec_diff[r] = diff;
-        mn_hash_insert(im, lo, hi, (int)r);
+        MN_REC_LH(im, r) = make_int2(lo, hi);
+        int hslot = mn_hash_insert(im, lo, hi, (int)r);
+        MN_REC_A(im, r) = make_uint4((uint32_t)lo, (uint32_t)hi, (uint32_t)hslot, mn_f2u(diff));
+        MN_REC_B(im, r) = make_float4(oml, same, mp >= 0.0f ? mp : -1.0f, mp);
         if (mp >= 0.0f) {
           uint32_t ord = (uint32_t)lo * (uint32_t)K + (uint32_t)rank_of_k[k];
           key = ((uint64_t)(~mn_f2u(mp == 0.0f ? 0.0f : mp)) << MN_ORD_BITS) | ord;
         }
       } else {
-        im.rec_lh[r] = make_int2(-1, -1);
-        im.rec_val[r] = make_float4(0, 0, -1.0f, -1.0f);
+        MN_REC_A(im, r) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
+        MN_REC_B(im, r) = make_float4(0, 0, -1.0f, -1.0f);
       }
       im.init_keys[r] = key;
     }
@@ -136,8 +133,8 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   }
   int status = im.ctl->status;
   if (getenv("EMUL_DEBUG")) {
-    for (size_t r = 0; r < E; r++) if (im.rec_lh[r].x >= 0 && im.rec_val[r].w >= 0.0f)
-      fprintf(stderr, "LEFTOVER rec %zu lo %d hi %d mp %.9g (bits %08x) root %d\n", r, im.rec_lh[r].x, im.rec_lh[r].y, im.rec_val[r].w, mn_f2u(im.rec_val[r].w), mn_root_of(im.rec_val[r].w));
+    for (size_t r = 0; r < E; r++) if (MN_REC_LH(im, r).x >= 0 && MN_REC_B(im, r).w >= 0.0f)
+      fprintf(stderr, "LEFTOVER rec %zu lo %d hi %d mp %.9g (bits %08x) root %d\n", r, MN_REC_LH(im, r).x, MN_REC_LH(im, r).y, MN_REC_B(im, r).w, mn_f2u(MN_REC_B(im, r).w), mn_root_of(MN_REC_B(im, r).w));
     fprintf(stderr, "status %d fail_line %d hash_ovf_n %d peak_entries %d peak_chunks %d (E %zu) tn_bump %d qc_bump %d pix_bump %d\n", im.ctl->status, im.ctl->fail_line, im.ctl->hash_ovf_n, im.ctl->peak_entries, im.ctl->peak_chunks, E, im.ctl->tn_bump, im.ctl->qc_bump, im.ctl->pix_bump);
     fprintf(stderr, "tree_entries %d static_cursor %d n_init %d nins %d nhot %d cold_empty %d\n", im.ctl->tree_entries, im.ctl->static_cursor, im.ctl->n_init, sm->nins, sm->nhot, sm->cold_empty);
   }
