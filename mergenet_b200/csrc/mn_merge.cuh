@@ -50,6 +50,7 @@
 #define MN_SB 1024       // sort buffer capacity
 #define MN_LEAFCAP 512   // tree leaves larger than this are split before they are loaded
 #define MN_CT 2048       // conflict-table slots (power of two)
+#define MN_LF 128         // leaves one refill may load
 #define MN_OVF 128        // records in the hash overflow area (cached in shared memory)
 #define MN_REFILL_TARGET 384      // stop loading tree leaves once this many entries are staged
 #define MN_REFILL_STATIC_MIN 128  // sort-buffer slots always left for initial entries
@@ -98,6 +99,8 @@ struct MnSm {
   uint32_t root_bits[(MN_NROOTS + 31) / 32];
   uint32_t root_sum[((MN_NROOTS + 31) / 32 + 31) / 32];
   int cw_chunk[MN_CW];
+  int lf_start[MN_LF + 1]; int lf_cnt[MN_LF]; int lf_base[MN_LF]; int nlf;  // leaves of one refill: sb ranges
+  int red_idx[1024];  // argmax reduction scratch
   int4 scan_nd[MN_TREE_FANOUT]; int4 leaf_nd; int path_cnt[32];
   int qc_free_top, qc_bump, tn_bump, tree_entries, static_cursor, n_init;  // mirrors of MnCtl
   int peak_entries, peak_chunks;
@@ -581,9 +584,9 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
     // ---- load + validate successive top leaves (each pops entirely before the next) until a
     //      useful number of entries is staged; their chunks are recycled ----
     int nleaf = 0;
-    if (MN_T0) sm.npr = 0;
+    if (MN_T0) { sm.npr = 0; sm.nlf = 0; sm.lf_start[0] = 0; }
     MN_SYNC();
-    for (int lguard = 0; lguard < 4096 && nleaf < MN_REFILL_TARGET; lguard++) {
+    for (int lguard = 0; lguard < MN_LF && nleaf < MN_REFILL_TARGET; lguard++) {
       int root = 0;
       int leaf = mn_top_leaf(im, sm, &root, nleaf == 0);  // splitting reuses the staging buffers
       if (nleaf == 0) { MN_SYNC(); if (MN_T0) sm.npr = 0; MN_SYNC(); }  // (a split used npr)
@@ -621,6 +624,7 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
         const int root_cnt = sm.path_n > 0 ? sm.path_cnt[0] - have : 0;
         if (root_cnt <= 0) mn_root_clear(sm, root);
         if (sm.npr > MN_SB) { mn_fail(im, MN_ERR_INTERNAL); sm.npr = MN_SB; }
+        if (sm.npr > sm.lf_start[sm.nlf]) { sm.nlf++; sm.lf_start[sm.nlf] = sm.npr; }  // its entries: a contiguous sb range
       }
       MN_SYNC();
       nleaf = sm.npr;
@@ -628,14 +632,22 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
     MN_TOC(MN_CY_RF_LEAVES);
     // ---- the leaf's last entry in pop order bounds what may be taken from the sorted initial
     //      entries: everything else in the tree pops after it ----
-    if (MN_T0) {
-      int w = -1;
-      for (int i = 0; i < nleaf; i++)
-        if (w < 0 || mn_before(sm.sb_mp[w], sm.sb_lo[w], sm.sb_hi[w], sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i])) w = i;
-      sm.tmp0 = w;
-      sm.tmp2 = 0;
+    {  // (leaves were loaded in pop order: the last one holds it; tournament over its sb range)
+      const int r0 = sm.nlf > 0 ? sm.lf_start[sm.nlf - 1] : 0, m = nleaf - r0;
+      MN_FOR(i, m) sm.red_idx[i] = r0 + i;
+      MN_SYNC();
+      for (int len = m; len > 1;) {
+        const int half = (len + 1) >> 1;
+        MN_FOR(i, len - half) {
+          const int a = sm.red_idx[i], b = sm.red_idx[half + i];
+          if (mn_before(sm.sb_mp[a], sm.sb_lo[a], sm.sb_hi[a], sm.sb_mp[b], sm.sb_lo[b], sm.sb_hi[b])) sm.red_idx[i] = b;
+        }
+        MN_SYNC();
+        len = half;
+      }
+      if (MN_T0) { sm.tmp0 = m > 0 ? sm.red_idx[0] : -1; sm.tmp2 = 0; }
+      MN_SYNC();
     }
-    MN_SYNC();
     const int w = sm.tmp0;
     const float lmp = w >= 0 ? sm.sb_mp[w] : 0.f; const int llo = w >= 0 ? sm.sb_lo[w] : 0, lhi = w >= 0 ? sm.sb_hi[w] : 0;
     const int sc = sm.static_cursor, ninit = sm.n_init;
@@ -703,20 +715,13 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
           v.z = v.w;
           MN_REC_B(im, rec) = v;
           MN_ATOMIC_ADD(&sm.tmp1, 1);
-          if (!sm.cold_empty && mn_before(sm.b_mp, sm.b_lo, sm.b_hi, v.w, lh.x, lh.y)) {  // cold
-            int p = MN_ATOMIC_ADD(&sm.nins, 1);
-            sm.ins_mp[p] = v.w; sm.ins_lo[p] = lh.x; sm.ins_hi[p] = lh.y; sm.ins_rec[p] = rec;
-            sm.sb_mp[i] = MN_NEG_INF;
-          } else {  // still hot-bound: re-key in place (an initial entry then breaks its sorted run)
-            sm.sb_mp[i] = v.w; sm.sb_lo[i] = lh.x; sm.sb_hi[i] = lh.y;
-            if (i >= nleaf) sm.tmp0 = 1;
-          }
+          mn_push_entry(sm, v.w, lh.x, lh.y, rec);  // cold -> insert buffer; still hot-bound -> ne, merged below
+          sm.sb_mp[i] = MN_NEG_INF;
         }
       }
     }
     MN_SYNC();
     if (MN_T0) { sm.st_requeues += sm.tmp1; sm.tmp1 = 0; }
-    const bool init_unsorted = sm.tmp0 != 0;
     if (more_before) {
       // push the leaf entries that pop after the bound back to the insert buffer
       MN_FOR(i, nleaf) {
@@ -738,11 +743,14 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
       MN_SYNC();
       return;  // nothing left anywhere (cold_empty set above)
     }
-    if (!init_unsorted) {
-      // ---- order the leaf entries only (the initial entries are a sorted run already): compact the
-      //      initial run with a scan, sort the leaf part (brute-force ranks when small, else bitonic),
-      //      then merge the two runs by binary search.  Duplicates of one record stay adjacent and are
-      //      dropped when they are popped. ----
+    {
+      // ---- order the batch: the initial entries are a sorted run already (compacted with a scan); the
+      //      leaf entries are ranked inside their own leaf (leaves were loaded in pop order, so a
+      //      leaf's entries all pop before the next leaf's), which needs no barrier-heavy sort; then
+      //      the two runs are merged by binary search.  Duplicates of one record stay adjacent and
+      //      are dropped when they are popped. ----
+      const int nlf = sm.nlf;
+      MN_FOR(k, nlf) sm.lf_cnt[k] = 0;
       MN_FOR(i, ntake) sm.sb_node[i] = sm.sb_mp[nleaf + i] > MN_NEG_INF ? 1 : 0;
       MN_SYNC();
       const int ns = mn_exclusive_scan(sm, sm.sb_node, sm.w.ds.el, ntake);
@@ -753,40 +761,39 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
           sm.hot_mp[cur][p] = sm.sb_mp[q]; sm.hot_lo[cur][p] = sm.sb_lo[q]; sm.hot_hi[cur][p] = sm.sb_hi[q]; sm.hot_rec[cur][p] = sm.sb_rec[q];
         }
       }
-      if (MN_T0) sm.tmp0 = 0;
-      MN_SYNC();
-      const bool use_rank = nleaf <= MN_RANK_MAX;
-      if (use_rank) {
-        MN_FOR(i, nleaf) {
-          int rk = -1;
-          if (sm.sb_mp[i] > MN_NEG_INF) {
-            rk = 0;
-            for (int q = 0; q < nleaf; q++) {
-              if (q == i || !(sm.sb_mp[q] > MN_NEG_INF)) continue;
-              bool qb = mn_before(sm.sb_mp[q], sm.sb_lo[q], sm.sb_hi[q], sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i]);
-              bool ib = mn_before(sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i], sm.sb_mp[q], sm.sb_lo[q], sm.sb_hi[q]);
-              if (qb || (!ib && q < i)) rk++;
-            }
-            MN_ATOMIC_ADD(&sm.tmp0, 1);
+      MN_FOR(i, nleaf) {
+        int rk = -1, k = 0;
+        if (sm.sb_mp[i] > MN_NEG_INF) {
+          int a = 0, bnd = nlf;  // leaf of entry i: last k with lf_start[k] <= i
+          while (a + 1 < bnd) { int mid = (a + bnd) >> 1; if (sm.lf_start[mid] <= i) a = mid; else bnd = mid; }
+          k = a;
+          rk = 0;
+          const float mp = sm.sb_mp[i]; const int lo = sm.sb_lo[i], hi = sm.sb_hi[i];
+          for (int q = sm.lf_start[k]; q < sm.lf_start[k + 1]; q++) {
+            const float qmp = sm.sb_mp[q];
+            if (q == i || !(qmp > MN_NEG_INF)) continue;
+            bool qb = mn_before(qmp, sm.sb_lo[q], sm.sb_hi[q], mp, lo, hi);
+            bool ib = mn_before(mp, lo, hi, qmp, sm.sb_lo[q], sm.sb_hi[q]);
+            if (qb || (!ib && q < i)) rk++;
           }
-          sm.ne_pos[i] = rk;
+          MN_ATOMIC_ADD(&sm.lf_cnt[k], 1);
         }
-        MN_SYNC();
-        MN_FOR(i, nleaf) {
-          int p = sm.ne_pos[i];
-          if (p >= 0) { sm.ne_mp[p] = sm.sb_mp[i]; sm.ne_lo[p] = sm.sb_lo[i]; sm.ne_hi[p] = sm.sb_hi[i]; sm.ne_rec[p] = sm.sb_rec[i]; }
-        }
-      } else {
-        const int n2 = mn_pow2_ge(nleaf);
-        MN_FOR(i, n2 - nleaf) { sm.sb_mp[nleaf + i] = MN_NEG_INF; sm.sb_lo[nleaf + i] = INT_MAX; sm.sb_hi[nleaf + i] = INT_MAX; sm.sb_rec[nleaf + i] = -1; }
-        MN_FOR(i, nleaf) if (sm.sb_mp[i] > MN_NEG_INF) MN_ATOMIC_ADD(&sm.tmp0, 1);
-        MN_SYNC();
-        mn_sort_sb(sm, n2);  // valid entries first: pads / invalid sort last
+        sm.w.ds.node[i] = k; sm.w.ds.tail[i] = rk;
       }
       MN_SYNC();
+      if (MN_T0) { int acc = 0; for (int k = 0; k < nlf; k++) { sm.lf_base[k] = acc; acc += sm.lf_cnt[k]; } sm.tmp0 = acc; }
+      MN_SYNC();
       const int nl = sm.tmp0;
-      const float* Lmp = use_rank ? sm.ne_mp : sm.sb_mp; const int* Llo = use_rank ? sm.ne_lo : sm.sb_lo;
-      const int* Lhi = use_rank ? sm.ne_hi : sm.sb_hi; const int* Lrec = use_rank ? sm.ne_rec : sm.sb_rec;
+      // the sorted leaf run goes to the (idle) tail of the pair-plan arrays, which distribute()'s scratch does not cover
+      float* Lmp = sm.w.pr.mp; int* Llo = sm.w.pr.lo; int* Lhi = sm.w.pr.hi; int* Lrec = sm.w.pr.eslot;
+      MN_FOR(i, nleaf) {
+        const int rk = sm.w.ds.tail[i];
+        if (rk >= 0) {
+          const int p = sm.lf_base[sm.w.ds.node[i]] + rk;
+          Lmp[p] = sm.sb_mp[i]; Llo[p] = sm.sb_lo[i]; Lhi[p] = sm.sb_hi[i]; Lrec[p] = sm.sb_rec[i];
+        }
+      }
+      MN_SYNC();
       MN_FOR(i, nl) {  // leaf entry i -> i + #initial entries popping before-or-equal it
         float mp = Lmp[i]; int lo = Llo[i], hi = Lhi[i];
         int a = 0, bnd = ns;
@@ -804,24 +811,8 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
       MN_SYNC();
       if (MN_T0) { sm.hsel = dst; sm.nhot = nl + ns; }
       MN_SYNC();
-    } else {
-      const int n2 = mn_pow2_ge(n);
-      MN_FOR(i, n2 - n) { sm.sb_mp[n + i] = MN_NEG_INF; sm.sb_lo[n + i] = INT_MAX; sm.sb_hi[n + i] = INT_MAX; sm.sb_rec[n + i] = -1; }
-      MN_SYNC();
-      mn_sort_sb(sm, n2);
-      // valid entries first (pads / invalid sort last); they are a prefix after the sort
-      if (MN_T0) sm.tmp0 = 0;
-      MN_SYNC();
-      MN_FOR(i, n) {
-        if (sm.sb_mp[i] > MN_NEG_INF) {
-          MN_ATOMIC_ADD(&sm.tmp0, 1);
-          HOT_MP(i) = sm.sb_mp[i]; HOT_LO(i) = sm.sb_lo[i]; HOT_HI(i) = sm.sb_hi[i]; HOT_REC(i) = sm.sb_rec[i];
-        }
-      }
-      MN_SYNC();
-      if (MN_T0) sm.nhot = sm.tmp0;
-      MN_SYNC();
     }
+    if (sm.nne > 0) mn_hot_update(im, sm, 0);  // exact entries of requeued guards that are still hot-bound
     MN_TOC(MN_CY_RF_SORT);
     if (sm.nhot > 0 || (sm.cold_empty && sm.nins == 0)) return;
     // everything loaded was invalid: lower the bound again
