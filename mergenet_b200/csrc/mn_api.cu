@@ -127,16 +127,20 @@ __global__ void mn_label_write_kernel(const MnImage* imgs, int nimg, int N, int*
 
 __global__ void mn_libm_kernel(int which, uint32_t first_bits, uint32_t n, float bias, float* out) {
   __shared__ MnLogfTab tab[16];
+  __shared__ MnLog1mTab tab1m[128];
   if (threadIdx.x < 16) {
     const MnLogfTab t16[16] = {MN_LOGF_TABLE};
     tab[threadIdx.x] = t16[threadIdx.x];
   }
+  if (threadIdx.x < 128) tab1m[threadIdx.x] = mn_log1m_table[threadIdx.x];
   __syncthreads();
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float x = __uint_as_float(first_bits + i);
     float r;
-    if (which == 0) r = mn_logf_exact(x, tab);
-    else if (which == 1) r = mn_log1m_exact(x);
+    if (which == 0) r = mn_logf_fast(x, tab);            // what the edge pass evaluates
+    else if (which == 1) r = mn_log1m_fast(x, tab1m);
+    else if (which == 3) r = mn_logf_exact(x, tab);      // the unfused recipe (bias path)
+    else if (which == 4) r = mn_log1m_exact(x);
     else r = mn_bias_sameness(x, bias, tab);
     out[i] = r;
   }
@@ -212,15 +216,15 @@ extern "C" size_t mn_workspace_bytes_per_image(int H, int W, int C, int K) {
 }
 
 static int choose_edge_tile(int C, int K, int* smem_bytes) {
-  // per pixel: double-buffered inputs 2*(C+K) floats + staged outputs (C + 2K) floats
-  const size_t per_px = 4 * (size_t)(2 * (C + K) + C + 2 * K);
-  size_t budget = 200 * 1024;
+  // per pixel: double-buffered inputs 2*(C+K) floats + double-buffered staged outputs 2*(C + 2K) floats
+  const size_t per_px = 4 * (size_t)(2 * (C + K) + 2 * (C + 2 * K));
+  size_t budget = 220 * 1024;
   int tp = (int)(budget / per_px);
   tp = std::min(tp, 512);
   tp = tp / 4 * 4;
   if (tp >= 128) tp = tp / 128 * 128;
   if (tp < 4) tp = 4;
-  *smem_bytes = (int)(128 + per_px * tp + 16 * sizeof(MnLogfTab) + 64);
+  *smem_bytes = (int)(128 + per_px * tp + 16 * sizeof(MnLogfTab) + 128 * sizeof(MnLog1mTab) + 64);
   return tp;
 }
 
@@ -358,7 +362,7 @@ static int run_front(mn_plan* p, int B, const float* d_class, float* d_adj, int 
   P.clip = clip; P.sdb = sdb;
   long long tiles = (long long)B * P.tiles_per_image;
   int grid = (int)std::min<long long>(tiles, p->num_sms);
-  mn_edge_pass_kernel<<<grid, 512, p->edge_smem, s>>>(P);
+  mn_edge_pass_kernel<<<grid, MN_EDGE_THREADS, p->edge_smem, s>>>(P);
   p->timings.edge_launches++;
   MN_CUDA_OK(cudaEventRecord(p->ev[2], s));
   for (int b = 0; b < B; b++) {

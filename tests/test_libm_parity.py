@@ -66,6 +66,16 @@ def test_device_log1m_equals_host_exhaustive(oracle_mod, lib_mod):
 
 
 @pytest.mark.gpu
+def test_device_unfused_recipes_equal_host_sampled(oracle_mod, lib_mod):
+    """The unfused logf recipe and the plain fp64 log (used by the same_different_bias path)."""
+    L = oracle_mod.oracle_lib()
+    bad, first = _device_vs_host(oracle_mod, lib_mod, 3, L.mno_host_logf_table, stride_chunks=3)
+    assert bad == 0, first[:5]
+    bad, first = _device_vs_host(oracle_mod, lib_mod, 4, L.mno_host_log1m_table, stride_chunks=3)
+    assert bad == 0, first[:5]
+
+
+@pytest.mark.gpu
 def test_device_bias_transform_equals_host_sampled(oracle_mod, lib_mod):
     # same_different_bias != 0 (segment.cc:183-195): every 4th 16M-chunk of the domain, two biases
     for bias in (0.5, -1.25):
