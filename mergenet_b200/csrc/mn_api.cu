@@ -188,7 +188,7 @@ static WsLayout ws_layout(int H, int W, int C, int K) {
   // queue entry pool: 16-byte entries in chunks of MN_QCH; it aliases rec_same | rec_diff (8*E bytes,
   // dead after record init) and extends past them: one chunk per live tree leaf plus the entries.
   L.qc_cap = (int)(E * 3 / 4 / MN_QCH + 4 * MN_NROOTS + 4096);  // measured peak: 0.6 E entries
-  L.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)std::max<size_t>(16384, E / 128);
+  L.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)std::max<size_t>(4096, E / 512);  // measured: < E / 1700 splits
   L.hash_nbuckets = (uint32_t)(E * 18 / 10 / 8 + 64);
   L.hash_ovf_cap = 16384;
   L.clp = take(N * C * 4);
