@@ -239,6 +239,8 @@ def run_own_arm(args):
     ms, edge_ms, merge_ms, launches = timed(step_device, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     stats = [seg.stats(b) for b in range(B)]
+    tm_dev = seg.timings()
+    logprob0 = seg.total_logprob(0)[3]
     value = world * B * args.steps / (ms / 1e3)
 
     # e2e through the host-buffer ABI (one warm-up, then the same number of steps).  The device-resident
@@ -296,7 +298,15 @@ def run_own_arm(args):
                           "us_per_round": 1e6 * merge_s / max(1.0, float(np.max(rounds))),
                           "merges_per_s_per_image": float(np.mean(merges)) / merge_s,
                           "merges_per_s_batch": float(np.sum(merges)) / merge_s},
-            "phases_ms": {k: seg.timings()[k] for k in ("edge_ms", "record_init_sort_ms", "merge_ms", "label_ms")},
+            "phases_ms": {k: tm_dev[k] for k in ("edge_ms", "record_init_sort_ms", "merge_ms", "aggregate_ms", "label_ms")},
+            # second HBM-bound pass: total log-prob terms from the maintained sums (segment.cc:272-287);
+            # algorithmic bytes per image: obj 16 N + parent 4 N + record key/differentness halves 16 E
+            "aggregation": {"kernel": "mn_logprob_kernel", "bound": "hbm", "unit": "GB/s",
+                            "algorithmic_bytes_per_launch": float(B * (20 * n + 16 * n * K)),
+                            "avg_launch_ms": tm_dev["aggregate_ms"],
+                            "achieved": B * (20 * n + 16 * n * K) / max(1e-9, tm_dev["aggregate_ms"] * 1e-3) / 1e9,
+                            "frac": B * (20 * n + 16 * n * K) / max(1e-9, tm_dev["aggregate_ms"] * 1e-3) / 1e9 / peak,
+                            "total_logprob_image0": logprob0},
         }
         print(json.dumps(line))
     seg.close()

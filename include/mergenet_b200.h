@@ -78,7 +78,7 @@ typedef struct {
 
 /* Device time of the phases of the last batch (CUDA events on the plan's stream), milliseconds. */
 typedef struct {
-  float h2d_ms, edge_ms, record_init_sort_ms, merge_ms, label_ms, d2h_ms, total_ms;
+  float h2d_ms, edge_ms, record_init_sort_ms, merge_ms, label_ms, d2h_ms, total_ms, aggregate_ms;
   long long edge_launches, other_launches; /* kernels of this library launched by the last batch */
 } mn_timings;
 
@@ -110,6 +110,12 @@ int mn_segment_batch_host(mn_plan* plan, int batch, const float* h_class, float*
 
 int mn_plan_image_stats(mn_plan* plan, int image, mn_image_stats* out);
 int mn_plan_timings(mn_plan* plan, mn_timings* out);
+/* Total log-probability of the last run's segmentation of `image`, the quantity the reference prints
+ * in ShowStats (segment.cc:236-287: ComputeTotalLogprob) and does not return: out4 = {sum over
+ * surviving objects of their class log-prob, sum of the sameness inside objects, sum over surviving
+ * records of differentness, class + object_merge_factor * (differentness + sameness)}.  Computed on
+ * the GPU by an aggregation pass over the statistics the merges maintained. */
+int mn_plan_image_logprob(mn_plan* plan, int image, double* out4);
 
 /* ---- test hooks (parity tests call these through the same library) --------------------------- */
 /* Edge pass + record init of ONE image (host buffers in, host buffers out), i.e. what the reference

@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXPORTS = ["c_run_segmentation", "mn_last_error", "mn_status_string", "mn_device_count",
            "mn_workspace_bytes_per_image", "mn_plan_create", "mn_plan_destroy",
            "mn_segment_batch_device", "mn_segment_batch_host", "mn_plan_image_stats",
-           "mn_plan_timings", "mn_debug_edge_dump", "mn_debug_libm"]
+           "mn_plan_timings", "mn_plan_image_logprob", "mn_debug_edge_dump", "mn_debug_libm"]
 
 
 class MergeNetError(RuntimeError):
@@ -72,7 +72,7 @@ class ImageStats(ctypes.Structure):
 
 class Timings(ctypes.Structure):
     _fields_ = [(n, ctypes.c_float) for n in ("h2d_ms", "edge_ms", "record_init_sort_ms", "merge_ms",
-                                               "label_ms", "d2h_ms", "total_ms")] + [
+                                               "label_ms", "d2h_ms", "total_ms", "aggregate_ms")] + [
         ("edge_launches", ctypes.c_longlong), ("other_launches", ctypes.c_longlong)]
 
     def as_dict(self):
@@ -115,6 +115,8 @@ def lib():
                                         ctypes.c_float, ctypes.c_float]
     L.mn_plan_image_stats.restype = ctypes.c_int
     L.mn_plan_image_stats.argtypes = [_V, ctypes.c_int, ctypes.POINTER(ImageStats)]
+    L.mn_plan_image_logprob.restype = ctypes.c_int
+    L.mn_plan_image_logprob.argtypes = [_V, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     L.mn_plan_timings.restype = ctypes.c_int
     L.mn_plan_timings.argtypes = [_V, ctypes.POINTER(Timings)]
     L.mn_debug_edge_dump.restype = ctypes.c_int

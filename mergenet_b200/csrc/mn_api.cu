@@ -125,6 +125,41 @@ __global__ void mn_label_write_kernel(const MnImage* imgs, int nimg, int N, int*
   }
 }
 
+// Aggregation pass (cc:272-287, ComputeTotalLogprob): the sufficient statistics the merges maintained
+// -- per surviving object its class log-prob and the sameness inside it, per surviving record its
+// differentness -- summed per image.  A pure HBM-bound streaming reduction over obj[N] (16 B), the
+// class vectors of the roots, and the record sectors rec[E] (first half, 16 B of each 32 B); fp32
+// accumulators are added up in fp64 (block tree, then one atomicAdd per block and term).
+__global__ void __launch_bounds__(256) mn_logprob_kernel(const MnImage* imgs, int nimg, int N, int C, long long E,
+                                                         double* out /* [nimg][4] */) {
+  __shared__ double red[3][256];
+  for (int b = blockIdx.y; b < nimg; b += gridDim.y) {
+    const MnImage im = imgs[b];
+    double tc = 0.0, ts = 0.0, td = 0.0;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    for (long long p = tid; p < N; p += nth) {
+      if (im.parent[p] == (int)p) {
+        const uint4 o = im.obj[p];
+        tc += (double)im.clp[(size_t)p * C + mn_nc_cls(o.x)];
+        ts += (double)mn_u2f(o.y);
+      }
+    }
+    for (long long r = tid; r < E; r += nth) {
+      const uint4 a = im.rec[2 * r];
+      if ((int)a.x >= 0) td += (double)mn_u2f(a.w);
+    }
+    red[0][threadIdx.x] = tc; red[1][threadIdx.x] = ts; red[2][threadIdx.x] = td;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if ((int)threadIdx.x < s)
+        for (int k = 0; k < 3; k++) red[k][threadIdx.x] += red[k][threadIdx.x + s];
+      __syncthreads();
+    }
+    if (threadIdx.x < 3) atomicAdd(&out[(size_t)b * 4 + threadIdx.x], red[threadIdx.x][0]);
+    __syncthreads();
+  }
+}
+
 __global__ void mn_libm_kernel(int which, uint32_t first_bits, uint32_t n, float bias, float* out) {
   __shared__ MnLogfTab tab[16];
   __shared__ MnLog1mTab tab1m[128];
@@ -164,10 +199,13 @@ struct mn_plan {
   float* d_in_class; float* d_in_adj; int* d_out_mask; int* d_out_cls; int* d_out_ninst;
   size_t staging_batch;
   cudaStream_t stream;
-  cudaEvent_t ev[8];
+  cudaEvent_t ev[9];
   int num_sms;
   int edge_tp, edge_smem, merge_smem, merge_H;
   std::vector<MnCtl> h_ctl;
+  double* d_logprob;            // [max_batch][4] class / sameness / differentness terms
+  std::vector<double> h_logprob;
+  float last_omf;
   mn_timings timings;
 };
 
@@ -232,10 +270,10 @@ extern "C" void mn_plan_destroy(mn_plan* p) {
   if (!p) return;
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
-  cudaFree(p->d_ws); cudaFree(p->d_imgs); cudaFree(p->d_keys_scratch); cudaFree(p->d_cub_temp);
+  cudaFree(p->d_ws); cudaFree(p->d_imgs); cudaFree(p->d_keys_scratch); cudaFree(p->d_cub_temp); cudaFree(p->d_logprob);
   cudaFree(p->d_in_class); cudaFree(p->d_in_adj); cudaFree(p->d_out_mask); cudaFree(p->d_out_cls);
   cudaFree(p->d_out_ninst);
-  for (int i = 0; i < 8; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+  for (int i = 0; i < 9; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
@@ -268,10 +306,10 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
   memset(&p->timings, 0, sizeof(p->timings));
   p->device = device; p->max_batch = max_batch; p->H = H; p->W = W; p->C = C; p->K = K; p->N = H * W;
   p->E = (long long)p->N * K;
-  p->d_ws = nullptr; p->d_imgs = nullptr; p->d_keys_scratch = nullptr; p->d_cub_temp = nullptr;
+  p->d_ws = nullptr; p->d_imgs = nullptr; p->d_keys_scratch = nullptr; p->d_cub_temp = nullptr; p->d_logprob = nullptr; p->last_omf = 1.0f;
   p->d_in_class = nullptr; p->d_in_adj = nullptr; p->d_out_mask = nullptr; p->d_out_cls = nullptr; p->d_out_ninst = nullptr;
   p->staging_batch = 0; p->stream = nullptr;
-  for (int i = 0; i < 8; i++) p->ev[i] = nullptr;
+  for (int i = 0; i < 9; i++) p->ev[i] = nullptr;
   memcpy(p->offsets, offset_list, sizeof(int) * 2 * K);
   std::vector<std::pair<int, int>> mag;
   p->off.K = K;
@@ -291,6 +329,8 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
   if (cudaMalloc(&p->d_ws, L.total * (size_t)max_batch) != cudaSuccess) return fail(MN_STATUS_CUDA);
   if (cudaMalloc(&p->d_imgs, sizeof(MnImage) * max_batch) != cudaSuccess) return fail(MN_STATUS_CUDA);
   if (cudaMalloc(&p->d_keys_scratch, (size_t)p->E * 8) != cudaSuccess) return fail(MN_STATUS_CUDA);
+  if (cudaMalloc(&p->d_logprob, sizeof(double) * 4 * max_batch) != cudaSuccess) return fail(MN_STATUS_CUDA);
+  p->h_logprob.assign((size_t)4 * max_batch, 0.0);
   p->h_imgs.resize(max_batch);
   for (int b = 0; b < max_batch; b++) {
     unsigned char* base = p->d_ws + (size_t)b * L.total;
@@ -322,7 +362,7 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
   p->cub_temp_bytes = std::max(t1, t2);
   if (cudaMalloc(&p->d_cub_temp, p->cub_temp_bytes) != cudaSuccess) return fail(MN_STATUS_CUDA);
   if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(MN_STATUS_CUDA);
-  for (int i = 0; i < 8; i++)
+  for (int i = 0; i < 9; i++)
     if (cudaEventCreate(&p->ev[i]) != cudaSuccess) return fail(MN_STATUS_CUDA);
   p->edge_tp = choose_edge_tile(C, K, &p->edge_smem);
   {
@@ -406,6 +446,15 @@ extern "C" int mn_segment_batch_device(mn_plan* p, int B, const float* d_class, 
   mn_merge_kernel<<<grid, MN_MERGE_THREADS, p->merge_smem, s>>>(p->d_imgs, B, A);
   p->timings.other_launches++;
   MN_CUDA_OK(cudaEventRecord(p->ev[4], s));
+  // aggregation pass: total log-prob terms from the maintained sums
+  {
+    MN_CUDA_OK(cudaMemsetAsync(p->d_logprob, 0, sizeof(double) * 4 * B, s));
+    dim3 g((unsigned)std::max(1, std::min(2 * p->num_sms / std::max(1, std::min(B, 8)), (int)((p->E + 255) / 256))), (unsigned)std::min(B, 65535));
+    mn_logprob_kernel<<<g, 256, 0, s>>>(p->d_imgs, B, N, p->C, p->E, p->d_logprob);
+    p->timings.other_launches++;
+    p->last_omf = omf;
+  }
+  MN_CUDA_OK(cudaEventRecord(p->ev[8], s));
   // labels
   {
     dim3 g((unsigned)std::min(1024, (N + 255) / 256), (unsigned)std::min(B, 65535));
@@ -423,12 +472,14 @@ extern "C" int mn_segment_batch_device(mn_plan* p, int B, const float* d_class, 
   // per-image status / statistics
   for (int b = 0; b < B; b++)
     MN_CUDA_OK(cudaMemcpyAsync(&p->h_ctl[b], p->h_imgs[b].ctl, sizeof(MnCtl), cudaMemcpyDeviceToHost, s));
+  MN_CUDA_OK(cudaMemcpyAsync(p->h_logprob.data(), p->d_logprob, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, s));
   MN_CUDA_OK(cudaStreamSynchronize(s));
   float ms = 0;
   cudaEventElapsedTime(&ms, p->ev[1], p->ev[2]); p->timings.edge_ms = ms;
   cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); p->timings.record_init_sort_ms = ms;
   cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->timings.merge_ms = ms;
-  cudaEventElapsedTime(&ms, p->ev[4], p->ev[5]); p->timings.label_ms = ms;
+  cudaEventElapsedTime(&ms, p->ev[4], p->ev[8]); p->timings.aggregate_ms = ms;
+  cudaEventElapsedTime(&ms, p->ev[8], p->ev[5]); p->timings.label_ms = ms;
   cudaEventElapsedTime(&ms, p->ev[1], p->ev[5]); p->timings.total_ms = ms;
   int worst = MN_STATUS_OK;
   for (int b = 0; b < B; b++)
@@ -497,6 +548,13 @@ extern "C" int mn_plan_image_stats(mn_plan* p, int image, mn_image_stats* o) {
   o->cycles_total = c.cycles_total;
   o->queue_chunks_used = c.qc_bump; o->pixel_pool_used = c.pix_bump; o->tree_nodes_used = c.tn_bump;
   o->requeues = c.requeues; o->hash_overflow = c.hash_ovf_n;
+  return MN_STATUS_OK;
+}
+extern "C" int mn_plan_image_logprob(mn_plan* p, int image, double* out4) {
+  if (!p || !out4 || image < 0 || image >= p->max_batch) return MN_STATUS_BAD_ARG;
+  const double* t = &p->h_logprob[(size_t)4 * image];
+  out4[0] = t[0]; out4[1] = t[1]; out4[2] = t[2];
+  out4[3] = t[0] + (double)p->last_omf * (t[2] + t[1]);  // cc:272-287
   return MN_STATUS_OK;
 }
 extern "C" int mn_plan_timings(mn_plan* p, mn_timings* o) {

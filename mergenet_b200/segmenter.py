@@ -139,6 +139,16 @@ class BatchSegmenter:
         _lib.lib().mn_plan_image_stats(self._plan, int(image), ctypes.byref(s))
         return s.as_dict()
 
+    def total_logprob(self, image):
+        """(class term, object sameness term, record differentness term, total) of the last run's
+        segmentation of ``image`` -- the reference's printed-only ComputeTotalLogprob
+        (segment.cc:272-287), evaluated on the GPU from the maintained sufficient statistics."""
+        out = (ctypes.c_double * 4)()
+        st = _lib.lib().mn_plan_image_logprob(self._plan, int(image), out)
+        if st != 0:
+            raise _lib.MergeNetError(st, "mn_plan_image_logprob")
+        return tuple(float(v) for v in out)
+
     def failed_images(self, B):
         out = []
         for b in range(B):

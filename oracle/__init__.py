@@ -67,6 +67,10 @@ def oracle_lib():
             _F, ctypes.c_int, _F, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _I, _I, _I,
             ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.POINTER(Stats), _I,
             ctypes.c_longlong]
+        lib.mno_run_segmentation_totals.restype = ctypes.c_int
+        lib.mno_run_segmentation_totals.argtypes = [
+            _F, ctypes.c_int, _F, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _I, _I, _I,
+            ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.POINTER(ctypes.c_double)]
         lib.mno_init_dump.restype = ctypes.c_int
         lib.mno_init_dump.argtypes = [
             _F, ctypes.c_int, _F, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _I,
@@ -177,6 +181,19 @@ def oracle_run_segmentation(class_pred, adj_pred, num_classes, offset_list, same
     if want_merge_log:
         out = out + (log[:st.merges].copy(),)
     return out
+
+
+def oracle_total_logprob(class_pred, adj_pred, num_classes, offset_list, same_different_bias,
+                         object_merge_factor, merge_logprob_bias):
+    """segment.cc:272-287 from the oracle's own accumulators: (class term, object sameness term, record
+    differentness term, total)."""
+    cp, ap, off, mask, ocls = _glue(class_pred, adj_pred, offset_list)
+    tot = (ctypes.c_double * 4)()
+    oracle_lib().mno_run_segmentation_totals(
+        _fp(cp), cp.shape[0], _fp(ap), ap.shape[0], ap.shape[2], ap.shape[1], int(num_classes),
+        _ip(off), _ip(mask), _ip(ocls), ctypes.c_float(same_different_bias), ctypes.c_float(object_merge_factor),
+        ctypes.c_float(merge_logprob_bias), tot)
+    return tuple(float(v) for v in tot)
 
 
 def oracle_init_dump(class_pred, adj_pred, num_classes, offset_list, same_different_bias,

@@ -637,6 +637,35 @@ int mno_run_segmentation(float* class_pred, int class_dim, float* adj_pred, int 
 /* Dump of the constructor's results (cc:153-232) for edge-pass parity tests.
  *   clp[N*C] (pixel-major), cls[N]; per record slot r = pixel*K + k: same, diff, oml, mp (0 when
  *   the offset leaves the image) and valid[r]. */
+/* cc:272-287 (ComputeTotalLogprob): sum over surviving objects of their class log-prob, plus
+ * object_merge_factor * (sum over surviving records of differentness + sum over objects of the
+ * sameness inside them).  The per-object / per-record sums are the fp32 accumulators the merges
+ * maintained; they are added up here in double, in index order (the reference prints a float sum in
+ * hash-map order).  totals = {class term, object sameness term, record differentness term, total}. */
+int mno_run_segmentation_totals(float* class_pred, int class_dim, float* adj_pred, int offset_dim,
+                                int img_width, int img_height, int num_classes,
+                                const int* offset_list, int* output, int* object_class,
+                                float same_different_bias, float object_merge_factor,
+                                float merge_logprob_bias, double* totals) {
+  seg_t s;
+  seg_init(&s, class_pred, class_dim, adj_pred, offset_dim, img_width, img_height, num_classes,
+           offset_list, same_different_bias, object_merge_factor, merge_logprob_bias, 1);
+  seg_run(&s, NULL, 0);
+  seg_output(&s, output, object_class);
+  double tc = 0.0, ts = 0.0, td = 0.0;
+  for (int o = 0; o < s.N; o++) {
+    if (!s.oalive[o]) continue;
+    tc += (double)s.clp[(size_t)o * s.C + s.cls[o]];
+    ts += (double)s.same_obj[o];
+  }
+  for (long long r = 0; r < s.E; r++)
+    if (s.state[r] == 1) td += (double)s.diff[r];
+  totals[0] = tc; totals[1] = ts; totals[2] = td;
+  totals[3] = tc + (double)object_merge_factor * (td + ts);
+  seg_free(&s);
+  return 0;
+}
+
 int mno_init_dump(float* class_pred, int class_dim, float* adj_pred, int offset_dim, int img_width,
                   int img_height, int num_classes, const int* offset_list,
                   float same_different_bias, float object_merge_factor, float merge_logprob_bias,

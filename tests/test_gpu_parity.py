@@ -131,6 +131,24 @@ def test_batch_api_host_and_device_agree_and_are_deterministic(oracle_mod, lib_m
     seg.close()
 
 
+def test_total_logprob_aggregation_matches_oracle(oracle_mod, lib_mod):
+    """segment.cc:272-287: the GPU aggregation pass over the maintained sums against the oracle's own
+    accumulators (same fp32 sums, same merge order) and against the float64 from-scratch evaluation of
+    the final partition (north star: 1e-5 relative)."""
+    from mergenet_b200 import BatchSegmenter, SegmenterOptions
+    for name, cp, sp, C, offs in cases.small_cases()[:6] + cases.medium_cases()[:1]:
+        H, W = cp.shape[1], cp.shape[2]
+        seg = BatchSegmenter(1, H, W, C, offs)
+        opts = SegmenterOptions(*cases.RECIPE_OPTS)
+        m, oc, n = seg.segment_host(cp[None], sp[None], opts)
+        got = seg.total_logprob(0)
+        ref = oracle_mod.oracle_total_logprob(cp, sp, C, offs, *cases.RECIPE_OPTS)
+        for g, r in zip(got, ref):
+            assert abs(g - r) <= 1e-6 * max(1.0, abs(r)), (name, got, ref)
+        seg.close()
+
+
+@pytest.mark.gpu
 def test_invariants_at_larger_size(oracle_mod, lib_mod):
     """Size-independent properties (no oracle needed): labels are 1..n, every labelled object is one
     4... offset-connected set of pixels, idempotent determinism, and merges = N - surviving objects."""

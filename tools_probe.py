@@ -19,6 +19,6 @@ for it in range(2):
     except Exception as e:
         print('ERR', e)
     dt = time.time() - t
-    print('iter', it, 'wall %.3fs' % dt, json.dumps(seg.timings()))
+    print("iter", it, "wall %.3fs" % dt, json.dumps(seg.timings()), seg.total_logprob(0))
 print(json.dumps(seg.stats(0)))
 print('ninst', n[:4] if 'n' in dir() else None)
