@@ -282,7 +282,7 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
                               const int* offset_list, int device) {
   g_last_error = MN_STATUS_OK;
   if (!out || max_batch <= 0 || H <= 0 || W <= 0 || C <= 0 || C >= MN_MAX_C || K <= 0 || K > MN_MAX_K ||
-      !offset_list || (long long)H * W * K > (1ll << MN_ORD_BITS) || (long long)H * W >= (1 << 24)) {
+      !offset_list || (long long)H * W * K > (1ll << 25) || (long long)H * W >= (1 << 24)) {
     g_last_error = MN_STATUS_BAD_ARG;
     return MN_STATUS_BAD_ARG;
   }

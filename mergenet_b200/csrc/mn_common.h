@@ -59,16 +59,38 @@ MN_HD float mn_u2f(uint32_t u) {
 }
 
 // ---- queue order -----------------------------------------------------------------------------
-// A queue entry pops before another iff (mp desc, lo asc, hi asc): the deterministic tie-break the
-// north star prescribes for what the reference leaves to libstdc++ heap layout (h:270-275).
+// A queue entry pops before another iff (mp desc, tie(lo, hi) asc): a deterministic tie-break for
+// what the reference leaves to libstdc++ heap layout and unordered_map iteration order (h:270-275).
+// tie(lo, hi) = (u, D) compared lexicographically, D = hi - lo, u = (bitrev24(lo) + 0x9E3779 * D) mod
+// 2^24.  (u, D) <-> (lo, hi) is a bijection, so the order is total; it scatters equal priorities
+// (oracle-mode maps have millions) over the image AND over the records of one object, the way the
+// reference's own hash-driven order does: consecutive pops rarely touch the same or neighbouring
+// objects (few conflicts per round) and objects grow compactly.  For an initial record D is one of the
+// K offset distances, so (u, rank of D) fits the 28-bit ordinal of the sorted initial keys.  Any
+// fixed rule is equally valid against the reference; this one is fast on a GPU.
+#define MN_TIE_MUL 0x9E3779u
+MN_HD uint32_t mn_brev24(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __brev(v) >> 8;
+#else
+  uint32_t r = 0;
+  for (int i = 0; i < 24; i++) { r = (r << 1) | (v & 1u); v >>= 1; }
+  return r;
+#endif
+}
+MN_HD uint32_t mn_tie_u(int lo, int hi) {
+  return (mn_brev24((uint32_t)lo) + MN_TIE_MUL * (uint32_t)(hi - lo)) & 0xFFFFFFu;
+}
+MN_HD uint64_t mn_tie(int lo, int hi) {
+  return ((uint64_t)mn_tie_u(lo, hi) << 24) | (uint64_t)(uint32_t)(hi - lo);
+}
 struct MnEnt {
   float mp;
   int lo, hi, rec;
 };
 MN_HD bool mn_before(float amp, int alo, int ahi, float bmp, int blo, int bhi) {
   if (amp != bmp) return amp > bmp;
-  if (alo != blo) return alo < blo;
-  return ahi < bhi;
+  return mn_tie(alo, ahi) < mn_tie(blo, bhi);
 }
 MN_HD bool mn_ent_before(const MnEnt& a, const MnEnt& b) {
   return mn_before(a.mp, a.lo, a.hi, b.mp, b.lo, b.hi);

@@ -66,7 +66,7 @@ template <typename T> static inline T mn_h_cas(T* p, T c, T v) { T o = *p; if (o
 #define MN_ATOMIC_CAS(p, c, v) mn_h_cas((p), (c), (v))
 #endif
 
-#define MN_ORD_BITS 25       // initial-entry tie-break ordinal lo*K + rank  (N*K <= 2^25)
+#define MN_ORD_BITS 28       // initial-entry tie-break ordinal: tie u << 4 | rank of the offset distance (K <= 16)
 #define MN_QCH 64            // queue entries per tree chunk (16 B each)
 #define MN_HASH_FP_SHIFT 26  // slot = fingerprint(6) << 26 | (rec + 1)
 #define MN_TREE_BITS 3       // digit width of the queue tree below a root

@@ -168,7 +168,7 @@ struct MnMergeArgs {
 #define MN_CLZ(x) __builtin_clz((unsigned)(x))
 #define MN_POPC(x) __builtin_popcount((unsigned)(x))
 #endif
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(MN_PHASE_CYCLES)  // per-phase cycle buckets cost ~4 %: profiling builds only
 #define MN_TIC() do { if (MN_T0) sm.cyc_t0 = clock64(); } while (0)
 #define MN_TOC(k) do { if (MN_T0) { long long t__ = clock64(); sm.cyc[k] += t__ - sm.cyc_t0; sm.cyc_t0 = t__; } } while (0)
 #else
@@ -220,15 +220,15 @@ MN_D int mn_root_of(float mp) {
   if (b >= MN_ROOT_HI_BITS) return MN_NROOTS - 1;
   return (int)((b - MN_ROOT_LO_BITS) >> MN_ROOT_SHIFT) + 1;
 }
-// MN_TREE_BITS-bit digit `level` (1-based, below the root) of the 80-bit pop-order key [~mpbits:32][lo:24][hi:24].
+// MN_TREE_BITS-bit digit `level` (1-based, below the root) of the 80-bit pop-order key [~mpbits:32][tie u:24][D:24].
 // Regular roots fix the top 32 - MN_ROOT_SHIFT key bits, where their digits start; the two open-ended roots
 // start at bit 0.  Smaller digit = pops first.
 MN_D int mn_digit(int root, int level, float mp, int lo, int hi) {
   int start = (root == 0 || root == MN_NROOTS - 1) ? 0 : 32 - MN_ROOT_SHIFT;
   int pos = start + MN_TREE_BITS * (level - 1);  // bit offset from the top of the 80-bit key
-  unsigned long long hi64 = ((unsigned long long)(~mn_f2u(mp)) << 32) | ((unsigned long long)(uint32_t)lo << 8) |
-                            ((unsigned long long)(uint32_t)hi >> 16);
-  unsigned long long lo16 = (unsigned long long)((uint32_t)hi & 0xFFFFu);
+  const unsigned long long tie = mn_tie(lo, hi);  // 48 bits: (u, D)
+  unsigned long long hi64 = ((unsigned long long)(~mn_f2u(mp)) << 32) | (tie >> 16);
+  unsigned long long lo16 = tie & 0xFFFFull;
   int d = 0;
   for (int b = 0; b < MN_TREE_BITS; b++) {
     int p = pos + b;
@@ -541,10 +541,12 @@ MN_D int mn_top_leaf(const MnImage& im, MnSm& sm, int* root_out, bool allow_spli
 MN_D void mn_decode_init(const MnMergeArgs& A, uint64_t key, float* mp, int* lo, int* hi, int* rec) {
   uint32_t ord = (uint32_t)(key & ((1ull << MN_ORD_BITS) - 1));
   *mp = mn_u2f(~(uint32_t)(key >> MN_ORD_BITS));
-  int l = (int)(ord / (uint32_t)A.K), rank = (int)(ord % (uint32_t)A.K);
+  const int rank = (int)(ord & 15u);
   int k = A.off.k_of_rank[rank];
   int d = A.off.delta[k];
-  int h = l + (d > 0 ? d : -d);
+  const uint32_t D = (uint32_t)(d > 0 ? d : -d);
+  int l = (int)mn_brev24(((ord >> 4) - MN_TIE_MUL * D) & 0xFFFFFFu);  // (the 24-bit reversal is an involution)
+  int h = l + (int)D;
   *lo = l; *hi = h;
   int p = d > 0 ? l : h;
   *rec = p * A.K + k;

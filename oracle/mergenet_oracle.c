@@ -11,7 +11,7 @@
  *     stored (mp, lo, hi) -- observationally the same "indexed map of stored priorities" as the
  *     reference heap (duplicates of a valid key are no-ops there: cc:554-559);
  *   - ties between equal priorities, which the reference leaves to libstdc++ heap layout and
- *     unordered_map iteration order, are broken deterministically: (mp desc, lo asc, hi asc);
+ *     unordered_map iteration order, are broken deterministically: (mp desc, then a fixed scattering bijection of (lo, hi));
  *   - per-object unordered_map adjacency lists (h:136) become intrusive doubly-linked lists plus
  *     one global (lo,hi)->record hash table.
  * PARITY PIN: the reference ships no golden vectors for this path ("parity unpinned" by its own
@@ -178,11 +178,21 @@ typedef struct {
   int lo, hi, rec;
 } heap_ent;
 
-/* a pops before b?  (mp desc, lo asc, hi asc) */
+/* a pops before b?  (mp desc, tie(lo, hi) asc), tie = (u, D) lexicographic with D = hi - lo and
+ * u = (bitrev24(lo) + 0x9E3779 * D) mod 2^24 -- a bijection of the pair, hence a total order.  The
+ * reference leaves ties to libstdc++ heap layout / unordered_map order; this fixed rule scatters equal
+ * priorities over the image and over the records of one object (the CUDA scheduler uses the same one,
+ * mn_common.h). */
+static inline uint64_t mno_tie(int lo, int hi) {
+  uint32_t v = (uint32_t)lo, r = 0;
+  for (int i = 0; i < 24; i++) { r = (r << 1) | (v & 1u); v >>= 1; }
+  uint32_t D = (uint32_t)(hi - lo);
+  uint32_t u = (r + 0x9E3779u * D) & 0xFFFFFFu;
+  return ((uint64_t)u << 24) | D;
+}
 static inline int ent_before(const heap_ent* a, const heap_ent* b) {
   if (a->mp != b->mp) return a->mp > b->mp;
-  if (a->lo != b->lo) return a->lo < b->lo;
-  return a->hi < b->hi;
+  return mno_tie(a->lo, a->hi) < mno_tie(b->lo, b->hi);
 }
 
 typedef struct {

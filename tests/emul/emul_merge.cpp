@@ -99,7 +99,7 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
         MN_REC_A(im, r) = make_uint4((uint32_t)lo, (uint32_t)hi, (uint32_t)hslot, mn_f2u(diff));
         MN_REC_B(im, r) = make_float4(oml, same, mp >= 0.0f ? mp : -1.0f, mp);
         if (mp >= 0.0f) {
-          uint32_t ord = (uint32_t)lo * (uint32_t)K + (uint32_t)rank_of_k[k];
+          uint32_t ord = (mn_tie_u(lo, hi) << 4) | (uint32_t)rank_of_k[k];
           key = ((uint64_t)(~mn_f2u(mp == 0.0f ? 0.0f : mp)) << MN_ORD_BITS) | ord;
         }
       } else {
