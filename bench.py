@@ -290,7 +290,12 @@ def run_own_arm(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "mn_edge_pass_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this
+                         # kernel (profiles/r01_hbm_kernels_ncu_full.json: 384.9 MB per 1024x2048 image,
+                         # algorithmic 402.7 MB -- part of the last tiles' output is still in L2 at kernel end)
+                         "traffic": (384.9e6 * B) if (h, w, C, K) == (1024, 2048, 9, 10) else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": edge_bytes, "avg_launch_ms": edge_s * 1e3},
             "cpu_baseline": cpu,
             "scheduler": {"merge_kernel_ms": merge_s * 1e3, "rounds_per_image": float(np.mean(rounds)),
@@ -306,6 +311,7 @@ def run_own_arm(args):
                             "avg_launch_ms": tm_dev["aggregate_ms"],
                             "achieved": B * (20 * n + 16 * n * K) / max(1e-9, tm_dev["aggregate_ms"] * 1e-3) / 1e9,
                             "frac": B * (20 * n + 16 * n * K) / max(1e-9, tm_dev["aggregate_ms"] * 1e-3) / 1e9 / peak,
+                            "traffic": (679.6e6 * B) if (h, w, C, K) == (1024, 2048, 9, 10) else None,
                             "total_logprob_image0": logprob0},
         }
         print(json.dumps(line))

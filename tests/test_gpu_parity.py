@@ -168,3 +168,50 @@ def test_invariants_at_larger_size(oracle_mod, lib_mod):
     assert st["status"] == 0 and st["events"] == st["merges"] + st["restores"]
     assert st["merges"] <= H * W - 1
     seg.close()
+
+
+@pytest.mark.gpu
+def test_coco_shaped_medium_matches_oracle(oracle_mod, lib_mod):
+    """cfg4 family (81 classes, 16 offsets up to (23,40)): soft and oracle-mode maps at 96x96."""
+    from mergenet_b200 import c_segment
+    for soft in (True, False):
+        cp, sp, C, offs = cases.coco_like(96, 96, 31, soft)
+        m0, c0, st0 = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *cases.RECIPE_OPTS)
+        m1, c1 = c_segment.run_segmentation(cp, sp, C, offs, *cases.RECIPE_OPTS)
+        assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), soft
+
+
+@pytest.mark.gpu
+def test_full_resolution_properties(oracle_mod, lib_mod):
+    """BASELINE.json's full size (1024x2048, C=9, K=10), where the oracle is too slow for the suite:
+    size-independent properties only.  Two images in one batch (soft and oracle-mode maps):
+    status 0, labels exactly 1..n, every event accounted for, merges = N - surviving objects,
+    run twice -> identical bytes (determinism), and the maintained log-prob total is finite and equals
+    class + omf * (differentness + sameness)."""
+    from mergenet_b200 import BatchSegmenter, SegmenterOptions, synth
+    H, W, C = 1024, 2048, 9
+    cps, sps = [], []
+    for soft in (True, False):
+        cp, sp, offs, _ = synth.cfg_cityscapes(H, W, seed=5, n_shapes=400, rmax=120, soft=soft, noise_seed=9)
+        cps.append(cp); sps.append(sp)
+    cp = np.ascontiguousarray(np.stack(cps)); sp = np.ascontiguousarray(np.stack(sps))
+    seg = BatchSegmenter(2, H, W, C, offs)
+    opts = SegmenterOptions(*cases.RECIPE_OPTS)
+    m, oc, n = seg.segment_host(cp, sp, opts)
+    stats = [seg.stats(b) for b in range(2)]
+    tot = [seg.total_logprob(b) for b in range(2)]
+    m2, oc2, n2 = seg.segment_host(cp, sp, opts)
+    assert np.array_equal(m, m2) and np.array_equal(oc, oc2) and np.array_equal(n, n2)
+    for b in range(2):
+        st = stats[b]
+        assert st["status"] == 0
+        k = int(n[b])
+        labs = np.unique(m[b])
+        assert labs.min() >= 0 and labs.max() == k and len(labs[labs > 0]) == k
+        assert np.all(oc[b][:k] > 0) and np.all(oc[b][k:] == -1)
+        assert st["events"] == st["merges"] + st["restores"]
+        # every merge removes one object: surviving objects = N - merges >= instances (+ class-0 objects)
+        assert H * W - st["merges"] >= k
+        t = tot[b]
+        assert np.isfinite(t[3]) and abs(t[3] - (t[0] + opts.object_merge_factor * (t[2] + t[1]))) <= 1e-9 * abs(t[3])
+    seg.close()
