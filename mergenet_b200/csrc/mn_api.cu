@@ -256,9 +256,9 @@ extern "C" size_t mn_workspace_bytes_per_image(int H, int W, int C, int K) {
 static int choose_edge_tile(int C, int K, int* smem_bytes) {
   // per pixel: double-buffered inputs 2*(C+K) floats + double-buffered staged outputs 2*(C + 2K) floats
   const size_t per_px = 4 * (size_t)(2 * (C + K) + 2 * (C + 2 * K));
-  size_t budget = 220 * 1024;
+  size_t budget = (size_t)(226 * 1024) / MN_EDGE_CTAS_PER_SM - 4096;
   int tp = (int)(budget / per_px);
-  tp = std::min(tp, 512);
+  tp = std::min(tp, MN_EDGE_THREADS / 2);
   tp = tp / 4 * 4;
   if (tp >= 128) tp = tp / 128 * 128;
   if (tp < 4) tp = 4;
@@ -401,7 +401,7 @@ static int run_front(mn_plan* p, int B, const float* d_class, float* d_adj, int 
   P.use_tma = (N % 4 == 0) && (((uintptr_t)d_class & 15) == 0) && (((uintptr_t)d_adj & 15) == 0);
   P.clip = clip; P.sdb = sdb;
   long long tiles = (long long)B * P.tiles_per_image;
-  int grid = (int)std::min<long long>(tiles, p->num_sms);
+  int grid = (int)std::min<long long>(tiles, (long long)p->num_sms * MN_EDGE_CTAS_PER_SM);
   mn_edge_pass_kernel<<<grid, MN_EDGE_THREADS, p->edge_smem, s>>>(P);
   p->timings.edge_launches++;
   MN_CUDA_OK(cudaEventRecord(p->ev[2], s));

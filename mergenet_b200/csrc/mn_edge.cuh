@@ -80,15 +80,22 @@ __device__ __forceinline__ float mn_log1m_exact(float s) { return (float)log(1.0
 //
 // logf as glibc's FMA build evaluates it (the recipe of mn_logf_exact with its five multiply-adds
 // fused; bit-identical on the whole clipped domain, pinned exhaustively on the device): 6 fp64 ops.
+// (conversions run on the quarter-rate XU pipe, so the exact widenings are done with integer ops)
+__device__ __forceinline__ double mn_f32bits_to_f64(uint32_t b) {  // b = bits of a positive normal float
+  return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+}
+__device__ __forceinline__ double mn_small_int_to_f64(int k) {  // exact for |k| < 2^31
+  return __hiloint2double(0x43300000, (int)(0x80000000u ^ (uint32_t)k)) - 4503601774854144.0;  // 2^52 + 2^31
+}
 __device__ __forceinline__ float mn_logf_fast(float x, const MnLogfTab* tab) {
   const uint32_t ix = __float_as_uint(x);
   const uint32_t tmp = ix - 0x3f330000u;
   const int i = (tmp >> 19) & 15;
   const int k = (int32_t)tmp >> 23;
-  const double z = (double)__uint_as_float(ix - (tmp & 0xff800000u));
+  const double z = mn_f32bits_to_f64(ix - (tmp & 0xff800000u));
   const double2 e = *reinterpret_cast<const double2*>(&tab[i]);  // (invc, logc) in one 16-byte load
   const double r = __fma_rn(z, e.x, -1.0);
-  const double y0 = __fma_rn((double)k, 0x1.62e42fefa39efp-1, e.y);
+  const double y0 = __fma_rn(mn_small_int_to_f64(k), 0x1.62e42fefa39efp-1, e.y);
   const double r2 = __dmul_rn(r, r);
   double y = __fma_rn(0x1.5575b0be00b6ap-2, r, -0x1.ffffef20a4123p-2);
   y = __fma_rn(-0x1.00ea348b88334p-2, r2, y);
@@ -106,15 +113,15 @@ struct MnLog1mTab {
 };
 __constant__ MnLog1mTab mn_log1m_table[128] = {MN_LOG1M_TABLE};
 __device__ __forceinline__ float mn_log1m_fast(float s, const MnLog1mTab* tab) {
-  const double x = 1.0 - (double)s;
-  const unsigned long long ix = (unsigned long long)__double_as_longlong(x);
-  const unsigned long long tmp = ix - MN_LOG1M_OFF;
-  const int i = (int)((tmp >> 45) & 127ull);
-  const int k = (int)((long long)tmp >> 52);
-  const double z = __longlong_as_double((long long)(ix - (tmp & 0xfff0000000000000ull)));
+  const double x = __dadd_rn(1.0, -mn_f32bits_to_f64(__float_as_uint(s)));  // exact
+  const uint32_t hx = (uint32_t)__double2hiint(x);
+  const uint32_t tmp = hx - (uint32_t)(MN_LOG1M_OFF >> 32);  // (the low word of OFF is zero)
+  const int i = (int)((tmp >> 13) & 127u);
+  const int k = (int32_t)tmp >> 20;
+  const double z = __hiloint2double((int)(hx - (tmp & 0xfff00000u)), __double2loint(x));
   const double2 e = *reinterpret_cast<const double2*>(&tab[i]);
   const double r = __fma_rn(z, e.x, -1.0);
-  const double t = __fma_rn((double)k, 0x1.62e42fefa39efp-1, e.y);
+  const double t = __fma_rn(mn_small_int_to_f64(k), 0x1.62e42fefa39efp-1, e.y);
   double q = __fma_rn(r, -1.0 / 6, 0.2);
   q = __fma_rn(r, q, -0.25);
   q = __fma_rn(r, q, 1.0 / 3);
@@ -122,8 +129,7 @@ __device__ __forceinline__ float mn_log1m_fast(float s, const MnLog1mTab* tab) {
   const double r2 = __dmul_rn(r, r);
   double y = __fma_rn(r2, q, r);
   y = __dadd_rn(y, t);
-  const uint32_t low = (uint32_t)((unsigned long long)__double_as_longlong(y) & 0x1fffffffull);
-  const int d = abs((int)low - 0x10000000);
+  const int d = abs((int)((uint32_t)__double2loint(y) & 0x1fffffffu) - 0x10000000);
   if (d < (1 << 14)) return (float)log(x);  // too close to a float rounding boundary: decide exactly
   return (float)y;
 }
@@ -181,8 +187,11 @@ struct MnEdgeParams {
 };
 
 // dynamic smem layout: [bar0, bar1][pad to 128][in0][in1][out0: clp|same|diff][out1][logf tab][log1m tab]
-#define MN_EDGE_THREADS 1024
-__global__ void __launch_bounds__(MN_EDGE_THREADS, 1) mn_edge_pass_kernel(MnEdgeParams P) {
+// two CTAs of 512 threads per SM (tiles of 256 pixels, ~100 KB of shared memory each): while one waits
+// at a barrier or on its TMA loads the other computes
+#define MN_EDGE_THREADS 512
+#define MN_EDGE_CTAS_PER_SM 2
+__global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_pass_kernel(MnEdgeParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int C = P.C, K = P.K, TP = P.TP, NPL = C + K;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -239,13 +248,6 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, 1) mn_edge_pass_kernel(MnEdge
     float* im_same = P.imgs[b].rec_same;
     float* im_diff = P.imgs[b].rec_diff;
     if (P.use_tma) {
-      // prefetch the next tile into the other stage (its previous readers passed the
-      // __syncthreads at the end of the last iteration)
-      long long nxt = tile + gridDim.x;
-      if (tid == 0 && nxt < total_tiles) {
-        mn_fence_proxy_async();
-        issue(nxt, stage ^ 1);
-      }
       mn_mbar_wait(&bars[stage], phase[stage]);
       phase[stage] ^= 1;
     } else {
@@ -262,11 +264,47 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, 1) mn_edge_pass_kernel(MnEdge
     // stores of the previous tile keep draining while this tile is computed
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
     __syncthreads();
+    if (P.use_tma) {
+      // prefetch the next tile into the other input stage: its readers finished before the barrier
+      // above, and only the issuing thread is held up by the 19 bulk-copy instructions
+      long long nxt = tile + gridDim.x;
+      if (tid == 0 && nxt < total_tiles) {
+        mn_fence_proxy_async();
+        issue(nxt, stage ^ 1);
+      }
+    }
 
     // ---- compute: one item per (plane, pixel); consecutive lanes -> consecutive pixels.  In a full
     //      tile (a power of two of pixels) a thread keeps its pixel and walks the planes: no index
     //      arithmetic beyond pointer increments ----
-    if (tl == TP && (TP & (TP - 1)) == 0 && nt >= TP) {
+    bool cls_done = false;
+    if (tl == TP && nt == 2 * TP && P.sdb == 0.0f) {
+      // two thread groups per tile: group 0 takes every class plane of its pixel (first-argmax kept in
+      // registers, cc:18-20) and the last a0 offset planes, group 1 the other offset planes (an offset
+      // plane costs about 2.1 class planes) -- no separate argmax pass, no barrier in between
+      const int px = tid & (TP - 1), g = tid >= TP ? 1 : 0;
+      int a0 = (21 * K - 10 * C) / 42;
+      a0 = a0 < 0 ? 0 : (a0 > K ? K : a0);
+      if (g == 0) {
+        float best = 0.0f; int bc = 0;
+        for (int pl = 0; pl < C; pl++) {
+          float v = in[(size_t)pl * TP + px];
+          if (P.clip) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
+          const float l = MN_FADD(0.0f, mn_logf_fast(v, tab));  // cc:11-16
+          out_clp[px * C + pl] = l;
+          if (pl == 0 || l > best) { best = l; bc = pl; }
+        }
+        im_cls[start + px] = bc;
+      }
+      const int k0 = g == 0 ? K - a0 : 0, k1 = g == 0 ? K : K - a0;
+      for (int k = k0; k < k1; k++) {
+        float v = in[(size_t)(C + k) * TP + px];
+        if (P.clip) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
+        out_same[px * K + k] = mn_logf_fast(v, tab);     // cc:35
+        out_diff[px * K + k] = mn_log1m_fast(v, tab1m);  // cc:34
+      }
+      cls_done = true;
+    } else if (tl == TP && (TP & (TP - 1)) == 0 && nt >= TP) {
       const int sh = 31 - __clz(TP);
       const int px = tid & (TP - 1), g = tid >> sh, ng = nt >> sh;
       for (int pl = g; pl < C; pl += ng) {
@@ -303,9 +341,9 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, 1) mn_edge_pass_kernel(MnEdge
         }
       }
     }
-    __syncthreads();
+    if (!cls_done) __syncthreads();
     // ---- first-argmax class per pixel (cc:18-20) ----
-    for (int px = tid; px < tl; px += nt) {
+    for (int px = tid; !cls_done && px < tl; px += nt) {
       const float* v = out_clp + px * C;
       float best = v[0];
       int bc = 0;
@@ -339,7 +377,8 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, 1) mn_edge_pass_kernel(MnEdge
         g_diff[i] = out_diff[i];
       }
     }
-    __syncthreads();  // everyone is done with `in` before it is refilled
+    if (!P.use_tma) __syncthreads();  // (TMA path: the barrier before the stores already ordered every read
+                                      //  of `in`, which is refilled only after the next iteration's barrier)
   }
   if (tid == 0) mn_tma_store_wait_read();
 }
