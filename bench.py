@@ -326,7 +326,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--batch", type=int, default=env_int("MN_BENCH_BATCH", 96), help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=env_int("MN_BENCH_BATCH", 112), help="images per GPU per step")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic images per rank (tiled to the batch)")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)

@@ -212,9 +212,9 @@ struct mn_plan {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t clp, cls, obj, parent, pix_pool, rec, rec_sd, hash, hash_ovf,
-      init_keys, qc_next, qc_free, tn, tn_dir, ctl, total;
-  int pix_cap, qc_cap, tn_cap;
+  size_t clp, cls, obj, parent, pix_pool, rec, arena, hash, hash_ovf,
+      qc_next, qc_free, tn, tn_dir, ctl, total;
+  int pix_cap, qc_cap, qc_low_n, tn_cap;
   uint32_t hash_nbuckets, hash_ovf_cap;
 };
 static WsLayout ws_layout(int H, int W, int C, int K) {
@@ -223,9 +223,12 @@ static WsLayout ws_layout(int H, int W, int C, int K) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
   L.pix_cap = (int)(16 * N + 4096);
-  // queue entry pool: 16-byte entries in chunks of MN_QCH; it aliases rec_same | rec_diff (8*E bytes,
-  // dead after record init) and extends past them: one chunk per live tree leaf plus the entries.
-  L.qc_cap = (int)(E * 3 / 4 / MN_QCH + 4 * MN_NROOTS + 4096);  // measured peak: 0.6 E entries
+  // One arena holds, in turn, the edge pass outputs rec_same | rec_diff (8 E bytes, dead after record
+  // init), the sorted initial keys (8 E bytes, written by the sort), and the queue chunks: the consumed
+  // prefix of the keys is recycled as chunks (qc_low_n of them), and qc_cap - qc_low_n extra chunks
+  // cover the early demand (measured: 0.30 E entries at 256x512).
+  L.qc_low_n = (int)(E * 8 / ((size_t)MN_QCH * 16));
+  L.qc_cap = L.qc_low_n + (int)(E * 9 / 20 / MN_QCH + 4 * MN_NROOTS + 4096);
   L.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)std::max<size_t>(4096, E / 512);  // measured: < E / 1700 splits
   L.hash_nbuckets = (uint32_t)(E * 18 / 10 / 8 + 64);
   L.hash_ovf_cap = 16384;
@@ -235,10 +238,9 @@ static WsLayout ws_layout(int H, int W, int C, int K) {
   L.parent = take(N * 4);
   L.pix_pool = take((size_t)L.pix_cap * 4);
   L.rec = take(E * 32);
-  L.rec_sd = take(std::max(E * 8, (size_t)L.qc_cap * MN_QCH * 16));  // rec_same | rec_diff, then q_ent
+  L.arena = take(std::max(E * 8, (size_t)L.qc_cap * MN_QCH * 16));
   L.hash = take((size_t)L.hash_nbuckets * 8 * 4);
   L.hash_ovf = take((size_t)L.hash_ovf_cap * 4);
-  L.init_keys = take(E * 8);
   L.qc_next = take((size_t)L.qc_cap * 4);
   L.qc_free = take((size_t)L.qc_cap * 4);
   L.tn = take((size_t)L.tn_cap * 16);
@@ -341,14 +343,14 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
     im.parent = (int*)(base + L.parent);
     im.pix_pool = (int*)(base + L.pix_pool);
     im.rec = (uint4*)(base + L.rec);
-    im.rec_same = (float*)(base + L.rec_sd); im.rec_diff = im.rec_same + p->E;
+    im.rec_same = (float*)(base + L.arena); im.rec_diff = im.rec_same + p->E;
     im.hash = (uint32_t*)(base + L.hash); im.hash_ovf = (uint32_t*)(base + L.hash_ovf);
     im.hash_nbuckets = L.hash_nbuckets; im.hash_ovf_cap = L.hash_ovf_cap;
-    im.init_keys = (uint64_t*)(base + L.init_keys);
-    im.q_ent = (uint4*)(base + L.rec_sd);
+    im.init_keys = (uint64_t*)(base + L.arena);
+    im.q_ent = (uint4*)(base + L.arena);
     im.qc_next = (int*)(base + L.qc_next); im.qc_free = (int*)(base + L.qc_free);
     im.tn = (int4*)(base + L.tn); im.tn_dir = (int*)(base + L.tn_dir);
-    im.pix_cap = L.pix_cap; im.qc_cap = L.qc_cap; im.tn_cap = L.tn_cap;
+    im.pix_cap = L.pix_cap; im.qc_cap = L.qc_cap; im.qc_low_n = L.qc_low_n; im.tn_cap = L.tn_cap;
     im.out_mask = nullptr; im.out_cls = nullptr;
     im.ctl = (MnCtl*)(base + L.ctl);
     p->h_imgs[b] = im;
@@ -408,7 +410,7 @@ static int run_front(mn_plan* p, int B, const float* d_class, float* d_adj, int 
   for (int b = 0; b < B; b++) {
     MnRecInitParams R;
     R.im = p->h_imgs[b];
-    R.keys_out = sort_keys ? p->d_keys_scratch : p->h_imgs[b].init_keys;
+    R.keys_out = p->d_keys_scratch;  // (never init_keys: it shares the arena with the inputs rec_same | rec_diff)
     R.H = p->H; R.W = p->W; R.C = C; R.K = K; R.N = N; R.omf = omf; R.mlb = mlb;
     for (int k = 0; k < K; k++) { R.off_r[k] = p->offsets[2 * k]; R.off_c[k] = p->offsets[2 * k + 1]; R.rank_of_k[k] = p->rank_of_k[k]; }
     int g = (int)std::min<long long>((p->E + 255) / 256, (long long)p->num_sms * 16);

@@ -134,12 +134,14 @@ struct MnImage {
   uint32_t hash_ovf_cap;
   // queue
   uint64_t* init_keys;
-  uint4* q_ent;  // [qc_cap * MN_QCH] (mp bits, rec, lo, hi): validated against the record on load
+  uint4* q_ent;  // [qc_cap * MN_QCH] (mp bits, rec, lo, hi): validated against the record on load.  One arena with
+                 // init_keys: chunk c < qc_low_n overlays init_keys[2 * MN_QCH * c ...), usable once consumed
   int* qc_next;
   int* qc_free;
   int4* tn;     // tree nodes: (first chunk, last chunk, entries below, first child)
   int* tn_dir;  // first 8 chunk ids of every leaf
   int pix_cap, qc_cap, tn_cap;
+  int qc_low_n;  // chunks covered by the initial-key array (arena prefix)
   // outputs
   int* out_mask;
   int* out_cls;

@@ -103,6 +103,7 @@ struct MnSm {
   int red_idx[1024];  // argmax reduction scratch
   int4 scan_nd[MN_TREE_FANOUT]; int4 leaf_nd; int path_cnt[32];
   int qc_free_top, qc_bump, tn_bump, tree_entries, static_cursor, n_init;  // mirrors of MnCtl
+  int qc_low_bump, qc_low_avail;  // chunks recycled from the consumed prefix of the initial keys
   int peak_entries, peak_chunks;
   // candidates: staged loads
   int c_rec[MN_H]; float c_key[MN_H]; int c_lo[MN_H]; int c_hi[MN_H]; int c_kind[MN_H];
@@ -245,10 +246,19 @@ MN_D int mn_max_level(int root) {
   return (80 - start + MN_TREE_BITS - 1) / MN_TREE_BITS;
 }
 
+// Queue chunks come from one arena that starts with the sorted initial keys: the keys below the cursor
+// are consumed, so their 1 KB blocks (MN_QCH 16-byte entries = 2 * MN_QCH keys) are handed out as chunks
+// (ids below qc_low_n, available up to qc_low_avail); only the early demand, before enough of the
+// initial array is consumed, needs chunks of its own (ids from qc_low_n up to qc_cap).
 MN_D int mn_qc_alloc(const MnImage& im, MnSm& sm) {  // called only from phases that never free
   int t = MN_ATOMIC_SUB(&sm.qc_free_top, 1);
   if (t > 0) return im.qc_free[t - 1];
   MN_ATOMIC_ADD(&sm.qc_free_top, 1);
+  if (sm.qc_low_bump < sm.qc_low_avail) {
+    int c = MN_ATOMIC_ADD(&sm.qc_low_bump, 1);
+    if (c < sm.qc_low_avail) return c;
+    MN_ATOMIC_SUB(&sm.qc_low_bump, 1);
+  }
   int c = MN_ATOMIC_ADD(&sm.qc_bump, 1);
   if (c >= im.qc_cap) { mn_fail(im, MN_ERR_Q_POOL); return -1; }
   return c;
@@ -365,7 +375,7 @@ MN_D void mn_flush_ins(const MnImage& im, MnSm& sm) {
     sm.nins = 0;
     sm.st_flushes++;
     if (sm.tree_entries > sm.peak_entries) sm.peak_entries = sm.tree_entries;
-    const int used = sm.qc_bump - (sm.qc_free_top > 0 ? sm.qc_free_top : 0);
+    const int used = (sm.qc_bump - im.qc_low_n) + sm.qc_low_bump - (sm.qc_free_top > 0 ? sm.qc_free_top : 0);
     if (used > sm.peak_chunks) sm.peak_chunks = used;
   }
   MN_SYNC();
@@ -703,6 +713,8 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
         sm.cold_empty = 0;
       }
       sm.static_cursor = sc + ntake;
+      sm.qc_low_avail = (int)(((long long)sm.static_cursor * 8) / (MN_QCH * 16));
+      if (sm.qc_low_avail > im.qc_low_n) sm.qc_low_avail = im.qc_low_n;
       sm.tmp1 = 0; sm.tmp0 = 0;
     }
     MN_SYNC();
@@ -1539,7 +1551,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     sm.hsel = 0; sm.nhot = 0; sm.nins = 0; sm.nne = 0; sm.cold_empty = 0;
     sm.b_mp = 0; sm.b_lo = 0; sm.b_hi = 0; sm.path_n = 0; sm.failed = 0;
     sm.pix_bump = 0; sm.hash_ovf_n = im.ctl->hash_ovf_n;
-    sm.qc_free_top = 0; sm.qc_bump = 0; sm.tn_bump = MN_NROOTS; sm.tree_entries = 0; sm.peak_entries = 0; sm.peak_chunks = 0;
+    sm.qc_free_top = 0; sm.qc_bump = im.qc_low_n; sm.qc_low_bump = 0; sm.qc_low_avail = 0; sm.tn_bump = MN_NROOTS; sm.tree_entries = 0; sm.peak_entries = 0; sm.peak_chunks = 0;
     sm.st_rounds = sm.st_events = sm.st_merges = sm.st_restores = sm.st_invalid = sm.st_solo = 0;
     sm.st_refills = sm.st_flushes = sm.st_splits = sm.st_pairs = sm.st_cut_conf = sm.st_cut_casc = sm.st_cut_cap = 0;
     sm.st_requeues = 0;

@@ -37,9 +37,10 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   im.hash = zalloc<uint32_t>((size_t)im.hash_nbuckets * 8);
   im.hash_ovf_cap = 4096;
   im.hash_ovf = zalloc<uint32_t>(im.hash_ovf_cap);
-  im.init_keys = zalloc<uint64_t>(E);
-  im.qc_cap = (int)(E / MN_QCH * 2) + 4 * MN_NROOTS + 4096;
-  im.q_ent = zalloc<uint4>((size_t)im.qc_cap * MN_QCH);
+  im.qc_low_n = (int)(E * 8 / ((size_t)MN_QCH * 16));
+  im.qc_cap = im.qc_low_n + (int)(E * 9 / 20 / MN_QCH) + 4 * MN_NROOTS + 4096;
+  im.q_ent = zalloc<uint4>((size_t)im.qc_cap * MN_QCH + 2 * MN_QCH);
+  im.init_keys = (uint64_t*)im.q_ent;  // one arena, as in the library
   im.qc_next = zalloc<int>(im.qc_cap);
   im.qc_free = zalloc<int>(im.qc_cap);
   im.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)(16384 + E / 128);
