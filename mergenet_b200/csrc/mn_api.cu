@@ -403,6 +403,7 @@ static int run_front(mn_plan* p, int B, const float* d_class, float* d_adj, int 
   P.use_tma = (N % 4 == 0) && (((uintptr_t)d_class & 15) == 0) && (((uintptr_t)d_adj & 15) == 0);
   P.clip = clip; P.sdb = sdb;
   long long tiles = (long long)B * P.tiles_per_image;
+  if (tiles >= (1ll << 31)) { g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
   int grid = (int)std::min<long long>(tiles, (long long)p->num_sms * MN_EDGE_CTAS_PER_SM);
   mn_edge_pass_kernel<<<grid, MN_EDGE_THREADS, p->edge_smem, s>>>(P);
   p->timings.edge_launches++;

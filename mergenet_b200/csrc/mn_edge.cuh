@@ -84,9 +84,7 @@ __device__ __forceinline__ float mn_log1m_exact(float s) { return (float)log(1.0
 __device__ __forceinline__ double mn_f32bits_to_f64(uint32_t b) {  // b = bits of a positive normal float
   return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
 }
-__device__ __forceinline__ double mn_small_int_to_f64(int k) {  // exact for |k| < 2^31
-  return __hiloint2double(0x43300000, (int)(0x80000000u ^ (uint32_t)k)) - 4503601774854144.0;  // 2^52 + 2^31
-}
+__device__ __forceinline__ double mn_small_int_to_f64(int k) { return (double)k; }  // (one XU op; exact)
 __device__ __forceinline__ float mn_logf_fast(float x, const MnLogfTab* tab) {
   const uint32_t ix = __float_as_uint(x);
   const uint32_t tmp = ix - 0x3f330000u;
@@ -215,8 +213,8 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_
   }
   __syncthreads();
 
-  const long long total_tiles = (long long)P.B * P.tiles_per_image;
-  auto issue = [&](long long tile, int stage) {
+  const int total_tiles = P.B * P.tiles_per_image;  // (checked < 2^31 by the host)
+  auto issue = [&](int tile, int stage) {
     // one elected thread: arm the barrier, then one bulk copy per input plane
     int b = (int)(tile / P.tiles_per_image);
     int start = (int)(tile % P.tiles_per_image) * TP;
@@ -232,7 +230,7 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_
   };
 
   uint32_t phase[2] = {0, 0};
-  long long tile = blockIdx.x;
+  int tile = blockIdx.x;
   if (P.use_tma && tid == 0 && tile < total_tiles) issue(tile, 0);
   int stage = 0;
   for (; tile < total_tiles; tile += gridDim.x, stage ^= 1) {
@@ -267,7 +265,7 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_
     if (P.use_tma) {
       // prefetch the next tile into the other input stage: its readers finished before the barrier
       // above, and only the issuing thread is held up by the 19 bulk-copy instructions
-      long long nxt = tile + gridDim.x;
+      int nxt = tile + (int)gridDim.x;
       if (tid == 0 && nxt < total_tiles) {
         mn_fence_proxy_async();
         issue(nxt, stage ^ 1);
