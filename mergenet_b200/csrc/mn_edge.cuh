@@ -80,6 +80,15 @@ __device__ __forceinline__ float mn_log1m_exact(float s) { return (float)log(1.0
 //
 // logf as glibc's FMA build evaluates it (the recipe of mn_logf_exact with its five multiply-adds
 // fused; bit-identical on the whole clipped domain, pinned exhaustively on the device): 6 fp64 ops.
+// polynomial constants live in constant memory: a DFMA takes one operand straight from the constant
+// bank, whereas an immediate double costs two MOVs per use inside the (register-tight) plane loops
+__constant__ double mn_kc[12] = {
+    0x1.62e42fefa39efp-1,    // 0: Ln2
+    0x1.5575b0be00b6ap-2,    // 1: logf A1
+    -0x1.ffffef20a4123p-2,   // 2: logf A2
+    -0x1.00ea348b88334p-2,   // 3: logf A0
+    -1.0 / 6, 0.2, -0.25, 1.0 / 3, -0.5,  // 4..8: log1p polynomial of log1m
+    -1.0, 1.0, 0.0};
 // (conversions run on the quarter-rate XU pipe, so the exact widenings are done with integer ops)
 __device__ __forceinline__ double mn_f32bits_to_f64(uint32_t b) {  // b = bits of a positive normal float
   return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
@@ -93,10 +102,10 @@ __device__ __forceinline__ float mn_logf_fast(float x, const MnLogfTab* tab) {
   const double z = mn_f32bits_to_f64(ix - (tmp & 0xff800000u));
   const double2 e = *reinterpret_cast<const double2*>(&tab[i]);  // (invc, logc) in one 16-byte load
   const double r = __fma_rn(z, e.x, -1.0);
-  const double y0 = __fma_rn(mn_small_int_to_f64(k), 0x1.62e42fefa39efp-1, e.y);
+  const double y0 = __fma_rn(mn_small_int_to_f64(k), mn_kc[0], e.y);
   const double r2 = __dmul_rn(r, r);
-  double y = __fma_rn(0x1.5575b0be00b6ap-2, r, -0x1.ffffef20a4123p-2);
-  y = __fma_rn(-0x1.00ea348b88334p-2, r2, y);
+  double y = __fma_rn(r, mn_kc[1], mn_kc[2]);
+  y = __fma_rn(r2, mn_kc[3], y);
   y = __fma_rn(y, r2, __dadd_rn(y0, r));
   return (float)y;
 }
@@ -119,11 +128,11 @@ __device__ __forceinline__ float mn_log1m_fast(float s, const MnLog1mTab* tab) {
   const double z = __hiloint2double((int)(hx - (tmp & 0xfff00000u)), __double2loint(x));
   const double2 e = *reinterpret_cast<const double2*>(&tab[i]);
   const double r = __fma_rn(z, e.x, -1.0);
-  const double t = __fma_rn(mn_small_int_to_f64(k), 0x1.62e42fefa39efp-1, e.y);
-  double q = __fma_rn(r, -1.0 / 6, 0.2);
-  q = __fma_rn(r, q, -0.25);
-  q = __fma_rn(r, q, 1.0 / 3);
-  q = __fma_rn(r, q, -0.5);
+  const double t = __fma_rn(mn_small_int_to_f64(k), mn_kc[0], e.y);
+  double q = __fma_rn(r, mn_kc[4], mn_kc[5]);
+  q = __fma_rn(r, q, mn_kc[6]);
+  q = __fma_rn(r, q, mn_kc[7]);
+  q = __fma_rn(r, q, mn_kc[8]);
   const double r2 = __dmul_rn(r, r);
   double y = __fma_rn(r2, q, r);
   y = __dadd_rn(y, t);
