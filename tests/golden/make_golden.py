@@ -35,5 +35,38 @@ def main():
         print(name, mask.shape, len(ocls), "instances")
 
 
+def unet_cfg1(h=64, w=128):
+    """BASELINE config 1 at a fixture-friendly size: the REFERENCE's own UNet(9, 10)
+    (models/Unet.py:118), torch.manual_seed(0), eval mode, input torch.rand(1, 3, h, w); class maps =
+    sigmoid channels 0..8, sameness maps = channels 9..18.  models/__init__.py is bypassed (it imports
+    caffe / pspnet code that this container lacks)."""
+    import types
+    import torch
+    pkg = types.ModuleType("models")
+    pkg.__path__ = ["/root/reference/models"]
+    sys.modules["models"] = pkg
+    from models.Unet import UNet
+    torch.manual_seed(0)
+    net = UNet(9, 10).eval()
+    with torch.no_grad():
+        out = torch.sigmoid(net(torch.rand(1, 3, h, w)))[0].numpy().astype(np.float32)
+    return np.ascontiguousarray(out[:9]), np.ascontiguousarray(out[9:19])
+
+
+def main_unet():
+    from mergenet_b200 import synth
+    out = os.path.dirname(os.path.abspath(__file__))
+    cp, sp = unet_cfg1()
+    offs = synth.generate_offsets(40, 10)
+    for tag, opts in (("recipe", cases.RECIPE_OPTS), ("plain", cases.PLAIN_OPTS)):
+        mask, ocls = oracle.ref_run_segmentation(cp, sp, 9, offs, *opts)
+        np.savez_compressed(os.path.join(out, "unet_cfg1_64x128_%s.npz" % tag), class_pred=cp, adj_pred=sp,
+                            num_classes=np.int32(9), offsets=np.array(offs, np.int32),
+                            opts=np.array(opts, np.float32), ref_mask=mask.astype(np.int16),
+                            ref_object_class=np.array(ocls, np.int32))
+        print("unet_cfg1", tag, mask.shape, len(ocls), "instances")
+
+
 if __name__ == "__main__":
     main()
+    main_unet()
