@@ -70,6 +70,7 @@ typedef struct {
   long long queue_chunks_used, pixel_pool_used, tree_nodes_used;
   long long requeues; /* guard entries replaced by an exact entry (lazy queue) */
   long long hash_overflow; /* records living in the hash overflow area */
+  long long pixel_pool_collections; /* semi-space collections of the pixel-array pool */
   /* SM cycles of the image's CTA: total, and by phase (select, plan, accept, commit, hot-queue update,
    * flush, refill, split, solo merges, gc) */
   long long cycles_total;

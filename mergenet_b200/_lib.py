@@ -58,7 +58,7 @@ class ImageStats(ctypes.Structure):
                 ("n_init_entries", ctypes.c_int)] + [(n, ctypes.c_longlong) for n in (
                     "rounds", "events", "merges", "restores", "invalid_pops", "solo_events", "refills",
                     "flushes", "splits", "pairs", "cuts_conflict", "cuts_cascade", "cuts_capacity",
-                    "queue_chunks_used", "pixel_pool_used", "tree_nodes_used", "requeues", "hash_overflow", "cycles_total")] + [
+                    "queue_chunks_used", "pixel_pool_used", "tree_nodes_used", "requeues", "hash_overflow", "pixel_pool_collections", "cycles_total")] + [
         ("cycles", ctypes.c_longlong * 16)]
 
     CYCLE_NAMES = ("select", "plan", "accept", "commit", "hot", "flush", "refill", "split", "solo", "gc",

@@ -222,7 +222,7 @@ static WsLayout ws_layout(int H, int W, int C, int K) {
   const size_t N = (size_t)H * W, E = N * K;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
-  L.pix_cap = (int)(16 * N + 4096);
+  L.pix_cap = (int)(2 * (3 * N + 2048));  // two halves; the live arrays never exceed 2 N ints (mn_pix_gc)
   // One arena holds, in turn, the edge pass outputs rec_same | rec_diff (8 E bytes, dead after record
   // init), the sorted initial keys (8 E bytes, written by the sort), and the queue chunks: the consumed
   // prefix of the keys is recycled as chunks (qc_low_n of them), and qc_cap - qc_low_n extra chunks
@@ -550,7 +550,7 @@ extern "C" int mn_plan_image_stats(mn_plan* p, int image, mn_image_stats* o) {
   for (int i = 0; i < 16; i++) o->cycles[i] = c.cyc[i];
   o->cycles_total = c.cycles_total;
   o->queue_chunks_used = c.qc_bump; o->pixel_pool_used = c.pix_bump; o->tree_nodes_used = c.tn_bump;
-  o->requeues = c.requeues; o->hash_overflow = c.hash_ovf_n;
+  o->requeues = c.requeues; o->hash_overflow = c.hash_ovf_n; o->pixel_pool_collections = c.pix_gcs;
   return MN_STATUS_OK;
 }
 extern "C" int mn_plan_image_logprob(mn_plan* p, int image, double* out4) {

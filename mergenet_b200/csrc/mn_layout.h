@@ -109,6 +109,7 @@ struct MnCtl {
   long long refills, flushes, splits, pairs, cuts_conflict, cuts_cascade, cuts_capacity;
   long long cycles_total;
   long long requeues;
+  long long pix_gcs;   // collections of the pixel-array pool
   long long cyc[16];   // cycle buckets (MN_CY_*)
 };
 

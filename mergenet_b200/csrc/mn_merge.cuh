@@ -50,6 +50,7 @@
 #define MN_SB 1024       // sort buffer capacity
 #define MN_LEAFCAP 512   // tree leaves larger than this are split before they are loaded
 #define MN_CT 2048       // conflict-table slots (power of two)
+#define MN_GCL 512        // objects scanned per garbage-collection step (one per thread)
 #define MN_LF 128         // leaves one refill may load
 #define MN_OVF 128        // records in the hash overflow area (cached in shared memory)
 #define MN_REFILL_TARGET 384      // stop loading tree leaves once this many entries are staged
@@ -139,6 +140,10 @@ struct MnSm {
   int nhot, nins, nne, ncw, npw, npr, ncand, nacc, cutpos, solo, first, tmp0, tmp1, tmp2, tmp3;
   int ds_ngroups, ds_ndir;  // distribute() counters
   int pix_bump;             // pixel-array pool bump pointer (mirrors MnCtl)
+  int pix_hi;               // end of the active half of the pool (semi-space: the live arrays never exceed 2 N ints)
+  int need_gc, gc_tried;    // the round's arrays do not fit: collect, then redo the round
+  int gc_list[MN_GCL]; int gc_dst[MN_GCL]; int gc_src[MN_GCL]; int gc_n;  // large arrays of one scan block, copied cooperatively
+  long long st_gcs;
   int hash_ovf_n;           // entries of the overflow cache below (tombstones included)
   int ovf_lo[MN_OVF]; int ovf_hi[MN_OVF]; int ovf_rec[MN_OVF];  // records that fit neither hash bucket
   int failed;               // sticky copy of ctl->status != 0
@@ -1274,7 +1279,7 @@ MN_D void mn_alloc_pixels(const MnImage& im, MnSm& sm, int j) {
   const int capn = mn_pix_cap(na), capo = mn_pix_cap(n_a);
   if (capn != capo) {
     int ptr = sm.pix_bump;
-    if (ptr + capn > im.pix_cap) { mn_fail(im, MN_ERR_PL_POOL); ptr = 0; }
+    if (ptr + capn > sm.pix_hi) { sm.need_gc = 1; ptr = 0; }
     else sm.pix_bump = ptr + capn;
     sm.c_newptr[j] = ptr;
     sm.cp_list[sm.ncp] = j; sm.cp_base[sm.ncp + 1] = sm.cp_base[sm.ncp] + n_a; sm.ncp++;
@@ -1304,6 +1309,7 @@ MN_D void mn_solo_merge(const MnImage& im, MnSm& sm, const MnMergeArgs& A, float
     sm.c_kind[0] = MN_K_MERGE; sm.c_accept[0] = 1; sm.c_maxnew[0] = 0; sm.c_pbase[0] = 0; sm.c_pwbase[0] = 0;
     // entries of the consumed prefix that forget their guard
     sm.st_solo++; sm.st_events++; sm.st_merges++; sm.st_rounds++;
+    sm.gc_tried = 0;
     sm.nne = 0;
     sm.ncp = 0; sm.cp_base[0] = 0;
     mn_alloc_pixels(im, sm, 0);
@@ -1368,6 +1374,25 @@ MN_D void mn_solo_merge(const MnImage& im, MnSm& sm, const MnMergeArgs& A, float
   if (MN_T0) mn_commit_merge_object(im, sm, A, 0);
   MN_FOR(c, C) im.clp[(size_t)sm.c_surv[0] * C + c] = c_clp[(size_t)2 * C + c];
   MN_SYNC();
+}
+
+MN_D void mn_pix_gc(const MnImage& im, MnSm& sm, const MnMergeArgs& A);
+// The solo merge of candidate f allocates its survivor array up front: collect the pool first when it
+// would not fit.  Returns true when the round has to be planned again (or the image failed).
+MN_D bool mn_solo_needs_gc(const MnImage& im, MnSm& sm, const MnMergeArgs& A, int f) {
+  MN_SYNC();
+  if (MN_T0) {
+    const int na = sm.c_na[f], n_a = na - sm.c_nb[f];
+    const int capn = mn_pix_cap(na), capo = mn_pix_cap(n_a);
+    sm.tmp3 = (capn != capo && sm.pix_bump + capn > sm.pix_hi) ? 1 : 0;
+  }
+  MN_SYNC();
+  if (!sm.tmp3) return false;
+  if (sm.gc_tried) { if (MN_T0) mn_fail(im, MN_ERR_PL_POOL); MN_SYNC(); return true; }
+  mn_pix_gc(im, sm, A);
+  if (MN_T0) sm.gc_tried = 1;
+  MN_SYNC();
+  return true;
 }
 
 // consume the non-event entries of the window prefix [0, n): forget guards of dormant records
@@ -1500,7 +1525,7 @@ MN_D void mn_pass_accept(const MnImage& im, MnSm& sm, int ncand, int npr) {
   const int total_need = __shfl_sync(0xffffffffu, need_incl, 31);
   const int total_cp = __shfl_sync(0xffffffffu, cp_incl, 31);
   const int bump = sm.pix_bump;
-  const bool fits = bump + total_need <= im.pix_cap;
+  const bool fits = bump + total_need <= sm.pix_hi;
   if (acc && k == MN_K_MERGE) {
     if (need) {
       const int ci = __popc(needm & lt);
@@ -1513,18 +1538,25 @@ MN_D void mn_pass_accept(const MnImage& im, MnSm& sm, int ncand, int npr) {
   if (lane == 0) {
     const int ncp = __popc(needm);
     sm.ncp = ncp; sm.cp_base[ncp] = total_cp;
-    if (fits) sm.pix_bump = bump + total_need; else mn_fail(im, MN_ERR_PL_POOL);
     sm.cutpos = cut; sm.nacc = __popc(accm);
-    sm.st_merges += __popc(mergem); sm.st_restores += __popc(restm); sm.st_requeues += __popc(reqm);
-    sm.st_events += __popc(mergem) + __popc(restm);
-    sm.st_invalid += __popc(ungm) + __popc(dropm);
-    if (cm) { if (confcut) sm.st_cut_conf++; else sm.st_cut_casc++; }
-    sm.st_rounds++; sm.st_pairs += npr;
+    if (fits) {
+      sm.pix_bump = bump + total_need;
+      sm.st_merges += __popc(mergem); sm.st_restores += __popc(restm); sm.st_requeues += __popc(reqm);
+      sm.st_events += __popc(mergem) + __popc(restm);
+      sm.st_invalid += __popc(ungm) + __popc(dropm);
+      if (cm) { if (confcut) sm.st_cut_conf++; else sm.st_cut_casc++; }
+      sm.st_rounds++; sm.st_pairs += npr;
+    } else {
+      sm.need_gc = 1;  // nothing of this round is committed: collect the pixel pool and plan it again
+    }
   }
 #else
   uint32_t runmax = 0;  // bits+1 of the largest priority stored by an accepted member
   int cut = ncand, nacc = 0;
   sm.ncp = 0; sm.cp_base[0] = 0;
+  const long long s0 = sm.st_invalid, s1 = sm.st_cut_conf, s2 = sm.st_cut_casc, s3 = sm.st_merges, s4 = sm.st_events,
+                  s5 = sm.st_restores, s6 = sm.st_requeues;
+  const int bump0 = sm.pix_bump;
   for (int j = 0; j < ncand; j++) {
     const int k = sm.c_kind[j];
     if (k == MN_K_DROP) { sm.st_invalid++; continue; }
@@ -1540,8 +1572,65 @@ MN_D void mn_pass_accept(const MnImage& im, MnSm& sm, int ncand, int npr) {
     else sm.st_invalid++;
   }
   sm.cutpos = cut; sm.nacc = nacc;
-  sm.st_rounds++; sm.st_pairs += npr;
+  if (sm.need_gc) {  // nothing of this round is committed: collect the pixel pool and plan it again
+    sm.st_invalid = s0; sm.st_cut_conf = s1; sm.st_cut_casc = s2; sm.st_merges = s3; sm.st_events = s4;
+    sm.st_restores = s5; sm.st_requeues = s6; sm.pix_bump = bump0;
+  } else {
+    sm.st_rounds++; sm.st_pairs += npr;
+  }
 #endif
+}
+
+// Semi-space collection of the pixel pool.  Every merge that outgrows its survivor's array abandons the
+// old one (and the absorbed object's), so the bump pointer runs far ahead of what is alive; but the live
+// arrays never exceed 2 N ints (capacity < 2 * npix, and the pixels of all objects add up to N).  When a
+// round's arrays do not fit the active half, the live arrays are copied, packed, to the other half: one
+// scan over the objects (MN_GCL per step, one per thread), small arrays copied by their thread, large
+// ones by the whole block.  Costs ~1 ms and happens a handful of times per image.
+MN_D void mn_pix_gc(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
+  MN_SYNC();
+  const int half = im.pix_cap / 2;
+  const int new_lo = sm.pix_hi > half ? 0 : half;
+  if (MN_T0) { sm.tmp0 = new_lo; sm.st_gcs++; }
+  MN_SYNC();
+  const int STEP = 8 * MN_GCL;  // objects per step: 8 per thread slot, parents fetched together
+  for (int base = 0; base < A.N; base += STEP) {
+    if (MN_T0) sm.gc_n = 0;
+    MN_SYNC();
+    MN_FOR(i, MN_GCL) {
+      int par[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) { const int p = base + q * MN_GCL + i; par[q] = p < A.N ? im.parent[p] : -1; }
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int p = base + q * MN_GCL + i;
+        if (par[q] != p) continue;
+        const uint4 o = im.obj[p];
+        const int n = mn_nc_npix(o.x);
+        if (n <= 1) continue;
+        const int dst = MN_ATOMIC_ADD(&sm.tmp0, mn_pix_cap(n));
+        int e = -1;
+        if (n > 32) { e = MN_ATOMIC_ADD(&sm.gc_n, 1); if (e >= MN_GCL) e = -1; }
+        if (e >= 0) { sm.gc_list[e] = p; sm.gc_dst[e] = dst; sm.gc_src[e] = (int)o.z; }
+        else for (int t = 0; t < n; t++) im.pix_pool[dst + t] = im.pix_pool[(int)o.z + t];  // small (or list full)
+        im.obj[p].z = (uint32_t)dst;
+      }
+    }
+    MN_SYNC();
+    const int nl = sm.gc_n < MN_GCL ? sm.gc_n : MN_GCL;
+    for (int e = 0; e < nl; e++) {  // large arrays: the whole block copies each
+      const int p = sm.gc_list[e], dst = sm.gc_dst[e], src = sm.gc_src[e];
+      const int n = mn_nc_npix(im.obj[p].x);
+      MN_FOR(q, n) im.pix_pool[dst + q] = im.pix_pool[src + q];
+    }
+    MN_SYNC();
+  }
+  if (MN_T0) {
+    sm.pix_bump = sm.tmp0;
+    sm.pix_hi = new_lo + half;
+    if (sm.pix_bump > sm.pix_hi) mn_fail(im, MN_ERR_PL_POOL);  // (cannot happen: live <= 2 N <= half)
+  }
+  MN_SYNC();
 }
 
 // The scheduler for one image.  c_clp: MN_H * 3 * C floats of shared memory.
@@ -1550,7 +1639,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
   if (MN_T0) {
     sm.hsel = 0; sm.nhot = 0; sm.nins = 0; sm.nne = 0; sm.cold_empty = 0;
     sm.b_mp = 0; sm.b_lo = 0; sm.b_hi = 0; sm.path_n = 0; sm.failed = 0;
-    sm.pix_bump = 0; sm.hash_ovf_n = im.ctl->hash_ovf_n;
+    sm.pix_bump = 0; sm.pix_hi = im.pix_cap / 2; sm.need_gc = 0; sm.gc_tried = 0; sm.st_gcs = 0; sm.hash_ovf_n = im.ctl->hash_ovf_n;
     sm.qc_free_top = 0; sm.qc_bump = im.qc_low_n; sm.qc_low_bump = 0; sm.qc_low_avail = 0; sm.tn_bump = MN_NROOTS; sm.tree_entries = 0; sm.peak_entries = 0; sm.peak_chunks = 0;
     sm.st_rounds = sm.st_events = sm.st_merges = sm.st_restores = sm.st_invalid = sm.st_solo = 0;
     sm.st_refills = sm.st_flushes = sm.st_splits = sm.st_pairs = sm.st_cut_conf = sm.st_cut_casc = sm.st_cut_cap = 0;
@@ -1629,6 +1718,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     MN_SYNC();
     if (sm.solo) {
       const int f = sm.first;
+      if (mn_solo_needs_gc(im, sm, A, f)) continue;
       mn_consume_unguard(im, sm, f);
       mn_solo_merge(im, sm, A, c_clp, f);
       MN_TOC(MN_CY_SOLO);
@@ -1657,6 +1747,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     MN_SYNC();
     if (sm.solo) {
       const int f = sm.first;
+      if (mn_solo_needs_gc(im, sm, A, f)) continue;
       mn_consume_unguard(im, sm, f);
       mn_solo_merge(im, sm, A, c_clp, f);
       MN_TOC(MN_CY_SOLO);
@@ -1714,6 +1805,13 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     // ---- phase 6: accept the longest provably sequential prefix ----
     mn_pass_accept(im, sm, ncand, npr);
     MN_SYNC();
+    if (sm.need_gc) {
+      if (sm.gc_tried) { if (MN_T0) mn_fail(im, MN_ERR_PL_POOL); continue; }  // even a packed pool is too small
+      mn_pix_gc(im, sm, A);
+      if (MN_T0) { sm.need_gc = 0; sm.gc_tried = 1; }
+      continue;  // nothing was committed: the same window is staged and planned again
+    }
+    if (MN_T0) sm.gc_tried = 0;
 #ifdef MN_EMUL_TRACE
     fprintf(stderr, "round: ncand %d nacc %d cut %d nhot %d nins %d npr %d cold_empty %d key0 %.9g\n", ncand, sm.nacc, sm.cutpos, sm.nhot, sm.nins, npr, sm.cold_empty, sm.c_key[0]);
 #endif
@@ -1760,7 +1858,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     c->invalid_pops = sm.st_invalid; c->solo_events = sm.st_solo; c->refills = sm.st_refills;
     c->flushes = sm.st_flushes; c->splits = sm.st_splits; c->pairs = sm.st_pairs;
     c->cuts_conflict = sm.st_cut_conf; c->cuts_cascade = sm.st_cut_casc; c->cuts_capacity = sm.st_cut_cap;
-    c->requeues = sm.st_requeues;
+    c->requeues = sm.st_requeues; c->pix_gcs = sm.st_gcs;
     c->pix_bump = sm.pix_bump; c->hash_ovf_n = sm.hash_ovf_n;
     c->qc_bump = sm.qc_bump; c->qc_free_top = sm.qc_free_top; c->tn_bump = sm.tn_bump; c->tree_entries = sm.tree_entries;
     c->static_cursor = sm.static_cursor; c->n_init = sm.n_init;

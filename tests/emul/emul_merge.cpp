@@ -30,7 +30,7 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   im.cls = zalloc<int>(N);
   im.obj = zalloc<uint4>(N);
   im.parent = zalloc<int>(N);
-  im.pix_cap = 16 * N + 4096;
+  im.pix_cap = 2 * (3 * N + 2048);
   im.pix_pool = zalloc<int>(im.pix_cap);
   im.rec = zalloc<uint4>(2 * E);
   im.hash_nbuckets = (uint32_t)(E * 16 / 10 / 8 + 64);
@@ -143,7 +143,7 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
     MnCtl* c = im.ctl;
     long long v[16] = {c->rounds, c->events, c->merges, c->restores, c->invalid_pops, c->solo_events,
                        c->refills, c->flushes, c->splits, c->pairs, c->cuts_conflict, c->cuts_cascade,
-                       c->cuts_capacity, (long long)c->qc_bump, (long long)c->pix_bump, (long long)c->tn_bump};
+                       c->cuts_capacity, (long long)c->qc_bump, (long long)c->pix_gcs, (long long)c->tn_bump};
     memcpy(stats, v, sizeof(v));
   }
   // (leaks on purpose: short-lived test process helper)
