@@ -175,8 +175,20 @@ def run_own_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    B = args.batch
     h, w = args.height, args.width
+    B = args.batch
+    if B <= 0:
+        # one persistent CTA per image: the more images in flight the better, up to one per SM; a
+        # 1024x2048 image needs 1.36 GB of workspace + its maps + its outputs (device and staging copies)
+        free_b, _ = torch.cuda.mem_get_info(local)
+        per_img = (BatchSegmenter.workspace_bytes_per_image(h, w, C, K) + 4 * h * w * (C + K) + 8 * h * w)
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        B = int(max(1, min(sms, (free_b - (5 << 30)) // per_img)))
+        B = (B // 8) * 8 if B >= 16 else B
+        if distributed:  # every rank runs the same batch
+            t = torch.tensor([B], dtype=torch.int64, device=torch.device("cuda", local))
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            B = int(t.item())
     # synthetic inputs: `distinct` different images per rank, tiled to the batch (generation is slow)
     distinct = min(B, args.distinct)
     cp, sp, offs = make_images(distinct, 1000 + rank * B, h, w)
@@ -326,7 +338,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--batch", type=int, default=env_int("MN_BENCH_BATCH", 112), help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=env_int("MN_BENCH_BATCH", 0),
+                    help="images per GPU per step (0 = as many as fit the free HBM, at most one per SM)")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic images per rank (tiled to the batch)")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
