@@ -130,6 +130,9 @@ int mn_debug_edge_dump(int height, int width, int num_classes, int num_offsets,
 /* Device libm restatements over n consecutive float bit patterns starting at first_bits:
  * which = 0: logf(x); 1: (float)log(1.0 - (double)x); 2: the same_different_bias transform. */
 int mn_debug_libm(int which, unsigned first_bits, unsigned n, float bias, float* h_out);
+/* times the edge pass alone on `batch` synthetic images (development hook; average ms per launch) */
+int mn_debug_edge_bench(int height, int width, int num_classes, int num_offsets, const int* offset_list,
+                        int batch, int iters, int clip, float* ms_per_launch);
 
 #ifdef __cplusplus
 }

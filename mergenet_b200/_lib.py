@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXPORTS = ["c_run_segmentation", "mn_last_error", "mn_status_string", "mn_device_count",
            "mn_workspace_bytes_per_image", "mn_plan_create", "mn_plan_destroy",
            "mn_segment_batch_device", "mn_segment_batch_host", "mn_plan_image_stats",
-           "mn_plan_timings", "mn_plan_image_logprob", "mn_debug_edge_dump", "mn_debug_libm"]
+           "mn_plan_timings", "mn_plan_image_logprob", "mn_debug_edge_dump", "mn_debug_libm", "mn_debug_edge_bench"]
 
 
 class MergeNetError(RuntimeError):
@@ -122,6 +122,8 @@ def lib():
     L.mn_debug_edge_dump.restype = ctypes.c_int
     L.mn_debug_edge_dump.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _I, _F, _F,
                                      ctypes.c_float, ctypes.c_float, ctypes.c_float, _F, _I, _F, _F, _F, _F, _I, _I]
+    L.mn_debug_edge_bench.restype = ctypes.c_int
+    L.mn_debug_edge_bench.argtypes = [ctypes.c_int] * 4 + [_I] + [ctypes.c_int] * 3 + [_F]
     L.mn_debug_libm.restype = ctypes.c_int
     L.mn_debug_libm.argtypes = [ctypes.c_int, ctypes.c_uint, ctypes.c_uint, ctypes.c_float, _F]
     _lib = L

@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(256) mn_logprob_kernel(const MnImage* imgs, in
 __global__ void mn_libm_kernel(int which, uint32_t first_bits, uint32_t n, float bias, float* out) {
   __shared__ MnLogfTab tab[16];
   __shared__ MnLog1mTab tab1m[128];
+  __shared__ MnLogfTab2 tab2[MN_LOGF2_PAD];
+  mn_logf2_fill(tab2, threadIdx.x, blockDim.x);
   if (threadIdx.x < 16) {
     const MnLogfTab t16[16] = {MN_LOGF_TABLE};
     tab[threadIdx.x] = t16[threadIdx.x];
@@ -176,6 +178,8 @@ __global__ void mn_libm_kernel(int which, uint32_t first_bits, uint32_t n, float
     else if (which == 1) r = mn_log1m_fast(x, tab1m);
     else if (which == 3) r = mn_logf_exact(x, tab);      // the unfused recipe (bias path)
     else if (which == 4) r = mn_log1m_exact(x);
+    else if (which == 5) r = mn_logf_2d(__float_as_uint(x), mn_f32bits_to_f64(__float_as_uint(x)), tab2);  // warp-pipeline kernel
+    else if (which == 6) r = mn_log1m_2(mn_f32bits_to_f64(__float_as_uint(x)), tab1m);
     else r = mn_bias_sameness(x, bias, tab);
     out[i] = r;
   }
@@ -202,6 +206,7 @@ struct mn_plan {
   cudaEvent_t ev[9];
   int num_sms;
   int edge_tp, edge_smem, merge_smem, merge_H;
+  int edge2_ncons, edge2_ctas, edge2_smem;  // warp-pipeline edge kernel: consumer warps per CTA (0: not usable), CTAs per SM
   std::vector<MnCtl> h_ctl;
   double* d_logprob;            // [max_batch][4] class / sameness / differentness terms
   std::vector<double> h_logprob;
@@ -266,6 +271,30 @@ static int choose_edge_tile(int C, int K, int* smem_bytes) {
   if (tp < 4) tp = 4;
   *smem_bytes = (int)(128 + per_px * tp + 16 * sizeof(MnLogfTab) + 128 * sizeof(MnLog1mTab) + 64);
   return tp;
+}
+
+// warp-pipeline edge kernel: consumer warps per CTA and CTAs per SM that maximise the resident consumer
+// warps; 0 when the shape leaves too few (many classes: the tile kernel's smaller tiles win)
+static int choose_edge2(int C, int K, int* ctas_out, int* smem_bytes) {
+  const size_t per_warp = 128 * ((size_t)MN_EDGE2_STAGES * (C + K) + (size_t)(C + 2 * K));
+  const size_t fixed = sizeof(MnEdge2Smem) + 1024 + 256;  // static tables + per-CTA reservation
+  int best = 0, best_score = 0, best_ctas = 0;
+  for (int nc = 8; nc >= 1; nc--) {
+    size_t per_cta = per_warp * nc + fixed;
+    int ctas = (int)std::min<size_t>((size_t)(227 * 1024) / per_cta, 2048 / (32 * (nc + 1)));
+    ctas = std::min(ctas, 65536 / (80 * 32 * (nc + 1)));  // register file at <= 80 registers per thread
+    if (ctas * nc > best_score) { best_score = ctas * nc; best = nc; best_ctas = ctas; }
+  }
+  if (const char* e = getenv("MN_EDGE2_NCONS")) {  // tuning hook: "ncons,ctas"; "0" disables the kernel
+    int nc = 0, ct = 0;
+    int got = sscanf(e, "%d,%d", &nc, &ct);
+    if (got >= 1 && nc == 0) return 0;
+    if (got == 2 && nc >= 1 && nc <= 8 && ct >= 1) { best = nc; best_ctas = ct; best_score = 99; }
+  }
+  if (best_score < 12) return 0;
+  *ctas_out = best_ctas;
+  *smem_bytes = (int)(per_warp * best);
+  return best;
 }
 
 extern "C" void mn_plan_destroy(mn_plan* p) {
@@ -377,11 +406,46 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
     p->merge_smem = (int)(base + (size_t)Hwin * 3 * C * 4);
     if ((size_t)p->merge_smem > limit) return fail(MN_STATUS_BAD_ARG);
   }
+  p->edge2_ncons = choose_edge2(C, K, &p->edge2_ctas, &p->edge2_smem);
+  if (p->edge2_ncons &&
+      (cudaFuncSetAttribute(mn_edge_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->edge2_smem) != cudaSuccess ||
+       cudaFuncSetAttribute(mn_edge_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->edge2_smem) != cudaSuccess))
+    p->edge2_ncons = 0;
   if (cudaFuncSetAttribute(mn_edge_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->edge_smem) != cudaSuccess ||
       cudaFuncSetAttribute(mn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->merge_smem) != cudaSuccess)
     return fail(MN_STATUS_CUDA);
   p->h_ctl.resize(max_batch);
   *out = p;
+  return MN_STATUS_OK;
+}
+
+// the edge pass for images [0, B): the warp-pipeline kernel when it applies, else the tile kernel
+static int launch_edge(mn_plan* p, int B, const float* d_class, float* d_adj, int clip, float sdb, cudaStream_t s) {
+  const int N = p->N, C = p->C, K = p->K;
+  MnEdgeParams P;
+  P.class_pred = d_class; P.adj_pred = d_adj; P.adj_pred_rw = sdb != 0.0f ? d_adj : nullptr;
+  P.imgs = p->d_imgs;
+  P.B = B; P.C = C; P.K = K; P.N = N; P.TP = p->edge_tp;
+  P.tiles_per_image = (N + P.TP - 1) / P.TP;
+  P.use_tma = (N % 4 == 0) && (((uintptr_t)d_class & 15) == 0) && (((uintptr_t)d_adj & 15) == 0);
+  P.clip = clip; P.sdb = sdb;
+  const bool warp_pipeline = p->edge2_ncons > 0 && P.use_tma && sdb == 0.0f;
+  if (warp_pipeline) {
+    P.TP = 32 * p->edge2_ncons;
+    P.tiles_per_image = (N + P.TP - 1) / P.TP;
+  }
+  long long tiles = (long long)B * P.tiles_per_image;
+  if (tiles >= (1ll << 31)) { g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
+  if (warp_pipeline) {
+    int grid = (int)std::min<long long>(tiles, (long long)p->num_sms * p->edge2_ctas);
+    int threads = 32 * (p->edge2_ncons + 1);
+    if (clip) mn_edge_warp_kernel<true><<<grid, threads, p->edge2_smem, s>>>(P);
+    else mn_edge_warp_kernel<false><<<grid, threads, p->edge2_smem, s>>>(P);
+  } else {
+    int grid = (int)std::min<long long>(tiles, (long long)p->num_sms * MN_EDGE_CTAS_PER_SM);
+    mn_edge_pass_kernel<<<grid, MN_EDGE_THREADS, p->edge_smem, s>>>(P);
+  }
+  p->timings.edge_launches++;
   return MN_STATUS_OK;
 }
 
@@ -395,18 +459,7 @@ static int run_front(mn_plan* p, int B, const float* d_class, float* d_adj, int 
     p->timings.other_launches++;
   }
   MN_CUDA_OK(cudaEventRecord(p->ev[1], s));
-  MnEdgeParams P;
-  P.class_pred = d_class; P.adj_pred = d_adj; P.adj_pred_rw = sdb != 0.0f ? d_adj : nullptr;
-  P.imgs = p->d_imgs;
-  P.B = B; P.C = C; P.K = K; P.N = N; P.TP = p->edge_tp;
-  P.tiles_per_image = (N + P.TP - 1) / P.TP;
-  P.use_tma = (N % 4 == 0) && (((uintptr_t)d_class & 15) == 0) && (((uintptr_t)d_adj & 15) == 0);
-  P.clip = clip; P.sdb = sdb;
-  long long tiles = (long long)B * P.tiles_per_image;
-  if (tiles >= (1ll << 31)) { g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
-  int grid = (int)std::min<long long>(tiles, (long long)p->num_sms * MN_EDGE_CTAS_PER_SM);
-  mn_edge_pass_kernel<<<grid, MN_EDGE_THREADS, p->edge_smem, s>>>(P);
-  p->timings.edge_launches++;
+  if (int rc = launch_edge(p, B, d_class, d_adj, clip, sdb, s)) return rc;
   MN_CUDA_OK(cudaEventRecord(p->ev[2], s));
   for (int b = 0; b < B; b++) {
     MnRecInitParams R;
@@ -638,6 +691,45 @@ extern "C" int mn_debug_edge_dump(int H, int W, int C, int K, const int* offset_
     oml[r] = v ? b.x : 0.f; same[r] = v ? b.y : 0.f; diff[r] = v ? mn_u2f(a.w) : 0.f; mp[r] = v ? b.w : 0.f;
   }
   return done(MN_STATUS_OK);
+}
+
+// dev hook: time the edge pass alone on B synthetic images (values uniform in the clipped domain)
+__global__ void mn_fill_probs_kernel(float* p, size_t n, uint32_t seed) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    float v = (float)(h >> 8) * (1.0f / 16777216.0f);
+    p[i] = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
+  }
+}
+extern "C" int mn_debug_edge_bench(int H, int W, int C, int K, const int* offset_list, int B, int iters, int clip,
+                                   float* ms_per_launch) {
+  mn_plan* p = nullptr;
+  int rc = mn_plan_create(&p, B, H, W, C, K, offset_list, 0);
+  if (rc) return rc;
+  auto done = [&](int code) { mn_plan_destroy(p); g_last_error = code; return code; };
+  const size_t N = p->N;
+  float *dc = nullptr, *da = nullptr;
+  if (cudaMalloc(&dc, (size_t)B * C * N * 4) != cudaSuccess || cudaMalloc(&da, (size_t)B * K * N * 4) != cudaSuccess) {
+    cudaFree(dc);
+    return done(MN_STATUS_CUDA);
+  }
+  cudaStream_t s = p->stream;
+  mn_fill_probs_kernel<<<2048, 256, 0, s>>>(dc, (size_t)B * C * N, 1u);
+  mn_fill_probs_kernel<<<2048, 256, 0, s>>>(da, (size_t)B * K * N, 2u);
+  for (int w = 0; w < 2; w++) rc = launch_edge(p, B, dc, da, clip, 0.0f, s);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, s);
+  for (int it = 0; it < iters && !rc; it++) rc = launch_edge(p, B, dc, da, clip, 0.0f, s);
+  cudaEventRecord(e1, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(dc); cudaFree(da);
+  if (ms_per_launch) *ms_per_launch = ms / (float)(iters > 0 ? iters : 1);
+  return done(rc ? rc : (e == cudaSuccess ? MN_STATUS_OK : MN_STATUS_CUDA));
 }
 
 extern "C" int mn_debug_libm(int which, unsigned first_bits, unsigned n, float bias, float* h_out) {

@@ -118,6 +118,7 @@ __device__ __forceinline__ float mn_logf_fast(float x, const MnLogfTab* tab) {
 struct MnLog1mTab {
   double invc, logc;
 };
+__constant__ MnLogfTab mn_logf_table_c[16] = {MN_LOGF_TABLE};
 __constant__ MnLog1mTab mn_log1m_table[128] = {MN_LOG1M_TABLE};
 __device__ __forceinline__ float mn_log1m_fast(float s, const MnLog1mTab* tab) {
   const double x = __dadd_rn(1.0, -mn_f32bits_to_f64(__float_as_uint(s)));  // exact
@@ -388,6 +389,259 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_
                                       //  of `in`, which is refilled only after the next iteration's barrier)
   }
   if (tid == 0) mn_tma_store_wait_read();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 1b  mn_edge_warp_kernel: the same pass as a barrier-free warp pipeline (the fast path for
+// sdb == 0 and TMA-able inputs; mn_edge_pass_kernel above stays the general path).
+//   * one PRODUCER warp per CTA: an elected lane waits on the stage's `empty` mbarrier and issues the
+//     C+K 1-D TMA bulk loads of the next tile (full / empty mbarrier ring, no __syncthreads anywhere
+//     in the steady state);
+//   * each CONSUMER warp owns 32 consecutive pixels of the tile, one pixel per lane, all C+K planes
+//     (plane-major smem reads: conflict free), keeps the first-argmax in registers, stages its
+//     (C+2K)*32 results in its OWN buffer and sends them off with its own three bulk stores -- a
+//     warp never waits for another warp, only for data;
+//   * logf takes ONE 16-byte table entry {invc[i]*2^-k, fma(k, Ln2, logc[i])} indexed by the top
+//     mantissa/exponent bits (k in [-23, 0] on the clipped domain: 384 entries): the exponent
+//     scaling of z and the k*Ln2 term are exact functions of (k, i), so the result is the same bits
+//     as glibc's recipe with 6 fp64 operations, one conversion and 3 integer
+//     operations per value.  Inputs outside the clipped domain (possible only when the caller did
+//     not clip, c_segment.pyx:53-55) take the generic recipe.
+struct MnLogfTab2 {
+  double invc_s, y0;
+};
+#define MN_LOGF2_KMIN 23
+#define MN_LOGF2_N ((MN_LOGF2_KMIN + 1) * 16)  // rows k = -23 .. 0: x in [0.7 * 2^-23, 1.4)
+#define MN_LOGF2_PAD 512                       // table padded to a power of two: a masked index never leaves it
+#define MN_LOGF2_BIAS (0x3f330000u - ((uint32_t)(MN_LOGF2_KMIN * 16) << 19))
+__device__ __forceinline__ void mn_logf2_fill(MnLogfTab2* tab2, int tid, int nt) {
+  for (int e = tid; e < MN_LOGF2_PAD; e += nt) {
+    const int k = (e >> 4) - MN_LOGF2_KMIN, i = e & 15;
+    const double2 t = *reinterpret_cast<const double2*>(&mn_logf_table_c[i]);
+    MnLogfTab2 v;
+    v.invc_s = __dmul_rn(t.x, __hiloint2double((1023 - k) << 20, 0));  // exact: * 2^-k
+    v.y0 = __fma_rn((double)k, mn_kc[0], t.y);                           // the recipe's own y0
+    tab2[e] = v;
+  }
+}
+// x = float with bits ix lies in the table's range (a superset of the clipped domain [2^-23, 1 - 2^-23])
+__device__ __forceinline__ bool mn_logf2_covers(uint32_t ix) {
+  return (ix - MN_LOGF2_BIAS) < ((uint32_t)MN_LOGF2_N << 19);
+}
+// (the kernel keeps max(ix - BIAS) over a pixel's values and tests it once)
+// ix = bits of x, xd = (double)x; branch free; the result is meaningful iff mn_logf2_covers(ix)
+__device__ __forceinline__ float mn_logf_2d(uint32_t ix, double xd, const MnLogfTab2* tab2) {
+  const uint32_t off = ((ix - MN_LOGF2_BIAS) >> 15) & ((MN_LOGF2_PAD - 1) * 16);  // 16 * (k * 16 + i + 368)
+  const double2 e = *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(tab2) + off);
+  const double r = __fma_rn(xd, e.x, -1.0);  // = fma(z, invc, -1): z * invc == xd * (invc * 2^-k) exactly
+  const double r2 = __dmul_rn(r, r);
+  double y = __fma_rn(r, mn_kc[1], mn_kc[2]);
+  y = __fma_rn(r2, mn_kc[3], y);
+  y = __fma_rn(y, r2, __dadd_rn(e.y, r));
+  return (float)y;
+}
+// log(1 - xd) as mn_log1m_fast evaluates it, on an already widened argument, split in two so that the
+// rare exact decision stays out of the arithmetic: the fp64 value, and the test "its float rounding is
+// ambiguous" (low 29 bits within [-2^14, 2^14) of the rounding boundary 2^28; 6e-5 of all inputs)
+__device__ __forceinline__ double mn_log1m_y(double xd, const MnLog1mTab* tab) {
+  const double x = __dadd_rn(1.0, -xd);  // exact
+  const uint32_t hx = (uint32_t)__double2hiint(x);
+  const uint32_t tmp = hx - (uint32_t)(MN_LOG1M_OFF >> 32);
+  const uint32_t off = (tmp >> 9) & (127u * 16);
+  const int k = (int32_t)tmp >> 20;
+  const double z = __hiloint2double((int)(hx - (tmp & 0xfff00000u)), __double2loint(x));
+  const double2 e = *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(tab) + off);
+  const double r = __fma_rn(z, e.x, -1.0);
+  const double t = __fma_rn(mn_small_int_to_f64(k), mn_kc[0], e.y);
+  double q = __fma_rn(r, mn_kc[4], mn_kc[5]);
+  q = __fma_rn(r, q, mn_kc[6]);
+  q = __fma_rn(r, q, mn_kc[7]);
+  q = __fma_rn(r, q, mn_kc[8]);
+  const double r2 = __dmul_rn(r, r);
+  const double y = __fma_rn(r2, q, r);
+  return __dadd_rn(y, t);
+}
+__device__ __forceinline__ bool mn_log1m_ambiguous(double y) {
+  const uint32_t c = ((uint32_t)__double2loint(y) << 3) + ((0x4000u - 0x10000000u) << 3);
+  return c < (0x8000u << 3);
+}
+__device__ __noinline__ float mn_log1m_decide(double xd) { return (float)log(1.0 - xd); }
+__device__ __forceinline__ float mn_log1m_2(double xd, const MnLog1mTab* tab) {
+  const double y = mn_log1m_y(xd, tab);
+  return mn_log1m_ambiguous(y) ? mn_log1m_decide(xd) : (float)y;
+}
+
+#define MN_EDGE2_MAX_THREADS 288  // up to 8 consumer warps + the producer warp
+#define MN_EDGE2_STAGES 2
+struct MnEdge2Smem {
+  uint64_t full[MN_EDGE2_STAGES], empty[MN_EDGE2_STAGES];
+  uint64_t pad[12];
+  MnLogfTab2 tab2[MN_LOGF2_PAD];
+  MnLog1mTab tab1m[128];
+};
+
+// one pixel with the generic recipes (any positive normal input): unclipped callers only
+__device__ __noinline__ int mn_edge2_generic_lane(const float* in, int C, int K, int TP, float* my_clp, float* my_same,
+                                                  float* my_diff, const MnLogfTab* tab16, const MnLog1mTab* tab1m) {
+  float best = 0.0f;
+  int bc = 0;
+  for (int pl = 0; pl < C; pl++) {
+    const float l = MN_FADD(0.0f, mn_logf_fast(in[(size_t)pl * TP], tab16));
+    my_clp[pl] = l;
+    if (pl == 0 || l > best) { best = l; bc = pl; }
+  }
+  for (int k = 0; k < K; k++) {
+    const float v = in[(size_t)(C + k) * TP];
+    my_same[k] = mn_logf_fast(v, tab16);
+    my_diff[k] = mn_log1m_fast(v, tab1m);
+  }
+  return bc;
+}
+
+template <bool CLIP>
+__device__ __forceinline__ void mn_edge2_value(float v, uint32_t& ix, double& xd) {
+  if (CLIP) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
+  ix = __float_as_uint(v);
+  xd = mn_f32bits_to_f64(ix);
+}
+
+template <bool CLIP>
+__global__ void __launch_bounds__(MN_EDGE2_MAX_THREADS, 3) mn_edge_warp_kernel(MnEdgeParams P) {
+  __shared__ __align__(128) MnEdge2Smem S;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int C = P.C, K = P.K, TP = P.TP, NPL = C + K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncons = (int)(blockDim.x >> 5) - 1;  // TP == 32 * ncons
+  float* in_base = reinterpret_cast<float*>(smem_raw);
+  float* out_base = in_base + (size_t)MN_EDGE2_STAGES * NPL * TP;
+  const int OW = C + 2 * K;
+
+  mn_logf2_fill(S.tab2, tid, blockDim.x);
+  if (tid < 128) S.tab1m[tid] = mn_log1m_table[tid];
+  if (tid == 0) {
+    for (int s = 0; s < MN_EDGE2_STAGES; s++) {
+      mn_mbar_init(&S.full[s], 1);
+      mn_mbar_init(&S.empty[s], (uint32_t)ncons);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int total_tiles = P.B * P.tiles_per_image;
+  if (warp == ncons) {
+    // ---- producer ----
+    if (lane != 0) return;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+      const int stage = it % MN_EDGE2_STAGES;
+      if (it >= MN_EDGE2_STAGES) {
+        mn_mbar_wait(&S.empty[stage], (uint32_t)((it / MN_EDGE2_STAGES - 1) & 1));
+        mn_fence_proxy_async();
+      }
+      const int b = tile / P.tiles_per_image;
+      const int start = (tile % P.tiles_per_image) * TP;
+      const int tl = min(TP, P.N - start);
+      float* dst = in_base + (size_t)stage * NPL * TP;
+      const float* cbase = P.class_pred + ((size_t)b * C) * P.N + start;
+      const float* abase = P.adj_pred + ((size_t)b * K) * P.N + start;
+      mn_mbar_expect_tx(&S.full[stage], (uint32_t)(NPL * tl * 4));
+      for (int pl = 0; pl < C; pl++)
+        mn_tma_load_1d(dst + (size_t)pl * TP, cbase + (size_t)pl * P.N, tl * 4, &S.full[stage]);
+      for (int pl = 0; pl < K; pl++)
+        mn_tma_load_1d(dst + (size_t)(C + pl) * TP, abase + (size_t)pl * P.N, tl * 4, &S.full[stage]);
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const MnLogfTab2* tab2 = S.tab2;
+  const MnLog1mTab* tab1m = S.tab1m;
+  const MnLogfTab* tab16 = reinterpret_cast<const MnLogfTab*>(S.tab2 + MN_LOGF2_KMIN * 16);  // row k = 0
+  float* o_clp = out_base + (size_t)warp * 32 * OW;
+  float* o_same = o_clp + 32 * C;
+  float* o_diff = o_same + 32 * K;
+  float* my_clp = o_clp + lane * C;
+  float* my_same = o_same + lane * K;
+  float* my_diff = o_diff + lane * K;
+  const int px = warp * 32 + lane;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+    const int stage = it % MN_EDGE2_STAGES;
+    const int b = tile / P.tiles_per_image;
+    const int start = (tile % P.tiles_per_image) * TP;
+    const int tl = min(TP, P.N - start);
+    const int nvalid = min(32, max(0, tl - warp * 32));
+    const float* in = in_base + (size_t)stage * NPL * TP + px;
+    const MnImage& im = P.imgs[b];
+    mn_mbar_wait(&S.full[stage], (uint32_t)((it / MN_EDGE2_STAGES) & 1));
+    // this warp's previous bulk stores must have finished reading its staging buffer
+    if (lane == 0) mn_tma_store_wait_read();
+    __syncwarp();
+    int bc = 0;
+    if (lane < nvalid) {
+      // branch-free plane loops (independent values interleave); a value outside the logf table's
+      // range (only possible when the caller did not clip) raises `bad`, and the slice is redone
+      // with the generic recipes
+      uint32_t far = 0;  // max over the values of (bits - table bias): one test per pixel
+      float best = 0.0f;
+#pragma unroll 3
+      for (int pl = 0; pl < C; pl++) {  // Object ctor, cc:5-21  (0.0f + l == l: l is never -0)
+        uint32_t ix; double xd;
+        mn_edge2_value<CLIP>(in[(size_t)pl * TP], ix, xd);
+        if (!CLIP) far = max(far, ix - MN_LOGF2_BIAS);
+        const float l = mn_logf_2d(ix, xd, tab2);
+        my_clp[pl] = l;
+        if (pl == 0 || l > best) { best = l; bc = pl; }
+      }
+      const float* ina = in + (size_t)C * TP;
+      if ((K & 1) == 0) {
+        for (int k = 0; k < K; k += 2) {  // AdjacencyRecord ctor, cc:24-36; two offsets per step
+          uint32_t ix0, ix1; double xd0, xd1;
+          mn_edge2_value<CLIP>(ina[(size_t)k * TP], ix0, xd0);
+          mn_edge2_value<CLIP>(ina[(size_t)(k + 1) * TP], ix1, xd1);
+          if (!CLIP) far = max(far, max(ix0 - MN_LOGF2_BIAS, ix1 - MN_LOGF2_BIAS));
+          float2 sm, df;
+          sm.x = mn_logf_2d(ix0, xd0, tab2);
+          sm.y = mn_logf_2d(ix1, xd1, tab2);
+          const double y0 = mn_log1m_y(xd0, tab1m), y1 = mn_log1m_y(xd1, tab1m);
+          df.x = (float)y0;
+          df.y = (float)y1;
+          const bool a0 = mn_log1m_ambiguous(y0), a1 = mn_log1m_ambiguous(y1);
+          if (a0 | a1) {  // rare: the full-precision log decides (cc:34)
+            if (a0) df.x = mn_log1m_decide(xd0);
+            if (a1) df.y = mn_log1m_decide(xd1);
+          }
+          *reinterpret_cast<float2*>(my_same + k) = sm;  // 8-byte stores at a stride of K words: conflict free
+          *reinterpret_cast<float2*>(my_diff + k) = df;
+        }
+      } else {
+        for (int k = 0; k < K; k++) {
+          uint32_t ix; double xd;
+          mn_edge2_value<CLIP>(ina[(size_t)k * TP], ix, xd);
+          if (!CLIP) far = max(far, ix - MN_LOGF2_BIAS);
+          my_same[k] = mn_logf_2d(ix, xd, tab2);
+          my_diff[k] = mn_log1m_2(xd, tab1m);
+        }
+      }
+      const bool bad = far >= ((uint32_t)MN_LOGF2_N << 19);
+      if (!CLIP && bad) bc = mn_edge2_generic_lane(in, C, K, TP, my_clp, my_same, my_diff, tab16, tab1m);
+    }
+    mn_fence_proxy_async();  // staged results -> visible to the bulk-store engine
+    __syncwarp();
+    if (lane == 0) {
+      // hand the input stage back to the producer, then send this warp's slice off
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mn_smem_u32(&S.empty[stage])) : "memory");
+      if (nvalid > 0) {
+        const size_t p0 = (size_t)start + (size_t)warp * 32;
+        mn_tma_store_1d(im.clp + p0 * C, o_clp, (uint32_t)(nvalid * C * 4));
+        mn_tma_store_1d(im.rec_same + p0 * K, o_same, (uint32_t)(nvalid * K * 4));
+        mn_tma_store_1d(im.rec_diff + p0 * K, o_diff, (uint32_t)(nvalid * K * 4));
+        mn_tma_store_commit();
+      }
+    }
+    if (lane < nvalid) im.cls[start + px] = bc;
+  }
+  if (lane == 0) mn_tma_store_wait_read();
 }
 
 // ---------------------------------------------------------------------------------------------

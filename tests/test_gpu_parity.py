@@ -53,6 +53,29 @@ def test_edge_pass_bitwise_equals_reference_constructor(oracle_mod, lib_mod, opt
             assert np.array_equal(_bits(ref["adj_pred"]), _bits(got["adj"])), name
 
 
+def test_edge_kernels_agree_bitwise_incl_unclipped_input(lib_mod, monkeypatch):
+    """The warp-pipeline edge kernel (fast path) and the tile kernel (general path) must produce the
+    same bits, also when the caller did not clip (values below 2^-23 / equal to 1 - 2^-24 leave the
+    (k, i) table and take the generic recipe) and on a ragged last tile."""
+    rng = np.random.default_rng(5)
+    for (h, w) in ((64, 100), (37, 64)):
+        name, cp, sp, C, offs = ("x", ) + cases.cityscapes_like(h, w, 21, True)
+        cp = cp.copy(); sp = sp.copy()
+        for arr in (cp, sp):
+            flat = arr.reshape(-1)
+            idx = rng.choice(flat.size, flat.size // 50, replace=False)
+            flat[idx[0::3]] = np.float32(1e-12)
+            flat[idx[1::3]] = np.float32(3.0e-8)
+            flat[idx[2::3]] = np.nextafter(np.float32(1.0), np.float32(0.0))
+        monkeypatch.setenv("MN_EDGE2_NCONS", "0")
+        a = _edge_dump(lib_mod, cp, sp, C, offs, cases.PLAIN_OPTS)
+        monkeypatch.delenv("MN_EDGE2_NCONS")
+        b = _edge_dump(lib_mod, cp, sp, C, offs, cases.PLAIN_OPTS)
+        for k in ("clp", "same", "diff", "oml", "mp"):
+            assert np.array_equal(_bits(a[k]), _bits(b[k])), (h, w, k)
+        assert np.array_equal(a["cls"], b["cls"])
+
+
 @pytest.mark.parametrize("opts", [cases.RECIPE_OPTS, cases.PLAIN_OPTS, cases.QUARTER_OPTS])
 def test_drop_in_c_abi_matches_oracle_small(oracle_mod, lib_mod, opts):
     from mergenet_b200 import c_segment

@@ -66,6 +66,16 @@ def test_device_log1m_equals_host_exhaustive(oracle_mod, lib_mod):
 
 
 @pytest.mark.gpu
+def test_device_warp_pipeline_logs_equal_host_exhaustive(oracle_mod, lib_mod):
+    """The (k, i)-table logf and the split log1m of mn_edge_warp_kernel, whole clipped domain."""
+    L = oracle_mod.oracle_lib()
+    bad, first = _device_vs_host(oracle_mod, lib_mod, 5, L.mno_host_logf_table)
+    assert bad == 0, first[:5]
+    bad, first = _device_vs_host(oracle_mod, lib_mod, 6, L.mno_host_log1m_table)
+    assert bad == 0, first[:5]
+
+
+@pytest.mark.gpu
 def test_device_unfused_recipes_equal_host_sampled(oracle_mod, lib_mod):
     """The unfused logf recipe and the plain fp64 log (used by the same_different_bias path)."""
     L = oracle_mod.oracle_lib()
