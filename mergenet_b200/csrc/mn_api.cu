@@ -163,8 +163,10 @@ __global__ void __launch_bounds__(256) mn_logprob_kernel(const MnImage* imgs, in
 __global__ void mn_libm_kernel(int which, uint32_t first_bits, uint32_t n, float bias, float* out) {
   __shared__ MnLogfTab tab[16];
   __shared__ MnLog1mTab tab1m[128];
-  __shared__ MnLogfTab2 tab2[MN_LOGF2_PAD];
-  mn_logf2_fill(tab2, threadIdx.x, blockDim.x);
+  __shared__ double2 tabf_il[16 * 8], tab1m_il[64 * 8];  // the interleaved tables of mn_edge_warp_kernel
+  for (int e = threadIdx.x; e < 16 * 8; e += blockDim.x) tabf_il[e] = make_double2(mn_logf_table_c[e >> 3].invc, mn_logf_table_c[e >> 3].logc);
+  for (int e = threadIdx.x; e < 64 * 8; e += blockDim.x) tab1m_il[e] = make_double2(mn_log1m64_table[e >> 3].invc, mn_log1m64_table[e >> 3].logc);
+  const uint32_t lane16 = (threadIdx.x & 7) * 16u;
   if (threadIdx.x < 16) {
     const MnLogfTab t16[16] = {MN_LOGF_TABLE};
     tab[threadIdx.x] = t16[threadIdx.x];
@@ -178,8 +180,11 @@ __global__ void mn_libm_kernel(int which, uint32_t first_bits, uint32_t n, float
     else if (which == 1) r = mn_log1m_fast(x, tab1m);
     else if (which == 3) r = mn_logf_exact(x, tab);      // the unfused recipe (bias path)
     else if (which == 4) r = mn_log1m_exact(x);
-    else if (which == 5) r = mn_logf_2d(__float_as_uint(x), mn_f32bits_to_f64(__float_as_uint(x)), tab2);  // warp-pipeline kernel
-    else if (which == 6) r = mn_log1m_2(mn_f32bits_to_f64(__float_as_uint(x)), tab1m);
+    else if (which == 5) r = mn_logf_il(__float_as_uint(x), __float_as_uint(x) << 29, tabf_il, lane16);  // warp-pipeline kernel
+    else if (which == 6) {
+      const double y = mn_log1m_il(mn_f32bits_to_f64(__float_as_uint(x)), tab1m_il, lane16);
+      r = mn_log1m_ambiguous(y) ? mn_log1m_decide(x) : (float)y;
+    }
     else r = mn_bias_sameness(x, bias, tab);
     out[i] = r;
   }
@@ -206,7 +211,7 @@ struct mn_plan {
   cudaEvent_t ev[9];
   int num_sms;
   int edge_tp, edge_smem, merge_smem, merge_H;
-  int edge2_ncons, edge2_ctas, edge2_smem;  // warp-pipeline edge kernel: consumer warps per CTA (0: not usable), CTAs per SM
+  int edge2_ncons, edge2_ctas, edge2_smem, edge2_stages;  // warp-pipeline edge kernel: consumer warps per CTA (0: not usable), CTAs per SM
   std::vector<MnCtl> h_ctl;
   double* d_logprob;            // [max_batch][4] class / sameness / differentness terms
   std::vector<double> h_logprob;
@@ -275,11 +280,14 @@ static int choose_edge_tile(int C, int K, int* smem_bytes) {
 
 // warp-pipeline edge kernel: consumer warps per CTA and CTAs per SM that maximise the resident consumer
 // warps; 0 when the shape leaves too few (many classes: the tile kernel's smaller tiles win)
-static int choose_edge2(int C, int K, int* ctas_out, int* smem_bytes) {
-  const size_t per_warp = 128 * ((size_t)MN_EDGE2_STAGES * (C + K) + (size_t)(C + 2 * K));
+static int choose_edge2(int C, int K, int* ctas_out, int* smem_bytes, int* stages_out) {
+  int stages = 2;
+  if (const char* e = getenv("MN_EDGE2_STAGES")) { int v = atoi(e); if (v >= 2 && v <= MN_EDGE2_MAX_STAGES) stages = v; }
+  *stages_out = stages;
+  const size_t per_warp = 128 * ((size_t)stages * (C + K) + (size_t)(C + 2 * K));
   const size_t fixed = sizeof(MnEdge2Smem) + 1024 + 256;  // static tables + per-CTA reservation
   int best = 0, best_score = 0, best_ctas = 0;
-  for (int nc = 8; nc >= 1; nc--) {
+  for (int nc = MN_EDGE2_MAX_THREADS / 32 - 1; nc >= 1; nc--) {
     size_t per_cta = per_warp * nc + fixed;
     int ctas = (int)std::min<size_t>((size_t)(227 * 1024) / per_cta, 2048 / (32 * (nc + 1)));
     ctas = std::min(ctas, 65536 / (80 * 32 * (nc + 1)));  // register file at <= 80 registers per thread
@@ -289,7 +297,7 @@ static int choose_edge2(int C, int K, int* ctas_out, int* smem_bytes) {
     int nc = 0, ct = 0;
     int got = sscanf(e, "%d,%d", &nc, &ct);
     if (got >= 1 && nc == 0) return 0;
-    if (got == 2 && nc >= 1 && nc <= 8 && ct >= 1) { best = nc; best_ctas = ct; best_score = 99; }
+    if (got == 2 && nc >= 1 && nc <= MN_EDGE2_MAX_THREADS / 32 - 1 && ct >= 1) { best = nc; best_ctas = ct; best_score = 99; }
   }
   if (best_score < 12) return 0;
   *ctas_out = best_ctas;
@@ -406,7 +414,7 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
     p->merge_smem = (int)(base + (size_t)Hwin * 3 * C * 4);
     if ((size_t)p->merge_smem > limit) return fail(MN_STATUS_BAD_ARG);
   }
-  p->edge2_ncons = choose_edge2(C, K, &p->edge2_ctas, &p->edge2_smem);
+  p->edge2_ncons = choose_edge2(C, K, &p->edge2_ctas, &p->edge2_smem, &p->edge2_stages);
   if (p->edge2_ncons &&
       (cudaFuncSetAttribute(mn_edge_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->edge2_smem) != cudaSuccess ||
        cudaFuncSetAttribute(mn_edge_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->edge2_smem) != cudaSuccess))
@@ -432,6 +440,9 @@ static int launch_edge(mn_plan* p, int B, const float* d_class, float* d_adj, in
   const bool warp_pipeline = p->edge2_ncons > 0 && P.use_tma && sdb == 0.0f;
   if (warp_pipeline) {
     P.TP = 32 * p->edge2_ncons;
+    P.stages = p->edge2_stages;
+    P.ws0_clp = p->h_imgs[0].clp; P.ws0_same = p->h_imgs[0].rec_same; P.ws0_diff = p->h_imgs[0].rec_diff; P.ws0_cls = p->h_imgs[0].cls;
+    P.ws_stride = p->per_image_bytes;
     P.tiles_per_image = (N + P.TP - 1) / P.TP;
   }
   long long tiles = (long long)B * P.tiles_per_image;

@@ -192,6 +192,11 @@ struct MnEdgeParams {
   int use_tma;              // N % 4 == 0 and 16-byte aligned bases
   int clip;                 // apply the wrapper's clip to [2^-23, 1-2^-23] (c_segment.pyx:53-55)
   float sdb;
+  // warp-pipeline kernel: image b's outputs live at ws0_* + b * ws_stride (no pointer loads per tile)
+  float *ws0_clp, *ws0_same, *ws0_diff;
+  int* ws0_cls;
+  size_t ws_stride;  // bytes
+  int stages;        // input ring depth (2..4)
 };
 
 // dynamic smem layout: [bar0, bar1][pad to 128][in0][in1][out0: clp|same|diff][out1][logf tab][log1m tab]
@@ -401,56 +406,51 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_
 //     (plane-major smem reads: conflict free), keeps the first-argmax in registers, stages its
 //     (C+2K)*32 results in its OWN buffer and sends them off with its own three bulk stores -- a
 //     warp never waits for another warp, only for data;
-//   * logf takes ONE 16-byte table entry {invc[i]*2^-k, fma(k, Ln2, logc[i])} indexed by the top
-//     mantissa/exponent bits (k in [-23, 0] on the clipped domain: 384 entries): the exponent
-//     scaling of z and the k*Ln2 term are exact functions of (k, i), so the result is the same bits
-//     as glibc's recipe with 6 fp64 operations, one conversion and 3 integer
-//     operations per value.  Inputs outside the clipped domain (possible only when the caller did
-//     not clip, c_segment.pyx:53-55) take the generic recipe.
-struct MnLogfTab2 {
-  double invc_s, y0;
+//   * the kernel is bound by the shared-memory data pipe once the barriers are gone: a 16-byte table
+//     lookup with 32 unrelated indices costs ~9.3 wavefronts instead of 4.  Both tables are therefore
+//     kept as EIGHT bank-interleaved copies (entry i, copy j at 16-byte slot 8 i + j; lane l reads copy
+//     l & 7): the 8 lanes of every quarter-warp phase hit 8 different bank groups whatever their
+//     indices -- exactly 4 wavefronts per lookup.  That caps the table sizes: logf keeps glibc's own
+//     16 entries (2 KB), log(1 - s) uses a 64-bin table (8 KB) with the same degree-6 polynomial
+//     (tools/check_log1m64.c: 0 differences outside the fallback set over the whole clipped domain);
+//   * the rare exact decision of log(1 - s) (6e-5 of the values) is deferred to after the plane loops,
+//     so the loops carry no call and their constants stay in registers.
+struct MnEdge2Smem {
+  uint64_t full[4], empty[4];
+  uint64_t pad[8];
+  double2 tabf[16 * 8];    // (invc, logc) of logf, 8 interleaved copies
+  double2 tab1m[64 * 8];   // (invc, logc) of the 64-bin log(1 - s), 8 interleaved copies
 };
-#define MN_LOGF2_KMIN 23
-#define MN_LOGF2_N ((MN_LOGF2_KMIN + 1) * 16)  // rows k = -23 .. 0: x in [0.7 * 2^-23, 1.4)
-#define MN_LOGF2_PAD 512                       // table padded to a power of two: a masked index never leaves it
-#define MN_LOGF2_BIAS (0x3f330000u - ((uint32_t)(MN_LOGF2_KMIN * 16) << 19))
-__device__ __forceinline__ void mn_logf2_fill(MnLogfTab2* tab2, int tid, int nt) {
-  for (int e = tid; e < MN_LOGF2_PAD; e += nt) {
-    const int k = (e >> 4) - MN_LOGF2_KMIN, i = e & 15;
-    const double2 t = *reinterpret_cast<const double2*>(&mn_logf_table_c[i]);
-    MnLogfTab2 v;
-    v.invc_s = __dmul_rn(t.x, __hiloint2double((1023 - k) << 20, 0));  // exact: * 2^-k
-    v.y0 = __fma_rn((double)k, mn_kc[0], t.y);                           // the recipe's own y0
-    tab2[e] = v;
-  }
-}
-// x = float with bits ix lies in the table's range (a superset of the clipped domain [2^-23, 1 - 2^-23])
-__device__ __forceinline__ bool mn_logf2_covers(uint32_t ix) {
-  return (ix - MN_LOGF2_BIAS) < ((uint32_t)MN_LOGF2_N << 19);
-}
-// (the kernel keeps max(ix - BIAS) over a pixel's values and tests it once)
-// ix = bits of x, xd = (double)x; branch free; the result is meaningful iff mn_logf2_covers(ix)
-__device__ __forceinline__ float mn_logf_2d(uint32_t ix, double xd, const MnLogfTab2* tab2) {
-  const uint32_t off = ((ix - MN_LOGF2_BIAS) >> 15) & ((MN_LOGF2_PAD - 1) * 16);  // 16 * (k * 16 + i + 368)
-  const double2 e = *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(tab2) + off);
-  const double r = __fma_rn(xd, e.x, -1.0);  // = fma(z, invc, -1): z * invc == xd * (invc * 2^-k) exactly
+#define MN_EDGE2_MAX_STAGES 4
+#define MN_EDGE2_MAX_THREADS 256  // up to 7 consumer warps + the producer warp
+__constant__ MnLog1mTab mn_log1m64_table[64] = {MN_LOG1M64_TABLE};
+
+// glibc's logf recipe (the arithmetic of mn_logf_fast) on an interleaved table; lane16 = (lane & 7) * 16.
+// `lo29` = bits << 29 (the low word of the widened value: shared with the log(1 - s) of the same value)
+__device__ __forceinline__ float mn_logf_il(uint32_t ix, uint32_t lo29, const double2* tabf, uint32_t lane16) {
+  const uint32_t tmp = ix - 0x3f330000u;
+  const uint32_t off = ((tmp >> 12) & (15u << 7)) | lane16;
+  const int k = (int32_t)tmp >> 23;
+  const uint32_t iz = ix - (tmp & 0xff800000u);
+  const double z = __hiloint2double((int)((iz >> 3) + 0x38000000u), (int)lo29);
+  const double2 e = *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(tabf) + off);
+  const double r = __fma_rn(z, e.x, -1.0);
+  const double y0 = __fma_rn(mn_small_int_to_f64(k), mn_kc[0], e.y);
   const double r2 = __dmul_rn(r, r);
   double y = __fma_rn(r, mn_kc[1], mn_kc[2]);
   y = __fma_rn(r2, mn_kc[3], y);
-  y = __fma_rn(y, r2, __dadd_rn(e.y, r));
+  y = __fma_rn(y, r2, __dadd_rn(y0, r));
   return (float)y;
 }
-// log(1 - xd) as mn_log1m_fast evaluates it, on an already widened argument, split in two so that the
-// rare exact decision stays out of the arithmetic: the fp64 value, and the test "its float rounding is
-// ambiguous" (low 29 bits within [-2^14, 2^14) of the rounding boundary 2^28; 6e-5 of all inputs)
-__device__ __forceinline__ double mn_log1m_y(double xd, const MnLog1mTab* tab) {
+// log(1 - xd) in fp64 (64-bin interleaved table); the caller tests mn_log1m_ambiguous(y)
+__device__ __forceinline__ double mn_log1m_il(double xd, const double2* tab1m, uint32_t lane16) {
   const double x = __dadd_rn(1.0, -xd);  // exact
   const uint32_t hx = (uint32_t)__double2hiint(x);
-  const uint32_t tmp = hx - (uint32_t)(MN_LOG1M_OFF >> 32);
-  const uint32_t off = (tmp >> 9) & (127u * 16);
+  const uint32_t tmp = hx - (uint32_t)(MN_LOG1M64_OFF >> 32);
+  const uint32_t off = ((tmp >> 7) & (63u << 7)) | lane16;
   const int k = (int32_t)tmp >> 20;
   const double z = __hiloint2double((int)(hx - (tmp & 0xfff00000u)), __double2loint(x));
-  const double2 e = *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(tab) + off);
+  const double2 e = *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(tab1m) + off);
   const double r = __fma_rn(z, e.x, -1.0);
   const double t = __fma_rn(mn_small_int_to_f64(k), mn_kc[0], e.y);
   double q = __fma_rn(r, mn_kc[4], mn_kc[5]);
@@ -461,48 +461,16 @@ __device__ __forceinline__ double mn_log1m_y(double xd, const MnLog1mTab* tab) {
   const double y = __fma_rn(r2, q, r);
   return __dadd_rn(y, t);
 }
+// the float rounding of y is ambiguous: low 29 bits within [-2^14, 2^14) of the rounding boundary 2^28
 __device__ __forceinline__ bool mn_log1m_ambiguous(double y) {
   const uint32_t c = ((uint32_t)__double2loint(y) << 3) + ((0x4000u - 0x10000000u) << 3);
   return c < (0x8000u << 3);
 }
-__device__ __noinline__ float mn_log1m_decide(double xd) { return (float)log(1.0 - xd); }
-__device__ __forceinline__ float mn_log1m_2(double xd, const MnLog1mTab* tab) {
-  const double y = mn_log1m_y(xd, tab);
-  return mn_log1m_ambiguous(y) ? mn_log1m_decide(xd) : (float)y;
-}
-
-#define MN_EDGE2_MAX_THREADS 288  // up to 8 consumer warps + the producer warp
-#define MN_EDGE2_STAGES 2
-struct MnEdge2Smem {
-  uint64_t full[MN_EDGE2_STAGES], empty[MN_EDGE2_STAGES];
-  uint64_t pad[12];
-  MnLogfTab2 tab2[MN_LOGF2_PAD];
-  MnLog1mTab tab1m[128];
-};
-
-// one pixel with the generic recipes (any positive normal input): unclipped callers only
-__device__ __noinline__ int mn_edge2_generic_lane(const float* in, int C, int K, int TP, float* my_clp, float* my_same,
-                                                  float* my_diff, const MnLogfTab* tab16, const MnLog1mTab* tab1m) {
-  float best = 0.0f;
-  int bc = 0;
-  for (int pl = 0; pl < C; pl++) {
-    const float l = MN_FADD(0.0f, mn_logf_fast(in[(size_t)pl * TP], tab16));
-    my_clp[pl] = l;
-    if (pl == 0 || l > best) { best = l; bc = pl; }
-  }
-  for (int k = 0; k < K; k++) {
-    const float v = in[(size_t)(C + k) * TP];
-    my_same[k] = mn_logf_fast(v, tab16);
-    my_diff[k] = mn_log1m_fast(v, tab1m);
-  }
-  return bc;
-}
+__device__ __noinline__ float mn_log1m_decide(float s) { return (float)log(1.0 - (double)s); }
 
 template <bool CLIP>
-__device__ __forceinline__ void mn_edge2_value(float v, uint32_t& ix, double& xd) {
-  if (CLIP) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
-  ix = __float_as_uint(v);
-  xd = mn_f32bits_to_f64(ix);
+__device__ __forceinline__ float mn_edge2_clip(float v) {
+  return CLIP ? fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f) : v;
 }
 
 template <bool CLIP>
@@ -513,13 +481,20 @@ __global__ void __launch_bounds__(MN_EDGE2_MAX_THREADS, 3) mn_edge_warp_kernel(M
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncons = (int)(blockDim.x >> 5) - 1;  // TP == 32 * ncons
   float* in_base = reinterpret_cast<float*>(smem_raw);
-  float* out_base = in_base + (size_t)MN_EDGE2_STAGES * NPL * TP;
+  const int NS = P.stages;
+  float* out_base = in_base + (size_t)NS * NPL * TP;
   const int OW = C + 2 * K;
 
-  mn_logf2_fill(S.tab2, tid, blockDim.x);
-  if (tid < 128) S.tab1m[tid] = mn_log1m_table[tid];
+  for (int e = tid; e < 16 * 8; e += blockDim.x) {
+    const MnLogfTab t = mn_logf_table_c[e >> 3];
+    S.tabf[e] = make_double2(t.invc, t.logc);
+  }
+  for (int e = tid; e < 64 * 8; e += blockDim.x) {
+    const MnLog1mTab t = mn_log1m64_table[e >> 3];
+    S.tab1m[e] = make_double2(t.invc, t.logc);
+  }
   if (tid == 0) {
-    for (int s = 0; s < MN_EDGE2_STAGES; s++) {
+    for (int s = 0; s < NS; s++) {
       mn_mbar_init(&S.full[s], 1);
       mn_mbar_init(&S.empty[s], (uint32_t)ncons);
     }
@@ -527,19 +502,20 @@ __global__ void __launch_bounds__(MN_EDGE2_MAX_THREADS, 3) mn_edge_warp_kernel(M
   }
   __syncthreads();
 
-  const int total_tiles = P.B * P.tiles_per_image;
+  // tiles blockIdx.x, blockIdx.x + gridDim.x, ...: (image, tile in image) advance without divisions
+  const int tpi = P.tiles_per_image;
+  const int step_b = (int)gridDim.x / tpi, step_t = (int)gridDim.x % tpi;
+  int b = (int)blockIdx.x / tpi, t = (int)blockIdx.x % tpi;
   if (warp == ncons) {
     // ---- producer ----
     if (lane != 0) return;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
-      const int stage = it % MN_EDGE2_STAGES;
-      if (it >= MN_EDGE2_STAGES) {
-        mn_mbar_wait(&S.empty[stage], (uint32_t)((it / MN_EDGE2_STAGES - 1) & 1));
+    int stage = 0, lap = 0;  // lap = number of completed passes over the ring
+    for (; b < P.B;) {
+      if (lap > 0) {
+        mn_mbar_wait(&S.empty[stage], (uint32_t)((lap - 1) & 1));
         mn_fence_proxy_async();
       }
-      const int b = tile / P.tiles_per_image;
-      const int start = (tile % P.tiles_per_image) * TP;
+      const int start = t * TP;
       const int tl = min(TP, P.N - start);
       float* dst = in_base + (size_t)stage * NPL * TP;
       const float* cbase = P.class_pred + ((size_t)b * C) * P.N + start;
@@ -549,82 +525,112 @@ __global__ void __launch_bounds__(MN_EDGE2_MAX_THREADS, 3) mn_edge_warp_kernel(M
         mn_tma_load_1d(dst + (size_t)pl * TP, cbase + (size_t)pl * P.N, tl * 4, &S.full[stage]);
       for (int pl = 0; pl < K; pl++)
         mn_tma_load_1d(dst + (size_t)(C + pl) * TP, abase + (size_t)pl * P.N, tl * 4, &S.full[stage]);
+      b += step_b; t += step_t;
+      if (t >= tpi) { t -= tpi; b++; }
+      if (++stage == NS) { stage = 0; lap++; }
     }
     return;
   }
 
   // ---- consumers ----
-  const MnLogfTab2* tab2 = S.tab2;
-  const MnLog1mTab* tab1m = S.tab1m;
-  const MnLogfTab* tab16 = reinterpret_cast<const MnLogfTab*>(S.tab2 + MN_LOGF2_KMIN * 16);  // row k = 0
+  const double2* tabf = S.tabf;
+  const double2* tab1m = S.tab1m;
+  const uint32_t lane16 = (uint32_t)(lane & 7) * 16u;
   float* o_clp = out_base + (size_t)warp * 32 * OW;
   float* o_same = o_clp + 32 * C;
   float* o_diff = o_same + 32 * K;
-  float* my_clp = o_clp + lane * C;
-  float* my_same = o_same + lane * K;
-  float* my_diff = o_diff + lane * K;
+  float* __restrict__ my_clp = o_clp + lane * C;
+  float* __restrict__ my_same = o_same + lane * K;
+  float* __restrict__ my_diff = o_diff + lane * K;
   const int px = warp * 32 + lane;
-  int it = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
-    const int stage = it % MN_EDGE2_STAGES;
-    const int b = tile / P.tiles_per_image;
-    const int start = (tile % P.tiles_per_image) * TP;
-    const int tl = min(TP, P.N - start);
-    const int nvalid = min(32, max(0, tl - warp * 32));
-    const float* in = in_base + (size_t)stage * NPL * TP + px;
-    const MnImage& im = P.imgs[b];
-    mn_mbar_wait(&S.full[stage], (uint32_t)((it / MN_EDGE2_STAGES) & 1));
+  int stage = 0;
+  uint32_t parity = 0;
+  for (; b < P.B;) {
+    const int start = t * TP;
+    const int nvalid = min(32, P.N - start - warp * 32);  // (<= 0: this warp's slice lies beyond the image)
+    const float* __restrict__ in = in_base + (size_t)stage * NPL * TP + px;
+    const size_t wsb = (size_t)b * P.ws_stride;
+    float* g_clp = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(P.ws0_clp) + wsb);
+    float* g_same = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(P.ws0_same) + wsb);
+    float* g_diff = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(P.ws0_diff) + wsb);
+    int* g_cls = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(P.ws0_cls) + wsb);
+    mn_mbar_wait(&S.full[stage], parity);
     // this warp's previous bulk stores must have finished reading its staging buffer
     if (lane == 0) mn_tma_store_wait_read();
     __syncwarp();
     int bc = 0;
     if (lane < nvalid) {
-      // branch-free plane loops (independent values interleave); a value outside the logf table's
-      // range (only possible when the caller did not clip) raises `bad`, and the slice is redone
-      // with the generic recipes
-      uint32_t far = 0;  // max over the values of (bits - table bias): one test per pixel
+      // Independent values are loaded first and evaluated side by side: a warp's issue rate is set by
+      // the dependent fp64 chain of one value (few resident warps), so three / four chains interleave.
       float best = 0.0f;
-#pragma unroll 3
-      for (int pl = 0; pl < C; pl++) {  // Object ctor, cc:5-21  (0.0f + l == l: l is never -0)
-        uint32_t ix; double xd;
-        mn_edge2_value<CLIP>(in[(size_t)pl * TP], ix, xd);
-        if (!CLIP) far = max(far, ix - MN_LOGF2_BIAS);
-        const float l = mn_logf_2d(ix, xd, tab2);
+      int pl = 0;
+      for (; pl + 3 <= C; pl += 3) {  // Object ctor, cc:5-21  (0.0f + l == l: l is never -0)
+        const float v0 = mn_edge2_clip<CLIP>(in[(size_t)pl * TP]);
+        const float v1 = mn_edge2_clip<CLIP>(in[(size_t)(pl + 1) * TP]);
+        const float v2 = mn_edge2_clip<CLIP>(in[(size_t)(pl + 2) * TP]);
+        const uint32_t i0 = __float_as_uint(v0), i1 = __float_as_uint(v1), i2 = __float_as_uint(v2);
+        const float l0 = mn_logf_il(i0, i0 << 29, tabf, lane16);
+        const float l1 = mn_logf_il(i1, i1 << 29, tabf, lane16);
+        const float l2 = mn_logf_il(i2, i2 << 29, tabf, lane16);
+        my_clp[pl] = l0; my_clp[pl + 1] = l1; my_clp[pl + 2] = l2;
+        if (pl == 0 || l0 > best) { best = l0; bc = pl; }
+        if (l1 > best) { best = l1; bc = pl + 1; }
+        if (l2 > best) { best = l2; bc = pl + 2; }
+      }
+      for (; pl < C; pl++) {
+        const uint32_t ix = __float_as_uint(mn_edge2_clip<CLIP>(in[(size_t)pl * TP]));
+        const float l = mn_logf_il(ix, ix << 29, tabf, lane16);
         my_clp[pl] = l;
         if (pl == 0 || l > best) { best = l; bc = pl; }
       }
-      const float* ina = in + (size_t)C * TP;
+      const float* __restrict__ ina = in + (size_t)C * TP;
+      uint32_t amb = 0;  // offsets whose log(1 - s) needs the exact decision
+      int k = 0;
       if ((K & 1) == 0) {
-        for (int k = 0; k < K; k += 2) {  // AdjacencyRecord ctor, cc:24-36; two offsets per step
-          uint32_t ix0, ix1; double xd0, xd1;
-          mn_edge2_value<CLIP>(ina[(size_t)k * TP], ix0, xd0);
-          mn_edge2_value<CLIP>(ina[(size_t)(k + 1) * TP], ix1, xd1);
-          if (!CLIP) far = max(far, max(ix0 - MN_LOGF2_BIAS, ix1 - MN_LOGF2_BIAS));
-          float2 sm, df;
-          sm.x = mn_logf_2d(ix0, xd0, tab2);
-          sm.y = mn_logf_2d(ix1, xd1, tab2);
-          const double y0 = mn_log1m_y(xd0, tab1m), y1 = mn_log1m_y(xd1, tab1m);
-          df.x = (float)y0;
-          df.y = (float)y1;
-          const bool a0 = mn_log1m_ambiguous(y0), a1 = mn_log1m_ambiguous(y1);
-          if (a0 | a1) {  // rare: the full-precision log decides (cc:34)
-            if (a0) df.x = mn_log1m_decide(xd0);
-            if (a1) df.y = mn_log1m_decide(xd1);
-          }
-          *reinterpret_cast<float2*>(my_same + k) = sm;  // 8-byte stores at a stride of K words: conflict free
-          *reinterpret_cast<float2*>(my_diff + k) = df;
+        for (; k + 4 <= K; k += 4) {  // AdjacencyRecord ctor, cc:24-36; four offsets per step
+          uint32_t ix[4]; double xd[4], y[4]; float sm[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) ix[u] = __float_as_uint(mn_edge2_clip<CLIP>(ina[(size_t)(k + u) * TP]));
+#pragma unroll
+          for (int u = 0; u < 4; u++) xd[u] = mn_f32bits_to_f64(ix[u]);
+#pragma unroll
+          for (int u = 0; u < 4; u++) sm[u] = mn_logf_il(ix[u], (uint32_t)__double2loint(xd[u]), tabf, lane16);
+#pragma unroll
+          for (int u = 0; u < 4; u++) y[u] = mn_log1m_il(xd[u], tab1m, lane16);
+#pragma unroll
+          for (int u = 0; u < 4; u++) amb |= (mn_log1m_ambiguous(y[u]) ? 1u : 0u) << (k + u);
+          // 8-byte stores at a stride of K words: conflict free
+          *reinterpret_cast<float2*>(my_same + k) = make_float2(sm[0], sm[1]);
+          *reinterpret_cast<float2*>(my_same + k + 2) = make_float2(sm[2], sm[3]);
+          *reinterpret_cast<float2*>(my_diff + k) = make_float2((float)y[0], (float)y[1]);
+          *reinterpret_cast<float2*>(my_diff + k + 2) = make_float2((float)y[2], (float)y[3]);
+        }
+        for (; k < K; k += 2) {
+          const uint32_t ix0 = __float_as_uint(mn_edge2_clip<CLIP>(ina[(size_t)k * TP]));
+          const uint32_t ix1 = __float_as_uint(mn_edge2_clip<CLIP>(ina[(size_t)(k + 1) * TP]));
+          const double xd0 = mn_f32bits_to_f64(ix0), xd1 = mn_f32bits_to_f64(ix1);
+          const float s0 = mn_logf_il(ix0, (uint32_t)__double2loint(xd0), tabf, lane16);
+          const float s1 = mn_logf_il(ix1, (uint32_t)__double2loint(xd1), tabf, lane16);
+          const double y0 = mn_log1m_il(xd0, tab1m, lane16), y1 = mn_log1m_il(xd1, tab1m, lane16);
+          amb |= ((mn_log1m_ambiguous(y0) ? 1u : 0u) | (mn_log1m_ambiguous(y1) ? 2u : 0u)) << k;
+          *reinterpret_cast<float2*>(my_same + k) = make_float2(s0, s1);
+          *reinterpret_cast<float2*>(my_diff + k) = make_float2((float)y0, (float)y1);
         }
       } else {
-        for (int k = 0; k < K; k++) {
-          uint32_t ix; double xd;
-          mn_edge2_value<CLIP>(ina[(size_t)k * TP], ix, xd);
-          if (!CLIP) far = max(far, ix - MN_LOGF2_BIAS);
-          my_same[k] = mn_logf_2d(ix, xd, tab2);
-          my_diff[k] = mn_log1m_2(xd, tab1m);
+        for (; k < K; k++) {
+          const uint32_t ix = __float_as_uint(mn_edge2_clip<CLIP>(ina[(size_t)k * TP]));
+          const double xd = mn_f32bits_to_f64(ix);
+          my_same[k] = mn_logf_il(ix, (uint32_t)__double2loint(xd), tabf, lane16);
+          const double y = mn_log1m_il(xd, tab1m, lane16);
+          my_diff[k] = (float)y;
+          amb |= (mn_log1m_ambiguous(y) ? 1u : 0u) << k;
         }
       }
-      const bool bad = far >= ((uint32_t)MN_LOGF2_N << 19);
-      if (!CLIP && bad) bc = mn_edge2_generic_lane(in, C, K, TP, my_clp, my_same, my_diff, tab16, tab1m);
+      while (amb) {  // rare: the full-precision log decides (cc:34)
+        const int ka = __ffs((int)amb) - 1;
+        amb &= amb - 1;
+        my_diff[ka] = mn_log1m_decide(mn_edge2_clip<CLIP>(ina[(size_t)ka * TP]));
+      }
     }
     mn_fence_proxy_async();  // staged results -> visible to the bulk-store engine
     __syncwarp();
@@ -633,13 +639,16 @@ __global__ void __launch_bounds__(MN_EDGE2_MAX_THREADS, 3) mn_edge_warp_kernel(M
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mn_smem_u32(&S.empty[stage])) : "memory");
       if (nvalid > 0) {
         const size_t p0 = (size_t)start + (size_t)warp * 32;
-        mn_tma_store_1d(im.clp + p0 * C, o_clp, (uint32_t)(nvalid * C * 4));
-        mn_tma_store_1d(im.rec_same + p0 * K, o_same, (uint32_t)(nvalid * K * 4));
-        mn_tma_store_1d(im.rec_diff + p0 * K, o_diff, (uint32_t)(nvalid * K * 4));
+        mn_tma_store_1d(g_clp + p0 * C, o_clp, (uint32_t)(nvalid * C * 4));
+        mn_tma_store_1d(g_same + p0 * K, o_same, (uint32_t)(nvalid * K * 4));
+        mn_tma_store_1d(g_diff + p0 * K, o_diff, (uint32_t)(nvalid * K * 4));
         mn_tma_store_commit();
       }
     }
-    if (lane < nvalid) im.cls[start + px] = bc;
+    if (lane < nvalid) g_cls[start + px] = bc;
+    b += step_b; t += step_t;
+    if (t >= tpi) { t -= tpi; b++; }
+    if (++stage == NS) { stage = 0; parity ^= 1; }
   }
   if (lane == 0) mn_tma_store_wait_read();
 }
