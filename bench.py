@@ -301,12 +301,12 @@ def run_own_arm(args):
                     "steps": e2e_steps, "h2d_ms": tm_h["h2d_ms"], "d2h_ms": tm_h["d2h_ms"]},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "mn_edge_pass_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "mn_edge_warp_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this
-                         # kernel (profiles/r01_hbm_kernels_ncu_full.json: 384.9 MB per 1024x2048 image,
-                         # algorithmic 402.7 MB -- part of the last tiles' output is still in L2 at kernel end)
-                         "traffic": (384.9e6 * B) if (h, w, C, K) == (1024, 2048, 9, 10) else None,
+                         # kernel (profiles/r01_edge_warp_ncu_full.json: 408.0 MB per 1024x2048 image;
+                         # algorithmic 402.7 MB + the 8.4 MB class-index plane the pass also writes)
+                         "traffic": (408.0e6 * B) if (h, w, C, K) == (1024, 2048, 9, 10) else None,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": edge_bytes, "avg_launch_ms": edge_s * 1e3},
             "cpu_baseline": cpu,

@@ -9,7 +9,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmergenet_b200.so")
+# MN_LIB_PATH selects another BUILD of this same library (e.g. the -DMN_PHASE_CYCLES profiling build)
+LIB_PATH = os.environ.get("MN_LIB_PATH") or os.path.join(_HERE, "libmergenet_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["mn_api.cu", "mn_edge.cuh", "mn_merge.cuh", "mn_layout.h", "mn_common.h", "mn_log1m_tab.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
