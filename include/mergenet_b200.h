@@ -57,6 +57,9 @@ const char* mn_status_string(int status);
 int mn_device_count(void);
 
 /* ---- batched interface ---------------------------------------------------------------------- */
+#define MN_INPUT_CLIP 1
+#define MN_INPUT_LOGITS 2
+
 typedef struct mn_plan mn_plan; /* workspace for up to max_batch images of one shape on one GPU */
 
 /* Per-image statistics of the last run (north star: round count, merges, per-round latency). */
@@ -94,7 +97,11 @@ void mn_plan_destroy(mn_plan* plan);
  * Segment `batch` images whose maps are ALREADY ON THE DEVICE of the plan.
  *   d_class [B][C][H][W] fp32, d_adj [B][K][H][W] fp32 (rewritten when same_different_bias != 0),
  *   d_mask [B][H][W] int32, d_object_class [B][H*W] int32, d_num_instances [B] int32.
- *   clip != 0 applies the wrapper's clip to [2^-23, 1-2^-23] (c_segment.pyx:53-55) on the fly.
+ *   clip: input flags.  MN_INPUT_CLIP applies the wrapper's clip to [2^-23, 1-2^-23]
+ *   (c_segment.pyx:53-55) on the fly; MN_INPUT_LOGITS says the maps are the network's raw outputs:
+ *   the edge pass applies F.sigmoid (utils/inference_utils.py:43-44,95-96: 1 / (1 + exp(-x)) in fp32,
+ *   as torch evaluates it on the device) and the clip while it reads them, so the probability maps
+ *   never exist in memory.  0 = probabilities, already clipped (what c_run_segmentation receives).
  *   stream: a cudaStream_t (NULL = the plan's own stream).  The call returns after the work has
  *   completed (it synchronises the stream to read the per-image status words).
  */
@@ -117,6 +124,32 @@ int mn_plan_timings(mn_plan* plan, mn_timings* out);
  * records of differentness, class + object_merge_factor * (differentness + sameness)}.  Computed on
  * the GPU by an aggregation pass over the statistics the merges maintained. */
 int mn_plan_image_logprob(mn_plan* plan, int image, double* out4);
+
+/* ---- the step after the path: masks back at the image size, COCO run-length encoding ---- */
+/*
+ * cv2.resize(mask, (out_width, out_height), interpolation=cv2.INTER_NEAREST) for `batch` int32 masks on
+ * the device (egs/cityscape/local/segment.py:147-149): out[y][x] = in[min(floor(y * (H / out_h)), H - 1)]
+ * [min(floor(x * (W / out_w)), W - 1)], the scale factors and products evaluated in double like OpenCV's
+ * resizeNN.  d_in [B][H][W], d_out [B][out_height][out_width].
+ */
+int mn_resize_masks_nearest_device(const int* d_in, int batch, int height, int width, int* d_out,
+                                   int out_height, int out_width, void* stream);
+int mn_resize_masks_nearest_host(const int* h_in, int batch, int height, int width, int* h_out,
+                                 int out_height, int out_width);
+/*
+ * COCO run-length encoding of every instance of ONE int32 label mask [H][W] with labels 0..n_instances
+ * (egs/cityscape/local/segment.py:165-186: for i in 1..n: maskUtils.encode(asfortranarray(mask == i))):
+ * column-major runs (pycocotools rleEncode), written as the compressed ASCII `counts` string
+ * (pycocotools rleToString).  Instance i's string is counts[offsets[i-1] .. offsets[i]) (not
+ * NUL-terminated); offsets has n_instances + 1 entries.  Returns MN_STATUS_BAD_ARG when counts_capacity
+ * is too small (offsets[n] then holds the size needed).  Host buffers in and out; the work runs on
+ * the GPU.
+ */
+int mn_mask_to_coco_rle_host(const int* h_mask, int height, int width, int n_instances,
+                             unsigned char* counts, long long counts_capacity, long long* offsets);
+
+/* device time (CUDA events, ms) of the last mn_resize_masks_nearest_host / mn_mask_to_coco_rle_host call */
+float mn_post_last_ms(void);
 
 /* ---- test hooks (parity tests call these through the same library) --------------------------- */
 /* Edge pass + record init of ONE image (host buffers in, host buffers out), i.e. what the reference

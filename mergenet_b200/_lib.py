@@ -12,14 +12,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MN_LIB_PATH selects another BUILD of this same library (e.g. the -DMN_PHASE_CYCLES profiling build)
 LIB_PATH = os.environ.get("MN_LIB_PATH") or os.path.join(_HERE, "libmergenet_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["mn_api.cu", "mn_edge.cuh", "mn_merge.cuh", "mn_layout.h", "mn_common.h", "mn_log1m_tab.h"]
+SOURCES = ["mn_api.cu", "mn_edge.cuh", "mn_merge.cuh", "mn_post.cuh", "mn_layout.h", "mn_common.h", "mn_log1m_tab.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-fmad=false"]
 
 EXPORTS = ["c_run_segmentation", "mn_last_error", "mn_status_string", "mn_device_count",
            "mn_workspace_bytes_per_image", "mn_plan_create", "mn_plan_destroy",
            "mn_segment_batch_device", "mn_segment_batch_host", "mn_plan_image_stats",
-           "mn_plan_timings", "mn_plan_image_logprob", "mn_debug_edge_dump", "mn_debug_libm", "mn_debug_edge_bench"]
+           "mn_plan_timings", "mn_plan_image_logprob", "mn_debug_edge_dump", "mn_debug_libm", "mn_debug_edge_bench",
+           "mn_resize_masks_nearest_device", "mn_resize_masks_nearest_host", "mn_mask_to_coco_rle_host", "mn_post_last_ms"]
 
 
 class MergeNetError(RuntimeError):
@@ -125,6 +126,13 @@ def lib():
                                      ctypes.c_float, ctypes.c_float, ctypes.c_float, _F, _I, _F, _F, _F, _F, _I, _I]
     L.mn_debug_edge_bench.restype = ctypes.c_int
     L.mn_debug_edge_bench.argtypes = [ctypes.c_int] * 4 + [_I] + [ctypes.c_int] * 3 + [_F]
+    L.mn_resize_masks_nearest_device.restype = ctypes.c_int
+    L.mn_resize_masks_nearest_device.argtypes = [_V, ctypes.c_int, ctypes.c_int, ctypes.c_int, _V, ctypes.c_int, ctypes.c_int, _V]
+    L.mn_resize_masks_nearest_host.restype = ctypes.c_int
+    L.mn_resize_masks_nearest_host.argtypes = [_V, ctypes.c_int, ctypes.c_int, ctypes.c_int, _V, ctypes.c_int, ctypes.c_int]
+    L.mn_mask_to_coco_rle_host.restype = ctypes.c_int
+    L.mn_mask_to_coco_rle_host.argtypes = [_V, ctypes.c_int, ctypes.c_int, ctypes.c_int, _V, ctypes.c_longlong, _V]
+    L.mn_post_last_ms.restype = ctypes.c_float
     L.mn_debug_libm.restype = ctypes.c_int
     L.mn_debug_libm.argtypes = [ctypes.c_int, ctypes.c_uint, ctypes.c_uint, ctypes.c_float, _F]
     _lib = L

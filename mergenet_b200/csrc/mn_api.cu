@@ -19,6 +19,7 @@
 #include "../../include/mergenet_b200.h"
 #include "mn_common.h"
 #include "mn_edge.cuh"
+#include "mn_post.cuh"
 #include "mn_layout.h"
 #include "mn_merge.cuh"
 
@@ -416,8 +417,9 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
   }
   p->edge2_ncons = choose_edge2(C, K, &p->edge2_ctas, &p->edge2_smem, &p->edge2_stages);
   if (p->edge2_ncons &&
-      (cudaFuncSetAttribute(mn_edge_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->edge2_smem) != cudaSuccess ||
-       cudaFuncSetAttribute(mn_edge_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->edge2_smem) != cudaSuccess))
+      (cudaFuncSetAttribute(mn_edge_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->edge2_smem) != cudaSuccess ||
+       cudaFuncSetAttribute(mn_edge_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->edge2_smem) != cudaSuccess ||
+       cudaFuncSetAttribute(mn_edge_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->edge2_smem) != cudaSuccess))
     p->edge2_ncons = 0;
   if (cudaFuncSetAttribute(mn_edge_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->edge_smem) != cudaSuccess ||
       cudaFuncSetAttribute(mn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->merge_smem) != cudaSuccess)
@@ -436,7 +438,9 @@ static int launch_edge(mn_plan* p, int B, const float* d_class, float* d_adj, in
   P.B = B; P.C = C; P.K = K; P.N = N; P.TP = p->edge_tp;
   P.tiles_per_image = (N + P.TP - 1) / P.TP;
   P.use_tma = (N % 4 == 0) && (((uintptr_t)d_class & 15) == 0) && (((uintptr_t)d_adj & 15) == 0);
-  P.clip = clip; P.sdb = sdb;
+  P.logits = (clip & MN_INPUT_LOGITS) ? 1 : 0;
+  P.clip = ((clip & MN_INPUT_CLIP) || P.logits) ? 1 : 0;  // (sigmoid saturates to 0 / 1 in fp32: logits are always clipped)
+  P.sdb = sdb;
   const bool warp_pipeline = p->edge2_ncons > 0 && P.use_tma && sdb == 0.0f;
   if (warp_pipeline) {
     P.TP = 32 * p->edge2_ncons;
@@ -450,8 +454,9 @@ static int launch_edge(mn_plan* p, int B, const float* d_class, float* d_adj, in
   if (warp_pipeline) {
     int grid = (int)std::min<long long>(tiles, (long long)p->num_sms * p->edge2_ctas);
     int threads = 32 * (p->edge2_ncons + 1);
-    if (clip) mn_edge_warp_kernel<true><<<grid, threads, p->edge2_smem, s>>>(P);
-    else mn_edge_warp_kernel<false><<<grid, threads, p->edge2_smem, s>>>(P);
+    if (P.logits) mn_edge_warp_kernel<2><<<grid, threads, p->edge2_smem, s>>>(P);
+    else if (P.clip) mn_edge_warp_kernel<1><<<grid, threads, p->edge2_smem, s>>>(P);
+    else mn_edge_warp_kernel<0><<<grid, threads, p->edge2_smem, s>>>(P);
   } else {
     int grid = (int)std::min<long long>(tiles, (long long)p->num_sms * MN_EDGE_CTAS_PER_SM);
     mn_edge_pass_kernel<<<grid, MN_EDGE_THREADS, p->edge_smem, s>>>(P);
@@ -668,6 +673,77 @@ extern "C" void c_run_segmentation(float* class_pred, int class_dim, float* adj_
     memset(output, 0, sizeof(int) * (size_t)N);
     memset(object_class, 0xFF, sizeof(int) * (size_t)N);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the step after the path: masks at the image size, COCO RLE (mn_post.cuh)
+static float g_post_ms = 0.f;
+extern "C" float mn_post_last_ms(void) { return g_post_ms; }
+
+extern "C" int mn_resize_masks_nearest_device(const int* d_in, int B, int H, int W, int* d_out, int OH, int OW, void* stream) {
+  g_last_error = MN_STATUS_OK;
+  if (!d_in || !d_out || B <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0) { g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  MN_CUDA_OK(mn_resize_nearest_launch(d_in, B, H, W, d_out, OH, OW, (cudaStream_t)stream));
+  return MN_STATUS_OK;
+}
+
+extern "C" int mn_resize_masks_nearest_host(const int* h_in, int B, int H, int W, int* h_out, int OH, int OW) {
+  g_last_error = MN_STATUS_OK;
+  if (!h_in || !h_out || B <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0) { g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  int *di = nullptr, *dout = nullptr;
+  const size_t nin = (size_t)B * H * W * 4, nout = (size_t)B * OH * OW * 4;
+  if (cudaMalloc(&di, nin) != cudaSuccess || cudaMalloc(&dout, nout) != cudaSuccess) { cudaFree(di); g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaError_t e = cudaMemcpy(di, h_in, nin, cudaMemcpyHostToDevice);
+  cudaEventRecord(e0, 0);
+  if (e == cudaSuccess) e = mn_resize_nearest_launch(di, B, H, W, dout, OH, OW, 0);
+  cudaEventRecord(e1, 0);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(h_out, dout, nout, cudaMemcpyDeviceToHost);
+  cudaEventElapsedTime(&g_post_ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(di); cudaFree(dout);
+  if (e != cudaSuccess) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  return MN_STATUS_OK;
+}
+
+extern "C" int mn_mask_to_coco_rle_host(const int* h_mask, int H, int W, int n, unsigned char* counts, long long cap,
+                                        long long* offsets) {
+  g_last_error = MN_STATUS_OK;
+  if (!h_mask || !offsets || H <= 0 || W <= 0 || n < 0 || cap < 0 || (cap > 0 && !counts) || (long long)H * W >= (1ll << 31)) {
+    g_last_error = MN_STATUS_BAD_ARG;
+    return MN_STATUS_BAD_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  const size_t a = (size_t)H * W;
+  int* dm = nullptr; unsigned char* dc = nullptr; long long* dofs = nullptr;
+  if (cudaMalloc(&dm, a * 4) != cudaSuccess || cudaMalloc(&dc, (size_t)(cap > 0 ? cap : 1)) != cudaSuccess ||
+      cudaMalloc(&dofs, ((size_t)n + 1) * 8) != cudaSuccess) {
+    cudaFree(dm); cudaFree(dc); cudaFree(dofs);
+    g_last_error = MN_STATUS_CUDA;
+    return MN_STATUS_CUDA;
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  long long total = 0;
+  cudaError_t e = cudaMemcpy(dm, h_mask, a * 4, cudaMemcpyHostToDevice);
+  cudaEventRecord(e0, 0);
+  if (e == cudaSuccess) e = mn_coco_rle_device(dm, H, W, n, dc, cap, dofs, &total, 0);
+  cudaEventRecord(e1, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(offsets, dofs, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && total <= cap && total > 0) e = cudaMemcpy(counts, dc, (size_t)total, cudaMemcpyDeviceToHost);
+  cudaEventElapsedTime(&g_post_ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(dm); cudaFree(dc); cudaFree(dofs);
+  if (e != cudaSuccess) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  if (total > cap) { offsets[n] = total; g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
+  return MN_STATUS_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -181,6 +181,9 @@ __device__ __forceinline__ float mn_bias_sameness(float s, float sdb, const MnLo
   return (float)(1.0 / (1.0 + (double)mn_expf_exact(-logit)));
 }
 
+// F.sigmoid as torch evaluates it on the device in fp32: 1 / (1 + exp(-x)), IEEE division (utils/inference_utils.py:43-44)
+__device__ __forceinline__ float mn_sigmoid_f32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
 struct MnEdgeParams {
   const float* class_pred;  // [B][C][N]
   const float* adj_pred;    // [B][K][N]
@@ -191,6 +194,7 @@ struct MnEdgeParams {
   int tiles_per_image;
   int use_tma;              // N % 4 == 0 and 16-byte aligned bases
   int clip;                 // apply the wrapper's clip to [2^-23, 1-2^-23] (c_segment.pyx:53-55)
+  int logits;               // inputs are the network's logits: sigmoid first (inference_utils.py:43-44,95-96), then clip
   float sdb;
   // warp-pipeline kernel: image b's outputs live at ws0_* + b * ws_stride (no pointer loads per tile)
   float *ws0_clp, *ws0_same, *ws0_diff;
@@ -302,6 +306,7 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_
         float best = 0.0f; int bc = 0;
         for (int pl = 0; pl < C; pl++) {
           float v = in[(size_t)pl * TP + px];
+          if (P.logits) v = mn_sigmoid_f32(v);
           if (P.clip) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
           const float l = MN_FADD(0.0f, mn_logf_fast(v, tab));  // cc:11-16
           out_clp[px * C + pl] = l;
@@ -312,7 +317,8 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_
       const int k0 = g == 0 ? K - a0 : 0, k1 = g == 0 ? K : K - a0;
       for (int k = k0; k < k1; k++) {
         float v = in[(size_t)(C + k) * TP + px];
-        if (P.clip) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
+        if (P.logits) v = mn_sigmoid_f32(v);
+          if (P.clip) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
         out_same[px * K + k] = mn_logf_fast(v, tab);     // cc:35
         out_diff[px * K + k] = mn_log1m_fast(v, tab1m);  // cc:34
       }
@@ -322,12 +328,14 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_
       const int px = tid & (TP - 1), g = tid >> sh, ng = nt >> sh;
       for (int pl = g; pl < C; pl += ng) {
         float v = in[(size_t)pl * TP + px];
-        if (P.clip) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
+        if (P.logits) v = mn_sigmoid_f32(v);
+          if (P.clip) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
         out_clp[px * C + pl] = MN_FADD(0.0f, mn_logf_fast(v, tab));  // cc:11-16
       }
       for (int k = g; k < K; k += ng) {
         float v = in[(size_t)(C + k) * TP + px];
-        if (P.clip) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
+        if (P.logits) v = mn_sigmoid_f32(v);
+          if (P.clip) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
         if (P.sdb != 0.0f) {  // cc:183-195, in place on the caller's buffer
           v = mn_bias_sameness(v, P.sdb, tab);
           P.adj_pred_rw[((size_t)b * K + k) * P.N + start + px] = v;
@@ -340,7 +348,8 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_
       for (int i = tid; i < items; i += nt) {
         const int pl = i / tl, px = i - pl * tl;
         float v = in[(size_t)pl * TP + px];
-        if (P.clip) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
+        if (P.logits) v = mn_sigmoid_f32(v);
+          if (P.clip) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
         if (pl < C) {
           out_clp[px * C + pl] = MN_FADD(0.0f, mn_logf_fast(v, tab));  // cc:11-16
         } else {
@@ -468,12 +477,14 @@ __device__ __forceinline__ bool mn_log1m_ambiguous(double y) {
 }
 __device__ __noinline__ float mn_log1m_decide(float s) { return (float)log(1.0 - (double)s); }
 
-template <bool CLIP>
+// CLIP: 0 = values as given, 1 = clip, 2 = logits: sigmoid, then clip
+template <int CLIP>
 __device__ __forceinline__ float mn_edge2_clip(float v) {
+  if (CLIP == 2) v = mn_sigmoid_f32(v);
   return CLIP ? fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f) : v;
 }
 
-template <bool CLIP>
+template <int CLIP>
 __global__ void __launch_bounds__(MN_EDGE2_MAX_THREADS, 3) mn_edge_warp_kernel(MnEdgeParams P) {
   __shared__ __align__(128) MnEdge2Smem S;
   extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -91,7 +91,9 @@ class BatchSegmenter:
         except Exception:
             pass
 
-    def segment_device(self, class_probs, same_probs, opts, clip=True, out=None):
+    def segment_device(self, class_probs, same_probs, opts, clip=True, out=None, logits=False):
+        """logits=True: the maps are the network's raw outputs; the edge pass applies F.sigmoid
+        (utils/inference_utils.py:43-44,95-96) and the clip while it reads them."""
         import torch
         B = class_probs.shape[0]
         assert class_probs.is_cuda and same_probs.is_cuda and class_probs.dtype == torch.float32
@@ -108,13 +110,13 @@ class BatchSegmenter:
         stream = torch.cuda.current_stream(dev).cuda_stream
         st = _lib.lib().mn_segment_batch_device(
             self._plan, B, class_probs.data_ptr(), same_probs.data_ptr(), masks.data_ptr(), ocls.data_ptr(),
-            ninst.data_ptr(), 1 if clip else 0, float(opts.same_different_bias),
+            ninst.data_ptr(), (2 if logits else 0) | (1 if clip else 0), float(opts.same_different_bias),
             float(opts.object_merge_factor), float(opts.merge_logprob_bias), ctypes.c_void_p(stream))
         if st != 0:
             raise _lib.MergeNetError(st, "mn_segment_batch_device: " + str(self.failed_images(B)))
         return masks, ocls, ninst
 
-    def segment_host(self, class_probs, same_probs, opts, clip=True, out=None):
+    def segment_host(self, class_probs, same_probs, opts, clip=True, out=None, logits=False):
         B = class_probs.shape[0]
         assert class_probs.dtype == np.float32 and same_probs.dtype == np.float32
         assert class_probs.flags["C_CONTIGUOUS"] and same_probs.flags["C_CONTIGUOUS"]
@@ -128,7 +130,7 @@ class BatchSegmenter:
             masks, ocls, ninst = out
         st = _lib.lib().mn_segment_batch_host(
             self._plan, B, class_probs.ctypes.data, same_probs.ctypes.data, masks.ctypes.data,
-            ocls.ctypes.data, ninst.ctypes.data, 1 if clip else 0, float(opts.same_different_bias),
+            ocls.ctypes.data, ninst.ctypes.data, (2 if logits else 0) | (1 if clip else 0), float(opts.same_different_bias),
             float(opts.object_merge_factor), float(opts.merge_logprob_bias))
         if st != 0:
             raise _lib.MergeNetError(st, "mn_segment_batch_host: " + str(self.failed_images(B)))

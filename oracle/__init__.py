@@ -274,3 +274,39 @@ def total_logprob_from_scratch(mask, object_class, class_pred, adj_pred, offset_
         tot_same += np.log(s[same]).sum()
         tot_diff += np.log(1.0 - s[~same]).sum()
     return float(tot_class + (tot_diff + tot_same) * object_merge_factor)
+
+
+# ---- the step after the path: checkers for mergenet_b200/csrc/mn_post.cuh ------------
+def oracle_resize_nearest(mask, out_h, out_w):
+    """cv2.resize(mask, (out_w, out_h), interpolation=cv2.INTER_NEAREST), restated (resizeNN)."""
+    L = oracle_lib()
+    m = np.ascontiguousarray(mask, np.int32)
+    out = np.empty((out_h, out_w), np.int32)
+    L.mno_resize_nearest(m.ctypes.data_as(_I), m.shape[0], m.shape[1], out.ctypes.data_as(_I), out_h, out_w)
+    return out
+
+
+def oracle_coco_rle(mask, n):
+    """[counts bytes of maskUtils.encode(asfortranarray(mask == i)) for i in 1..n] (restated maskApi.c)."""
+    L = oracle_lib()
+    L.mno_coco_rle.restype = ctypes.c_longlong
+    L.mno_coco_rle.argtypes = [_I, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong,
+                               ctypes.c_void_p]
+    m = np.ascontiguousarray(mask, np.int32)
+    offs = np.zeros(n + 1, np.int64)
+    need = L.mno_coco_rle(m.ctypes.data_as(_I), m.shape[0], m.shape[1], n, None, 0, offs.ctypes.data)
+    buf = np.zeros(max(1, need), np.uint8)
+    L.mno_coco_rle(m.ctypes.data_as(_I), m.shape[0], m.shape[1], n, buf.ctypes.data, need, offs.ctypes.data)
+    return [bytes(buf[offs[i]:offs[i + 1]]) for i in range(n)]
+
+
+def oracle_coco_rle_decode(strings, h, w):
+    """Label mask painted from the per-instance counts strings (rleFrString + rleDecode)."""
+    L = oracle_lib()
+    L.mno_coco_rle_decode.restype = ctypes.c_int
+    L.mno_coco_rle_decode.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int, _I]
+    out = np.zeros((h, w), np.int32)
+    for i, s in enumerate(strings):
+        rc = L.mno_coco_rle_decode(s, len(s), h, w, i + 1, out.ctypes.data_as(_I))
+        assert rc == 0, (i, rc)
+    return out

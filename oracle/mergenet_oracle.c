@@ -878,3 +878,106 @@ int mno_run_rounds_model(float* class_pred, int class_dim, float* adj_pred, int 
   seg_free(s);
   return (int)(mno_model_mismatches != 0);
 }
+
+/* ================================================================================================
+ * The step after the path: checkers for mergenet_b200/csrc/mn_post.cuh.
+ *
+ * mno_resize_nearest: cv2.resize(mask, (ow, oh), interpolation=cv2.INTER_NEAREST) as OpenCV's resizeNN
+ * computes it (egs/cityscape/local/segment.py:147-149): sx = min(cvFloor(x * (1 / (ow / (double)w))), w-1).
+ * Pinned against cv2 itself by tests/test_post_oracle.py (cv2 is in this image).
+ *
+ * mno_coco_rle: maskUtils.encode(np.asfortranarray(mask == i)) for i = 1..n
+ * (egs/cityscape/local/segment.py:165-186).  pycocotools is NOT in /root/reference nor in this image and
+ * the reference pins no version: restated from the published cocoapi common/maskApi.c (rleEncode,
+ * rleToString, rleFrString, rleDecode).  PARITY UNPINNED against pycocotools itself; pinned only by the
+ * encode -> decode round trip (mno_coco_rle_decode) and hand-checked strings in the tests.
+ * ================================================================================================ */
+void mno_resize_nearest(const int* in, int h, int w, int* out, int oh, int ow) {
+  const double ifx = 1.0 / ((double)ow / (double)w), ify = 1.0 / ((double)oh / (double)h);
+  for (int y = 0; y < oh; y++) {
+    int sy = (int)floor(y * ify);
+    if (sy > h - 1) sy = h - 1;
+    for (int x = 0; x < ow; x++) {
+      int sx = (int)floor(x * ifx);
+      if (sx > w - 1) sx = w - 1;
+      out[(size_t)y * ow + x] = in[(size_t)sy * w + sx];
+    }
+  }
+}
+
+/* rleToString (maskApi.c): returns the number of characters written (no NUL) */
+static long long mno_rle_to_string(const unsigned* cnts, long long m, unsigned char* s, long long cap, long long p0) {
+  long long p = p0;
+  for (long long i = 0; i < m; i++) {
+    long long x = (long long)cnts[i];
+    if (i > 2) x -= (long long)cnts[i - 2];
+    int more = 1;
+    while (more) {
+      int c = (int)(x & 0x1f);
+      x >>= 5;
+      more = (c & 0x10) ? x != -1 : x != 0;
+      if (more) c |= 0x20;
+      c += 48;
+      if (p < cap) s[p] = (unsigned char)c;
+      p++;
+    }
+  }
+  return p - p0;
+}
+
+/* mask: int32 [h][w] labels 0..n.  offsets: n + 1 entries.  Returns the total number of bytes needed. */
+long long mno_coco_rle(const int* mask, int h, int w, int n, unsigned char* counts, long long cap, long long* offsets) {
+  const long long a = (long long)h * w;
+  unsigned* cnts = (unsigned*)malloc(sizeof(unsigned) * (size_t)(a + 1));
+  long long p = 0;
+  for (int v = 1; v <= n; v++) {
+    /* rleEncode over the column-major (Fortran) binary mask (mask == v) */
+    long long k = 0;
+    unsigned c = 0;
+    int prev = 0;
+    for (long long j = 0; j < a; j++) {
+      const int col = (int)(j / h), row = (int)(j % h);
+      const int t = mask[(size_t)row * w + col] == v;
+      if (t != prev) { cnts[k++] = c; c = 0; prev = t; }
+      c++;
+    }
+    cnts[k++] = c;
+    offsets[v - 1] = p;
+    p += mno_rle_to_string(cnts, k, counts, cap, p);
+  }
+  offsets[n] = p;
+  free(cnts);
+  return p;
+}
+
+/* rleFrString + rleDecode: paints instance v's pixels (value v) into a zeroed int32 [h][w] mask */
+int mno_coco_rle_decode(const unsigned char* s, long long len, int h, int w, int v, int* mask) {
+  const long long a = (long long)h * w;
+  unsigned* cnts = (unsigned*)malloc(sizeof(unsigned) * (size_t)(len + 1));
+  long long m = 0, p = 0;
+  while (p < len) {
+    long long x = 0;
+    int k = 0, more = 1;
+    while (more) {
+      if (p >= len) { free(cnts); return -1; }
+      const int c = (int)s[p] - 48;
+      x |= (long long)(c & 0x1f) << (5 * k);
+      more = c & 0x20;
+      p++; k++;
+      if (!more && (c & 0x10)) x |= -1ll << (5 * k);
+    }
+    if (m > 2) x += (long long)cnts[m - 2];
+    cnts[m++] = (unsigned)x;
+  }
+  long long j = 0;
+  int val = 0;
+  for (long long i = 0; i < m; i++) {
+    for (unsigned q = 0; q < cnts[i]; q++, j++) {
+      if (j >= a) { free(cnts); return -2; }
+      if (val) mask[(size_t)(j % h) * w + (size_t)(j / h)] = v;
+    }
+    val = !val;
+  }
+  free(cnts);
+  return j == a ? 0 : -3;
+}

@@ -154,6 +154,34 @@ def test_batch_api_host_and_device_agree_and_are_deterministic(oracle_mod, lib_m
     seg.close()
 
 
+def test_logits_input_equals_torch_sigmoid_then_segment(oracle_mod, lib_mod):
+    """MN_INPUT_LOGITS: the edge pass applies F.sigmoid + the wrapper's clip while it reads the maps
+    (utils/inference_utils.py:43-44,95-96; c_segment.pyx:53-55).  Same masks as sigmoid on the device
+    with torch, then the plain path -- on a shape served by the warp-pipeline kernel and on one served
+    by the tile kernel (odd pixel count), including saturating logits."""
+    import torch
+    from mergenet_b200 import BatchSegmenter, SegmenterOptions
+    opts = SegmenterOptions(*cases.RECIPE_OPTS)
+    for (h, w) in ((64, 96), (45, 67)):
+        name, cp, sp, C, offs = ("x", ) + cases.cityscapes_like(h, w, 31, True)
+        lc = np.log(cp.astype(np.float64) / (1.0 - cp.astype(np.float64))).astype(np.float32)
+        ls = np.log(sp.astype(np.float64) / (1.0 - sp.astype(np.float64))).astype(np.float32)
+        lc[0, :2, :5] = 40.0; ls[1, :3, :3] = -120.0; ls[2, 5:7, :] = 95.0   # sigmoid saturates: the clip matters
+        dlc = torch.from_numpy(lc[None]).cuda(); dls = torch.from_numpy(ls[None]).cuda()
+        seg = BatchSegmenter(1, h, w, C, offs)
+        m1, c1, n1 = seg.segment_device(dlc, dls, opts, logits=True)
+        pc = torch.sigmoid(dlc).contiguous(); ps = torch.sigmoid(dls).contiguous()
+        m2, c2, n2 = seg.segment_device(pc, ps, opts, clip=True)
+        assert torch.equal(m1, m2) and torch.equal(c1, c2) and torch.equal(n1, n2), (h, w)
+        # and against the oracle on the host copy of torch's probabilities
+        from mergenet_b200 import synth
+        m0, c0, _ = oracle_mod.oracle_run_segmentation(synth.clip_probs(pc[0].cpu().numpy()), synth.clip_probs(ps[0].cpu().numpy()),
+                                                       C, offs, *cases.RECIPE_OPTS)
+        k = int(n1[0])
+        assert cases.same_result(oracle_mod, (m0, c0), (m1[0].cpu().numpy(), list(c1[0, :k].cpu().numpy()))), (h, w)
+        seg.close()
+
+
 def test_total_logprob_aggregation_matches_oracle(oracle_mod, lib_mod):
     """segment.cc:272-287: the GPU aggregation pass over the maintained sums against the oracle's own
     accumulators (same fp32 sums, same merge order) and against the float64 from-scratch evaluation of
