@@ -192,6 +192,7 @@ __global__ void mn_libm_kernel(int which, uint32_t first_bits, uint32_t n, float
 }
 
 // ------------------------------------------------------------------------------------------------
+#define MN_COPY_EVENTS 64
 struct mn_plan {
   int device, max_batch, H, W, C, K, N;
   long long E;
@@ -209,6 +210,8 @@ struct mn_plan {
   float* d_in_class; float* d_in_adj; int* d_out_mask; int* d_out_cls; int* d_out_ninst;
   size_t staging_batch;
   cudaStream_t stream;
+  cudaStream_t copy_stream;  // uploads of the host-buffer entry point
+  cudaEvent_t copy_ev[MN_COPY_EVENTS];
   cudaEvent_t ev[9];
   int num_sms;
   int edge_tp, edge_smem, merge_smem, merge_H;
@@ -310,6 +313,11 @@ extern "C" void mn_plan_destroy(mn_plan* p) {
   if (!p) return;
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
+  if (p->copy_stream) {
+    cudaStreamSynchronize(p->copy_stream);
+    for (int i = 0; i < MN_COPY_EVENTS; i++) cudaEventDestroy(p->copy_ev[i]);
+    cudaStreamDestroy(p->copy_stream);
+  }
   cudaFree(p->d_ws); cudaFree(p->d_imgs); cudaFree(p->d_keys_scratch); cudaFree(p->d_cub_temp); cudaFree(p->d_logprob);
   cudaFree(p->d_in_class); cudaFree(p->d_in_adj); cudaFree(p->d_out_mask); cudaFree(p->d_out_cls);
   cudaFree(p->d_out_ninst);
@@ -430,11 +438,11 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
 }
 
 // the edge pass for images [0, B): the warp-pipeline kernel when it applies, else the tile kernel
-static int launch_edge(mn_plan* p, int B, const float* d_class, float* d_adj, int clip, float sdb, cudaStream_t s) {
+static int launch_edge(mn_plan* p, int b0, int B, const float* d_class, float* d_adj, int clip, float sdb, cudaStream_t s) {
   const int N = p->N, C = p->C, K = p->K;
   MnEdgeParams P;
   P.class_pred = d_class; P.adj_pred = d_adj; P.adj_pred_rw = sdb != 0.0f ? d_adj : nullptr;
-  P.imgs = p->d_imgs;
+  P.imgs = p->d_imgs + b0;
   P.B = B; P.C = C; P.K = K; P.N = N; P.TP = p->edge_tp;
   P.tiles_per_image = (N + P.TP - 1) / P.TP;
   P.use_tma = (N % 4 == 0) && (((uintptr_t)d_class & 15) == 0) && (((uintptr_t)d_adj & 15) == 0);
@@ -445,7 +453,7 @@ static int launch_edge(mn_plan* p, int B, const float* d_class, float* d_adj, in
   if (warp_pipeline) {
     P.TP = 32 * p->edge2_ncons;
     P.stages = p->edge2_stages;
-    P.ws0_clp = p->h_imgs[0].clp; P.ws0_same = p->h_imgs[0].rec_same; P.ws0_diff = p->h_imgs[0].rec_diff; P.ws0_cls = p->h_imgs[0].cls;
+    P.ws0_clp = p->h_imgs[b0].clp; P.ws0_same = p->h_imgs[b0].rec_same; P.ws0_diff = p->h_imgs[b0].rec_diff; P.ws0_cls = p->h_imgs[b0].cls;
     P.ws_stride = p->per_image_bytes;
     P.tiles_per_image = (N + P.TP - 1) / P.TP;
   }
@@ -465,19 +473,19 @@ static int launch_edge(mn_plan* p, int B, const float* d_class, float* d_adj, in
   return MN_STATUS_OK;
 }
 
-// edge pass + record init + sort for images [0, B)
-static int run_front(mn_plan* p, int B, const float* d_class, float* d_adj, int clip, float sdb, float omf,
-                     float mlb, cudaStream_t s, bool sort_keys) {
+// edge pass + record init + sort for images [b0, b0 + B); d_class / d_adj point at image b0's maps
+static int run_front(mn_plan* p, int b0, int B, const float* d_class, float* d_adj, int clip, float sdb, float omf,
+                     float mlb, cudaStream_t s, bool sort_keys, bool record_events = true) {
   const int N = p->N, C = p->C, K = p->K;
   {
     dim3 g((unsigned)std::min<long long>(4096, (p->h_imgs[0].hash_nbuckets * 8ll + 255) / 256), (unsigned)std::min(B, 65535));
-    mn_reset_kernel<<<g, 256, 0, s>>>(p->d_imgs, B);
+    mn_reset_kernel<<<g, 256, 0, s>>>(p->d_imgs + b0, B);
     p->timings.other_launches++;
   }
-  MN_CUDA_OK(cudaEventRecord(p->ev[1], s));
-  if (int rc = launch_edge(p, B, d_class, d_adj, clip, sdb, s)) return rc;
-  MN_CUDA_OK(cudaEventRecord(p->ev[2], s));
-  for (int b = 0; b < B; b++) {
+  if (record_events) MN_CUDA_OK(cudaEventRecord(p->ev[1], s));
+  if (int rc = launch_edge(p, b0, B, d_class, d_adj, clip, sdb, s)) return rc;
+  if (record_events) MN_CUDA_OK(cudaEventRecord(p->ev[2], s));
+  for (int b = b0; b < b0 + B; b++) {
     MnRecInitParams R;
     R.im = p->h_imgs[b];
     R.keys_out = p->d_keys_scratch;  // (never init_keys: it shares the arena with the inputs rec_same | rec_diff)
@@ -492,10 +500,12 @@ static int run_front(mn_plan* p, int B, const float* d_class, float* d_adj, int 
                                                 p->h_imgs[b].init_keys, (int)p->E, 0, 32 + MN_ORD_BITS, s));
     }
   }
-  MN_CUDA_OK(cudaEventRecord(p->ev[3], s));
+  if (record_events) MN_CUDA_OK(cudaEventRecord(p->ev[3], s));
   MN_CUDA_OK(cudaGetLastError());
   return MN_STATUS_OK;
 }
+
+static int run_back(mn_plan* p, int B, int* d_mask, int* d_object_class, int* d_ninst, float omf, float mlb, cudaStream_t s);
 
 extern "C" int mn_segment_batch_device(mn_plan* p, int B, const float* d_class, float* d_adj, int* d_mask,
                                        int* d_object_class, int* d_ninst, int clip, float sdb, float omf,
@@ -509,8 +519,14 @@ extern "C" int mn_segment_batch_device(mn_plan* p, int B, const float* d_class, 
   cudaStream_t s = stream ? (cudaStream_t)stream : p->stream;
   const int N = p->N;
   p->timings.edge_launches = 0; p->timings.other_launches = 0;
-  int rc = run_front(p, B, d_class, d_adj, clip, sdb, omf, mlb, s, true);
+  int rc = run_front(p, 0, B, d_class, d_adj, clip, sdb, omf, mlb, s, true);
   if (rc) return rc;
+  return run_back(p, B, d_mask, d_object_class, d_ninst, omf, mlb, s);
+}
+
+// merge scheduler + aggregation + labels for images [0, B), whose front end has been enqueued on s
+static int run_back(mn_plan* p, int B, int* d_mask, int* d_object_class, int* d_ninst, float omf, float mlb, cudaStream_t s) {
+  const int N = p->N;
   MnMergeArgs A;
   memset(&A, 0, sizeof(A));
   A.C = p->C; A.K = p->K; A.N = N; A.W = p->W; A.omf = omf; A.mlb = mlb; A.off = p->off; A.H = p->merge_H; A.max_rounds = 40ll * N + 100000;  // guard: rounds <= events, a few per pixel
@@ -588,11 +604,31 @@ extern "C" int mn_segment_batch_host(mn_plan* p, int B, const float* h_class, fl
   if (rc) return rc;
   const size_t N = p->N;
   cudaStream_t s = p->stream;
+  // The uploads run on a second stream, in chunks of a few images, while the front end (edge pass,
+  // record init, sort) of the previous chunk runs on the plan's stream: only the first chunk's copy is exposed.
+  if (!p->copy_stream) {
+    MN_CUDA_OK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < MN_COPY_EVENTS; i++) MN_CUDA_OK(cudaEventCreateWithFlags(&p->copy_ev[i], cudaEventDisableTiming));
+  }
+  p->timings.edge_launches = 0; p->timings.other_launches = 0;
   MN_CUDA_OK(cudaEventRecord(p->ev[0], s));
-  MN_CUDA_OK(cudaMemcpyAsync(p->d_in_class, h_class, (size_t)B * p->C * N * 4, cudaMemcpyHostToDevice, s));
-  MN_CUDA_OK(cudaMemcpyAsync(p->d_in_adj, h_adj, (size_t)B * p->K * N * 4, cudaMemcpyHostToDevice, s));
-  rc = mn_segment_batch_device(p, B, p->d_in_class, p->d_in_adj, p->d_out_mask, p->d_out_cls, p->d_out_ninst,
-                               clip, sdb, omf, mlb, s);
+  MN_CUDA_OK(cudaStreamWaitEvent(p->copy_stream, p->ev[0], 0));  // (the staging buffers are free: earlier work on s is done)
+  const int chunk = std::max(8, (B + MN_COPY_EVENTS - 1) / MN_COPY_EVENTS);  // 8 images (1.3 GB at 1024x2048), at most MN_COPY_EVENTS chunks
+  int ci = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ci++) {
+    const int nb = std::min(chunk, B - b0);
+    const size_t oc = (size_t)b0 * p->C * N, oa = (size_t)b0 * p->K * N;
+    MN_CUDA_OK(cudaMemcpyAsync(p->d_in_class + oc, h_class + oc, (size_t)nb * p->C * N * 4, cudaMemcpyHostToDevice, p->copy_stream));
+    MN_CUDA_OK(cudaMemcpyAsync(p->d_in_adj + oa, h_adj + oa, (size_t)nb * p->K * N * 4, cudaMemcpyHostToDevice, p->copy_stream));
+    MN_CUDA_OK(cudaEventRecord(p->copy_ev[ci], p->copy_stream));
+    MN_CUDA_OK(cudaStreamWaitEvent(s, p->copy_ev[ci], 0));
+    if (b0 == 0) MN_CUDA_OK(cudaEventRecord(p->ev[1], s));  // h2d_ms = the exposed part of the upload
+    rc = run_front(p, b0, nb, p->d_in_class + oc, p->d_in_adj + oa, clip, sdb, omf, mlb, s, true, false);
+    if (rc) return rc;
+  }
+  MN_CUDA_OK(cudaEventRecord(p->ev[2], s));  // (chunked: edge_ms covers the whole front end, record_init_sort_ms is 0)
+  MN_CUDA_OK(cudaEventRecord(p->ev[3], s));
+  rc = run_back(p, B, p->d_out_mask, p->d_out_cls, p->d_out_ninst, omf, mlb, s);
   MN_CUDA_OK(cudaEventRecord(p->ev[6], s));
   MN_CUDA_OK(cudaMemcpyAsync(h_mask, p->d_out_mask, (size_t)B * N * 4, cudaMemcpyDeviceToHost, s));
   MN_CUDA_OK(cudaMemcpyAsync(h_object_class, p->d_out_cls, (size_t)B * N * 4, cudaMemcpyDeviceToHost, s));
@@ -760,7 +796,7 @@ extern "C" int mn_debug_edge_dump(int H, int W, int C, int K, const int* offset_
   cudaStream_t s = p->stream;
   cudaMemcpyAsync(p->d_in_class, h_class, (size_t)C * N * 4, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(p->d_in_adj, h_adj, (size_t)K * N * 4, cudaMemcpyHostToDevice, s);
-  rc = run_front(p, 1, p->d_in_class, p->d_in_adj, 0, sdb, omf, mlb, s, false);
+  rc = run_front(p, 0, 1, p->d_in_class, p->d_in_adj, 0, sdb, omf, mlb, s, false);
   if (rc) return done(rc);
   std::vector<uint4> rec(2 * E);
   const MnImage& im = p->h_imgs[0];
@@ -804,11 +840,11 @@ extern "C" int mn_debug_edge_bench(int H, int W, int C, int K, const int* offset
   cudaStream_t s = p->stream;
   mn_fill_probs_kernel<<<2048, 256, 0, s>>>(dc, (size_t)B * C * N, 1u);
   mn_fill_probs_kernel<<<2048, 256, 0, s>>>(da, (size_t)B * K * N, 2u);
-  for (int w = 0; w < 2; w++) rc = launch_edge(p, B, dc, da, clip, 0.0f, s);
+  for (int w = 0; w < 2; w++) rc = launch_edge(p, 0, B, dc, da, clip, 0.0f, s);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, s);
-  for (int it = 0; it < iters && !rc; it++) rc = launch_edge(p, B, dc, da, clip, 0.0f, s);
+  for (int it = 0; it < iters && !rc; it++) rc = launch_edge(p, 0, B, dc, da, clip, 0.0f, s);
   cudaEventRecord(e1, s);
   cudaError_t e = cudaStreamSynchronize(s);
   float ms = 0.f;

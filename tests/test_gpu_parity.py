@@ -154,6 +154,28 @@ def test_batch_api_host_and_device_agree_and_are_deterministic(oracle_mod, lib_m
     seg.close()
 
 
+def test_host_entry_chunked_upload_equals_device_entry(oracle_mod, lib_mod):
+    """mn_segment_batch_host uploads in chunks of 8 images on a second stream while the front end of the
+    previous chunk runs: 21 images = chunks of 8, 8, 5; results must equal the device entry's."""
+    import torch
+    from mergenet_b200 import BatchSegmenter, SegmenterOptions
+    H, W = 32, 48
+    items = [cases.cityscapes_like(H, W, 40 + s, s % 3 != 0) for s in range(7)]
+    C, offs = items[0][2], items[0][3]
+    cp = np.ascontiguousarray(np.stack([items[i % 7][0] for i in range(21)]))
+    sp = np.ascontiguousarray(np.stack([items[i % 7][1] for i in range(21)]))
+    opts = SegmenterOptions(*cases.PLAIN_OPTS)
+    seg = BatchSegmenter(21, H, W, C, offs)
+    for _ in range(2):  # (the second call reuses the staging buffers and the copy stream)
+        m_h, oc_h, n_h = seg.segment_host(cp, sp, opts)
+        m_d, oc_d, n_d = seg.segment_device(torch.from_numpy(cp).cuda(), torch.from_numpy(sp).cuda(), opts)
+        assert np.array_equal(m_h, m_d.cpu().numpy()) and np.array_equal(oc_h, oc_d.cpu().numpy())
+        assert np.array_equal(n_h, n_d.cpu().numpy())
+    for b in range(7):
+        assert np.array_equal(m_h[b], m_h[b + 7]) and np.array_equal(m_h[b], m_h[b + 14])
+    seg.close()
+
+
 def test_logits_input_equals_torch_sigmoid_then_segment(oracle_mod, lib_mod):
     """MN_INPUT_LOGITS: the edge pass applies F.sigmoid + the wrapper's clip while it reads the maps
     (utils/inference_utils.py:43-44,95-96; c_segment.pyx:53-55).  Same masks as sigmoid on the device
