@@ -115,7 +115,8 @@ struct MnSm {
   int c_ptra[MN_H]; int c_ptrb[MN_H]; int c_newptr[MN_H]; int c_cpbase[MN_H];
   float c_same[MN_H]; int c_eslot[MN_H];
   int c_pwbase[MN_H]; int c_npairs[MN_H]; int c_pbase[MN_H]; int c_pfill[MN_H];
-  uint32_t c_maxnew[MN_H]; int c_conflict[MN_H]; int c_accept[MN_H];
+  unsigned long long c_maxnew[MN_H];  // pop-order key (mn_pop_key) of the earliest-popping entry the candidate stores; 0: none
+  int c_conflict[MN_H]; int c_accept[MN_H];
   int m_list[MN_H]; int m_base[MN_H + 1]; int nm;      // merging candidates and their pixel ranges
   int cp_list[MN_H]; int cp_base[MN_H + 1]; int ncp;   // accepted merges whose survivor array moves
   // work lists
@@ -948,6 +949,13 @@ MN_D int mn_hash_insert_hint(const MnImage& im, MnSm& sm, int lo, int hi, int re
   return -1;
 }
 
+// 64-bit pop-order key of a queue entry for the cascade test of the accept pass: larger = pops earlier.
+// [mp bits + 1 : 32][~(top 32 bits of the 48-bit tie) : 32].  Entries that differ only in the low 16 tie
+// bits get the same key; the test treats equal keys as "pops first", which is the safe side.
+MN_D unsigned long long mn_pop_key(float mp, int lo, int hi) {
+  return (((unsigned long long)mn_f2u(mp) + 1ull) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(mn_tie(lo, hi) >> 16));
+}
+
 // ---- plan the pairs [p0, p1) (record t of candidate j's absorbed object), cc:650-707 -----------
 // Dependent round trips: record t -> {neighbour object, new-key buckets, old-key buckets} ->
 // partner record (+ the neighbour's class vector when classes differ).
@@ -1023,7 +1031,7 @@ MN_D void mn_plan_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const
     sm.w.pr.x[i] = x; sm.w.pr.u[i] = u; sm.w.pr.oml[i] = oml; sm.w.pr.same[i] = same; sm.w.pr.diff[i] = diff;
     sm.w.pr.mp[i] = mp; sm.w.pr.lo[i] = nlo; sm.w.pr.hi[i] = nhi; sm.w.pr.q[i] = q;
     sm.w.pr.eslot[i] = (int)ta.z; sm.w.pr.islot[i] = islot;
-    if (mp >= 0.0f) MN_ATOMIC_MAX(&sm.c_maxnew[j], mn_f2u(mp) + 1u);
+    if (mp >= 0.0f) MN_ATOMIC_MAX(&sm.c_maxnew[j], mn_pop_key(mp, nlo, nhi));
   }
 }
 
@@ -1199,7 +1207,7 @@ MN_D void mn_classify(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const f
   if (st != MN_K_DROP && (sm.c_dup[j] & (st == MN_K_RESTORE ? 2 : 1))) st = MN_K_DROP;
   if (st != MN_K_RESTORE) {
     sm.c_kind[j] = st;
-    if (st == MN_K_REQUEUE) sm.c_maxnew[j] = mn_f2u(v.w) + 1u;
+    if (st == MN_K_REQUEUE) sm.c_maxnew[j] = mn_pop_key(v.w, lh.x, lh.y);
     // a guard touches its record, whose endpoints may have moved since the entry was queued
     if (st != MN_K_DROP) { sm.c_lo[j] = lh.x; sm.c_hi[j] = lh.y; }
     return;
@@ -1221,7 +1229,7 @@ MN_D void mn_classify(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const f
     sm.c_same[j] = MN_FADD(mn_u2f(oa.y), MN_FADD(v.y, mn_u2f(ob.y)));  // cc:641-642
   } else {  // cc:563-565
     sm.c_kind[j] = MN_K_RESTORE;
-    if (nmp >= 0.0f) sm.c_maxnew[j] = mn_f2u(nmp) + 1u;
+    if (nmp >= 0.0f) sm.c_maxnew[j] = mn_pop_key(nmp, lo, hi);
   }
 }
 
@@ -1414,10 +1422,10 @@ MN_D int mn_wscan_incl(int v, int lane) {
   for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += o; }
   return v;
 }
-MN_D uint32_t mn_wscan_max_excl(uint32_t v, int lane) {  // exclusive prefix maximum
-  for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d && o > v) v = o; }
-  uint32_t e = __shfl_up_sync(0xffffffffu, v, 1);
-  return lane == 0 ? 0u : e;
+MN_D unsigned long long mn_wscan_max_excl(unsigned long long v, int lane) {  // exclusive prefix maximum
+  for (int d = 1; d < 32; d <<= 1) { unsigned long long o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d && o > v) v = o; }
+  unsigned long long e = __shfl_up_sync(0xffffffffu, v, 1);
+  return lane == 0 ? 0ull : e;
 }
 #endif
 
@@ -1495,10 +1503,12 @@ MN_D void mn_pass_accept(const MnImage& im, MnSm& sm, int ncand, int npr) {
   const bool event = k == MN_K_RESTORE || k == MN_K_MERGE;
   const uint32_t memm = __ballot_sync(0xffffffffu, member);
   const uint32_t lt = (1u << lane) - 1u;
-  const uint32_t exmax = mn_wscan_max_excl(member ? sm.c_maxnew[lane] : 0u, lane);
+  const unsigned long long exmax = mn_wscan_max_excl(member ? sm.c_maxnew[lane] : 0ull, lane);
   const bool before = (memm & lt) != 0;
   const bool cconf = member && before && sm.c_conflict[lane] != 0;
-  const bool ccasc = member && before && !cconf && event && exmax != 0 && exmax - 1u >= mn_f2u(sm.c_key[lane]);
+  // rule (b), in the full pop order (mp, then tie): an entry stored by an earlier member pops before this event
+  const bool ccasc = member && before && !cconf && event && exmax != 0 &&
+                     exmax >= mn_pop_key(sm.c_key[lane], sm.c_lo[lane], sm.c_hi[lane]);
   const uint32_t cm = __ballot_sync(0xffffffffu, cconf || ccasc);
   const int cut = cm ? __ffs(cm) - 1 : ncand;
   const bool acc = member && lane < cut;
@@ -1551,7 +1561,7 @@ MN_D void mn_pass_accept(const MnImage& im, MnSm& sm, int ncand, int npr) {
     }
   }
 #else
-  uint32_t runmax = 0;  // bits+1 of the largest priority stored by an accepted member
+  unsigned long long runmax = 0;  // pop key of the earliest-popping entry stored by an accepted member
   int cut = ncand, nacc = 0;
   sm.ncp = 0; sm.cp_base[0] = 0;
   const long long s0 = sm.st_invalid, s1 = sm.st_cut_conf, s2 = sm.st_cut_casc, s3 = sm.st_merges, s4 = sm.st_events,
@@ -1562,7 +1572,7 @@ MN_D void mn_pass_accept(const MnImage& im, MnSm& sm, int ncand, int npr) {
     if (k == MN_K_DROP) { sm.st_invalid++; continue; }
     const bool event = (k == MN_K_RESTORE || k == MN_K_MERGE);
     if (sm.c_conflict[j] && nacc > 0) { cut = j; sm.st_cut_conf++; break; }
-    if (event && runmax != 0 && runmax - 1u >= mn_f2u(sm.c_key[j]) && nacc > 0) { cut = j; sm.st_cut_casc++; break; }
+    if (event && runmax != 0 && runmax >= mn_pop_key(sm.c_key[j], sm.c_lo[j], sm.c_hi[j]) && nacc > 0) { cut = j; sm.st_cut_casc++; break; }
     sm.c_accept[j] = 1;
     nacc++;
     if (sm.c_maxnew[j] > runmax) runmax = sm.c_maxnew[j];
