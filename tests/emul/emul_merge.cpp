@@ -149,3 +149,25 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   // (leaks on purpose: short-lived test process helper)
   return status;
 }
+
+// The accept pass compares 64-bit pop keys instead of full (mp, tie) orders: whenever entry a pops
+// before entry b, key(a) >= key(b) must hold (equal keys are treated as "pops first": the safe side).
+// Returns the number of violations over n random pairs (many of them tied on mp, close in lo/hi).
+extern "C" long long emul_pop_key_violations(long long n, unsigned seed) {
+  unsigned long long s = seed * 6364136223846793005ull + 1442695040888963407ull;
+  auto rnd = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (unsigned)(s >> 33); };
+  const float mps[6] = {0.0f, 0.03f, 0.030000001f, 1.5f, 2.4e-7f, 17.25f};
+  long long bad = 0;
+  for (long long i = 0; i < n; i++) {
+    const int N = 1 << (8 + rnd() % 14);
+    int alo = (int)(rnd() % N), ahi = alo + 1 + (int)(rnd() % 90000);
+    int blo = (rnd() % 4 == 0) ? alo : (int)(rnd() % N), bhi = blo + 1 + (int)(rnd() % 90000);
+    float amp = mps[rnd() % 6], bmp = (rnd() % 2) ? amp : mps[rnd() % 6];
+    const bool ab = mn_before(amp, alo, ahi, bmp, blo, bhi), ba = mn_before(bmp, blo, bhi, amp, alo, ahi);
+    const unsigned long long ka = mn_pop_key(amp, alo, ahi), kb = mn_pop_key(bmp, blo, bhi);
+    if (ab && !(ka >= kb)) bad++;
+    if (ba && !(kb >= ka)) bad++;
+    if (amp > bmp && !(ka > kb)) bad++;  // a higher priority always wins strictly
+  }
+  return bad;
+}

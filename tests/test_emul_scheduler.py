@@ -58,3 +58,11 @@ def test_emulated_scheduler_matches_oracle_medium(emul, oracle_mod):
         assert rc == 0, (name, rc)
         assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), name
         assert st["merges"] == st0["merges"], name
+
+
+def test_pop_key_is_consistent_with_the_pop_order(emul):
+    """Rule (b) of the accept pass is evaluated on 64-bit pop keys (mn_pop_key): a pops before b must
+    imply key(a) >= key(b), and a strictly higher priority a strictly larger key."""
+    emul.emul_pop_key_violations.restype = ctypes.c_longlong
+    emul.emul_pop_key_violations.argtypes = [ctypes.c_longlong, ctypes.c_uint]
+    assert emul.emul_pop_key_violations(2_000_000, 7) == 0
