@@ -517,7 +517,6 @@ extern "C" int mn_segment_batch_device(mn_plan* p, int B, const float* d_class, 
   }
   MN_CUDA_OK(cudaSetDevice(p->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : p->stream;
-  const int N = p->N;
   p->timings.edge_launches = 0; p->timings.other_launches = 0;
   int rc = run_front(p, 0, B, d_class, d_adj, clip, sdb, omf, mlb, s, true);
   if (rc) return rc;

@@ -1199,7 +1199,7 @@ MN_D void mn_stage_candidates(const MnImage& im, MnSm& sm, const MnMergeArgs& A,
 
 // Classify candidate j from the staged data (cc:554-561).  One thread per candidate.
 MN_D void mn_classify(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const float* c_clp, int j) {
-  const float mp = sm.c_key[j]; const int lo = sm.c_lo[j], hi = sm.c_hi[j], rec = sm.c_rec[j];
+  const float mp = sm.c_key[j]; const int lo = sm.c_lo[j], hi = sm.c_hi[j];
   const int2 lh = sm.c_lh[j];
   const float4 v = sm.c_val[j];
   int st = mn_entry_state(mp, lo, hi, lh, v);
