@@ -1,8 +1,8 @@
-"""dev tool: time the post-pass (nearest resize 512x1024 -> 1024x2048, COCO RLE of a 1024x2048 mask with
+"""checker script (run by hand, tests/ may use the oracle): time the post-pass (nearest resize 512x1024 -> 1024x2048, COCO RLE of a 1024x2048 mask with
 ~340 instances) on the GPU, device time from CUDA events, beside the oracle on one host core."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import oracle
 from mergenet_b200 import _lib, post, synth
 oracle.build()

@@ -7,7 +7,7 @@ a = [int(x) for x in sys.argv[1:]]
 H, W, C, K, B, iters = (a + [1024, 2048, 9, 10, 8, 20][len(a):])[:6]
 offs = np.ascontiguousarray(np.array(synth.generate_offsets(40, K), np.int32))
 L = _lib.lib()
-for clip in (0, 1):
+for clip in (0, 1, 2):
     ms = ctypes.c_float(0)
     rc = L.mn_debug_edge_bench(H, W, C, K, offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), B, iters, clip, ctypes.byref(ms))
     per_img = ms.value / B
