@@ -67,6 +67,13 @@ __global__ void __launch_bounds__(MN_MERGE_THREADS, 1) mn_merge_kernel(const MnI
   float* c_clp = reinterpret_cast<float*>(smem_raw + ((sizeof(MnSm) + 15) / 16) * 16);
   for (int b = blockIdx.x; b < nimg; b += gridDim.x) {
     const MnImage im = imgs[b];
+    // every array of the workspace is global memory: lets the compiler emit LDG / STG instead of
+    // generic loads and stores for the scheduler's scattered accesses
+    __builtin_assume(__isGlobal(im.clp)); __builtin_assume(__isGlobal(im.cls)); __builtin_assume(__isGlobal(im.obj));
+    __builtin_assume(__isGlobal(im.parent)); __builtin_assume(__isGlobal(im.pix_pool)); __builtin_assume(__isGlobal(im.rec));
+    __builtin_assume(__isGlobal(im.hash)); __builtin_assume(__isGlobal(im.hash_ovf)); __builtin_assume(__isGlobal(im.init_keys));
+    __builtin_assume(__isGlobal(im.q_ent)); __builtin_assume(__isGlobal(im.qc_next)); __builtin_assume(__isGlobal(im.qc_free));
+    __builtin_assume(__isGlobal(im.tn)); __builtin_assume(__isGlobal(im.tn_dir)); __builtin_assume(__isGlobal(im.ctl));
     long long t0 = clock64();
     mn_merge_image(im, sm, A, c_clp);
     if (threadIdx.x == 0) im.ctl->cycles_total = clock64() - t0;
