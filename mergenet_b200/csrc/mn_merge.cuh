@@ -48,13 +48,21 @@
 #define MN_IC 2048       // insert-buffer capacity
 #define MN_NE 1024       // new hot-bound entries per round (>= MN_WL + MN_H, <= MN_SB)
 #define MN_SB 1024       // sort buffer capacity
+#ifndef MN_LEAFCAP
 #define MN_LEAFCAP 512   // tree leaves larger than this are split before they are loaded
+#endif
 #define MN_CT 2048       // conflict-table slots (power of two)
 #define MN_GCL 512        // objects scanned per garbage-collection step (one per thread)
+#ifndef MN_LF
 #define MN_LF 128         // leaves one refill may load
+#endif
 #define MN_OVF 128        // records in the hash overflow area (cached in shared memory)
+#ifndef MN_REFILL_TARGET
 #define MN_REFILL_TARGET 384      // stop loading tree leaves once this many entries are staged
+#endif
+#ifndef MN_REFILL_STATIC_MIN
 #define MN_REFILL_STATIC_MIN 128  // sort-buffer slots always left for initial entries
+#endif
 #define MN_NEG_INF (-3.0e38f)
 #define MN_RANK_MAX 256  // up to this many entries are ordered by brute-force ranking (no barriers)
 // cycle accounting buckets (thread 0, clock64)
@@ -604,7 +612,10 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
     int nleaf = 0;
     if (MN_T0) { sm.npr = 0; sm.nlf = 0; sm.lf_start[0] = 0; }
     MN_SYNC();
-    for (int lguard = 0; lguard < MN_LF && nleaf < MN_REFILL_TARGET; lguard++) {
+    // (MN_LF bounds the leaves that CONTRIBUTE entries -- lf_start has a slot per contributing leaf --, not the
+    //  leaves visited: late in a run whole leaves are stale, and stopping after MN_LF fruitless leaves with
+    //  nothing staged would read "no leaf entry" below as "the tree is empty" and lose what is behind them)
+    for (int lguard = 0; lguard < (1 << 22) && sm.nlf < MN_LF && nleaf < MN_REFILL_TARGET; lguard++) {
       int root = 0;
       int leaf = mn_top_leaf(im, sm, &root, nleaf == 0);  // splitting reuses the staging buffers
       if (nleaf == 0) { MN_SYNC(); if (MN_T0) sm.npr = 0; MN_SYNC(); }  // (a split used npr)

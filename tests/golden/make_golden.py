@@ -67,6 +67,25 @@ def main_unet():
         print("unet_cfg1", tag, mask.shape, len(ocls), "instances")
 
 
+def main_full(images=(0, 1)):
+    """BASELINE config 2 at its full size (1024x2048, the bench generator with seeds 1000 + i): canonical
+    mask and classes of the UNMODIFIED reference -> tests/golden/full/ (75 KB each; the inputs are
+    regenerated from the seeds).  ~5 min and 7 GB of RAM per image:  python tests/golden/make_golden.py full"""
+    from mergenet_b200 import synth
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "full")
+    os.makedirs(out, exist_ok=True)
+    for i in images:
+        cp, sp, offs, _ = synth.cfg_cityscapes(1024, 2048, seed=1000 + i, n_shapes=400, rmax=120, soft=True, noise_seed=7 + i)
+        mask, ocls = oracle.ref_run_segmentation(cp, sp, 9, offs, *cases.RECIPE_OPTS)
+        cm, cc = oracle.canonical_result(mask, ocls)
+        np.savez_compressed(os.path.join(out, "cfg2_1024x2048_seed%d.npz" % (1000 + i)), mask=cm.astype(np.int32),
+                            cls=np.array(cc, np.int32), opts=np.array(cases.RECIPE_OPTS, np.float32))
+        print("full", i, len(cc), "instances")
+
+
 if __name__ == "__main__":
-    main()
-    main_unet()
+    if len(sys.argv) > 1 and sys.argv[1] == "full":
+        main_full()
+    else:
+        main()
+        main_unet()

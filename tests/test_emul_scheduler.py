@@ -66,3 +66,32 @@ def test_pop_key_is_consistent_with_the_pop_order(emul):
     emul.emul_pop_key_violations.restype = ctypes.c_longlong
     emul.emul_pop_key_violations.argtypes = [ctypes.c_longlong, ctypes.c_uint]
     assert emul.emul_pop_key_violations(2_000_000, 7) == 0
+
+
+STRESS = ["-DMN_LF=2 -DMN_LEAFCAP=64", "-DMN_REFILL_TARGET=16", "-DMN_LEAFCAP=128 -DMN_LF=1",
+          "-DMN_LEAFCAP=64 -DMN_REFILL_TARGET=32 -DMN_LF=4"]
+
+
+@pytest.mark.parametrize("flags", STRESS)
+def test_queue_limits_do_not_change_results(oracle_mod, flags):
+    """The queue's capacity constants must never change what is computed.  Regression: a refill used to
+    stop after MN_LF visited leaves even when none of them held a live entry, took "nothing staged" for
+    "the tree is empty" and dropped the entries behind them -- at 1024x2048 the last 1-3 merges of an
+    image were lost (341 instead of 338 instances).  Small limits make that situation common."""
+    so = os.path.join(EMUL_DIR, "libemul_stress_%s.so" % "".join(ch for ch in flags if ch.isalnum()))
+    srcs = [os.path.join(EMUL_DIR, "emul_merge.cpp")] + [
+        os.path.join(HERE, "..", "mergenet_b200", "csrc", f) for f in ("mn_merge.cuh", "mn_layout.h", "mn_common.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in srcs):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off"] + flags.split() +
+                              ["-o", so, srcs[0]])
+    lib = ctypes.CDLL(so)
+    F = ctypes.POINTER(ctypes.c_float); I = ctypes.POINTER(ctypes.c_int); LL = ctypes.POINTER(ctypes.c_longlong)
+    lib.emul_run_segmentation.argtypes = [F, ctypes.c_int, F, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          I, I, I, ctypes.c_float, ctypes.c_float, ctypes.c_float, LL]
+    for name, cp, sp, C, offs in cases.small_cases()[:5] + cases.medium_cases()[:2]:
+        m0, c0, st0 = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *cases.RECIPE_OPTS)
+        rc, m1, c1, st = run_emul(lib, oracle_mod, cp, sp, C, offs, cases.RECIPE_OPTS)
+        assert rc == 0, (name, rc)
+        assert st["merges"] == st0["merges"], name
+        assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), name

@@ -255,6 +255,27 @@ def test_coco_shaped_medium_matches_oracle(oracle_mod, lib_mod):
 
 
 @pytest.mark.gpu
+def test_full_resolution_equals_the_reference(oracle_mod, lib_mod):
+    """BASELINE config 2 at its full size: two 1024x2048 cfg2 images (the bench generator, seeds 1000 and
+    1001) against tests/golden/full/*.npz = canonical masks and classes computed by the UNMODIFIED compiled
+    reference in the build container (tests/golden/make_golden.py full; ~5 min and 7 GB per image there).
+    Regression for the refill leaf-limit bug, which only showed at this size."""
+    from mergenet_b200 import BatchSegmenter, SegmenterOptions, synth
+    h, w = 1024, 2048
+    ims = [synth.cfg_cityscapes(h, w, seed=1000 + i, n_shapes=400, rmax=120, soft=True, noise_seed=7 + i) for i in range(2)]
+    offs = ims[0][2]
+    cp = np.ascontiguousarray(np.stack([im[0] for im in ims])); sp = np.ascontiguousarray(np.stack([im[1] for im in ims]))
+    seg = BatchSegmenter(2, h, w, 9, offs)
+    m, oc, n = seg.segment_host(cp, sp, SegmenterOptions(*cases.RECIPE_OPTS), clip=False)
+    for i in range(2):
+        g = np.load(os.path.join(GOLDEN, "full", "cfg2_1024x2048_seed%d.npz" % (1000 + i)))
+        cm, cc = oracle_mod.canonical_result(m[i], [int(v) for v in oc[i][:n[i]]])
+        assert len(cc) == len(g["cls"]), (i, len(cc), len(g["cls"]))
+        assert np.array_equal(cm, g["mask"]) and list(cc) == list(g["cls"]), i
+        assert seg.stats(i)["status"] == 0
+    seg.close()
+
+
 def test_full_resolution_properties(oracle_mod, lib_mod):
     """BASELINE.json's full size (1024x2048, C=9, K=10), where the oracle is too slow for the suite:
     size-independent properties only.  Two images in one batch (soft and oracle-mode maps):
