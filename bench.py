@@ -97,6 +97,33 @@ def make_images(n, seed0, h=H, w=W):
     return np.ascontiguousarray(np.stack(cps)), np.ascontiguousarray(np.stack(sps)), offs
 
 
+def parity_with_reference_fixture(mask, classes, h, w):
+    """SURVEY 8d "parity check attached to every timing": image 0 of rank 0 (seed 1000, noise seed 1007) against
+    tests/golden/full/bench_image0_seed1000_noise1007.npz = canonical mask + classes computed by the UNMODIFIED
+    reference in the build container (tests/golden/make_golden.py).  Relabel = first appearance in raster
+    order, done here with numpy (nothing under oracle/ is used).  None when no fixture applies."""
+    path = os.path.join(ROOT, "tests", "golden", "full", "bench_image0_seed1000_noise1007.npz")
+    if (h, w, C, K) != (1024, 2048, 9, 10) or not os.path.exists(path):
+        return None
+    g = np.load(path)
+    flat = np.asarray(mask).ravel()
+    labels, first = np.unique(flat, return_index=True)
+    perm = np.zeros(int(labels.max()) + 1, dtype=np.int64)
+    nxt = 1
+    for idx in np.argsort(first, kind="stable"):
+        if labels[idx] != 0:
+            perm[labels[idx]] = nxt
+            nxt += 1
+    cm = perm[flat].reshape(h, w)
+    cc = np.zeros(nxt - 1, dtype=np.int64)
+    for k, c in enumerate(classes, start=1):
+        if k < perm.size and perm[k] > 0:
+            cc[perm[k] - 1] = c
+    return {"image": "rank 0, image 0", "fixture": "tests/golden/full/bench_image0_seed1000_noise1007.npz (unmodified reference)",
+            "instances": int(nxt - 1), "reference_instances": int(len(g["cls"])),
+            "mask_equal": bool(np.array_equal(cm, g["mask"])), "classes_equal": bool(list(cc) == list(g["cls"]))}
+
+
 # ---- CPU reference arm / baseline -----------------------------------------------------------------
 def _ref_worker(seed):
     import oracle
@@ -253,6 +280,10 @@ def run_own_arm(args):
     stats = [seg.stats(b) for b in range(B)]
     tm_dev = seg.timings()
     logprob0 = seg.total_logprob(0)[3]
+    parity = None
+    if rank == 0:
+        n0 = int(out_dev[2][0].item())
+        parity = parity_with_reference_fixture(out_dev[0][0].cpu().numpy(), out_dev[1][0, :n0].cpu().numpy().tolist(), h, w)
     value = world * B * args.steps / (ms / 1e3)
 
     # e2e through the host-buffer ABI (one warm-up, then the same number of steps).  The device-resident
@@ -310,6 +341,7 @@ def run_own_arm(args):
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": edge_bytes, "avg_launch_ms": edge_s * 1e3},
             "cpu_baseline": cpu,
+            "parity": parity,
             "scheduler": {"merge_kernel_ms": merge_s * 1e3, "rounds_per_image": float(np.mean(rounds)),
                           "events_per_image": float(np.mean(events)), "merges_per_image": float(np.mean(merges)),
                           "us_per_round": 1e6 * merge_s / max(1.0, float(np.max(rounds))),
