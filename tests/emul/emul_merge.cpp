@@ -33,7 +33,9 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   im.pix_cap = 2 * (3 * N + 2048);
   im.pix_pool = zalloc<int>(im.pix_cap);
   im.rec = zalloc<uint4>(2 * E);
-  im.hash_nbuckets = (uint32_t)(E * 16 / 10 / 8 + 64);
+  // EMUL_HASH_PERMILLE: slots per 1000 records (default 1600); a tight table exercises the overflow area
+  const long long permille = getenv("EMUL_HASH_PERMILLE") ? atoll(getenv("EMUL_HASH_PERMILLE")) : 1600;
+  im.hash_nbuckets = (uint32_t)(E * permille / 1000 / 8 + 64);
   im.hash = zalloc<uint32_t>((size_t)im.hash_nbuckets * 8);
   im.hash_ovf_cap = 4096;
   im.hash_ovf = zalloc<uint32_t>(im.hash_ovf_cap);

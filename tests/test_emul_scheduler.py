@@ -95,3 +95,16 @@ def test_queue_limits_do_not_change_results(oracle_mod, flags):
         assert rc == 0, (name, rc)
         assert st["merges"] == st0["merges"], name
         assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), name
+
+
+def test_hash_overflow_area_keeps_results_and_fails_loudly_when_full(emul, oracle_mod, monkeypatch):
+    """A tight (lo, hi) -> record table pushes records into the small overflow area (cached in shared
+    memory on the GPU): results must not change; past its 128 entries the run must FAIL, not go wrong."""
+    name, cp, sp, C, offs = cases.medium_cases()[0]
+    m0, c0, st0 = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *cases.RECIPE_OPTS)
+    monkeypatch.setenv("EMUL_HASH_PERMILLE", "1300")   # 1.3 slots per record instead of 1.6: tens of overflow records
+    rc, m1, c1, st = run_emul(emul, oracle_mod, cp, sp, C, offs, cases.RECIPE_OPTS)
+    assert rc == 0 and cases.same_result(oracle_mod, (m0, c0), (m1, c1)) and st["merges"] == st0["merges"]
+    monkeypatch.setenv("EMUL_HASH_PERMILLE", "1000")
+    rc, m1, c1, st = run_emul(emul, oracle_mod, cp, sp, C, offs, cases.RECIPE_OPTS)
+    assert rc != 0
