@@ -53,6 +53,21 @@ def test_edge_pass_bitwise_equals_reference_constructor(oracle_mod, lib_mod, opt
             assert np.array_equal(_bits(ref["adj_pred"]), _bits(got["adj"])), name
 
 
+def test_edge_pass_bitwise_at_full_resolution(oracle_mod, lib_mod):
+    """The warp-pipeline edge kernel over a whole 1024x2048 cfg2 image (9363 tiles of 224 pixels, ragged last
+    tile) against the oracle's constructor: every clp / same / diff / oml / initial-priority bit."""
+    from mergenet_b200 import synth
+    cp, sp, offs, _ = synth.cfg_cityscapes(1024, 2048, seed=1003, n_shapes=400, rmax=120, soft=True, noise_seed=11)
+    ref = oracle_mod.oracle_init_dump(cp, sp, 9, offs, *cases.RECIPE_OPTS)
+    got = _edge_dump(lib_mod, cp, sp, 9, offs, cases.RECIPE_OPTS)
+    valid = ref["valid"].astype(bool)
+    assert np.array_equal(valid, got["lo"] >= 0)
+    assert np.array_equal(_bits(ref["clp"]), _bits(got["clp"]))
+    assert np.array_equal(ref["cls"], got["cls"])
+    for k in ("same", "diff", "oml", "mp"):
+        assert np.array_equal(_bits(ref[k])[valid], _bits(got[k])[valid]), k
+
+
 def test_edge_kernels_agree_bitwise_incl_unclipped_input(lib_mod, monkeypatch):
     """The warp-pipeline edge kernel (fast path) and the tile kernel (general path) must produce the
     same bits, also when the caller did not clip (values below 2^-23 / equal to 1 - 2^-24 leave the
