@@ -68,6 +68,10 @@ def test_gpu_coco_rle_equals_oracle(oracle_mod, lib_mod):
     assert post.coco_rle_counts(z, 3) == oracle_mod.oracle_coco_rle(z, 3) == [b"Z1"] * 3   # 42 = the single count
     f = np.full((6, 7), 2, np.int32)   # instance 1 has no pixels, instance 2 all of them
     assert post.coco_rle_counts(f, 2) == oracle_mod.oracle_coco_rle(f, 2)
+    assert post.coco_rle_counts(f, 0) == []                       # no instances asked for
+    g = _label_mask(20, 30, 9, 8)
+    assert post.coco_rle_counts(g, 4) == oracle_mod.oracle_coco_rle(g, 4)   # labels above n belong to no instance
+    assert post.convert_to_coco_result(np.zeros((5, 5), np.int32), [], 1, [0]) == []
 
 
 @pytest.mark.gpu
