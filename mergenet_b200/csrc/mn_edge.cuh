@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_
 //     l & 7): the 8 lanes of every quarter-warp phase hit 8 different bank groups whatever their
 //     indices -- exactly 4 wavefronts per lookup.  That caps the table sizes: logf keeps glibc's own
 //     16 entries (2 KB), log(1 - s) uses a 64-bin table (8 KB) with the same degree-6 polynomial
-//     (tools/check_log1m64.c: 0 differences outside the fallback set over the whole clipped domain);
+//     (tests/check_log1m64.c: 0 differences outside the fallback set over the whole clipped domain);
 //   * the rare exact decision of log(1 - s) (6e-5 of the values) is deferred to after the plane loops,
 //     so the loops carry no call and their constants stay in registers.
 struct MnEdge2Smem {

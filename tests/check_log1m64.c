@@ -1,5 +1,5 @@
 // dev check (host): the 64-bin log(1 - s) evaluation of mn_edge_warp_kernel, emulated with fma(), against
-// the host libm on the whole clipped domain.  gcc -O2 -mfma tools/check_log1m64.c -lm -o /tmp/chk && /tmp/chk
+// the host libm on the whole clipped domain.  built and run by tests/test_libm_parity.py::test_log1m_64bin_table_exhaustive (gcc -O2 [-mfma] ... -lm)
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>

@@ -24,6 +24,27 @@ def test_expf_recipe_equals_libm_sampled(oracle_mod):
     assert L.mno_expf_recipe_mismatches(7) == 0
 
 
+def test_log1m_64bin_table_exhaustive(tmp_path):
+    """The 64-bin log(1 - s) evaluation of mn_edge_warp_kernel (table from tools/gen_log1m_table.py, degree-6
+    polynomial, ambiguity test), emulated on the host with fma(): its float rounding must equal the host
+    libm's (float)log(1.0 - (double)s) on every input of the clipped domain outside the fallback set."""
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "check_log1m64")
+    flags = ["-O2"]
+    try:
+        if " fma " in open("/proc/cpuinfo").read():
+            flags.append("-mfma")   # hardware fma: 3 s instead of a software fma() per step
+    except OSError:
+        pass
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc] + flags + [os.path.join(here, "check_log1m64.c"), "-lm", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "mismatches outside the fallback set 0" in out.stdout and "inputs 192937983" in out.stdout, out.stdout
+
+
 def _device_vs_host(oracle_mod, lib_mod, which, host_fn, stride_chunks=1, bias=0.0):
     L = lib_mod.lib()
     F = ctypes.POINTER(ctypes.c_float)
