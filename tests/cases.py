@@ -57,6 +57,23 @@ def medium_cases():
     return out
 
 
+def pathological_cases():
+    """Degenerate shapes and maps: 1x1 and one-row images, one class, one or sixteen offsets, constant 0.5
+    maps (every priority equal), all-same and all-different sameness, uniform random maps."""
+    rng = np.random.default_rng(0)
+    out = []
+    for (h, w, C, K) in [(1, 1, 2, 1), (1, 2, 2, 1), (2, 1, 3, 2), (5, 5, 1, 1), (8, 8, 2, 16), (16, 16, 9, 10),
+                         (32, 32, 9, 10), (3, 50, 4, 3)]:
+        offs = [(1, 0)] if K == 1 else synth.generate_offsets(40, K)
+        tag = "%dx%d_C%d_K%d" % (h, w, C, K)
+        f = lambda a: synth.clip_probs(np.asarray(a, np.float32))  # noqa: E731
+        out.append(("const_" + tag, f(np.full((C, h, w), 0.5)), f(np.full((K, h, w), 0.5)), C, offs))
+        out.append(("allsame_" + tag, f(np.full((C, h, w), 0.9)), f(np.full((K, h, w), 1.0)), C, offs))
+        out.append(("alldiff_" + tag, f(rng.random((C, h, w))), f(np.full((K, h, w), 0.0)), C, offs))
+        out.append(("random_" + tag, f(rng.random((C, h, w))), f(rng.random((K, h, w))), C, offs))
+    return out
+
+
 def same_result(oracle, a, b):
     ca = oracle.canonical_result(*a)
     cb = oracle.canonical_result(*b)

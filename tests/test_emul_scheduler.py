@@ -108,3 +108,12 @@ def test_hash_overflow_area_keeps_results_and_fails_loudly_when_full(emul, oracl
     monkeypatch.setenv("EMUL_HASH_PERMILLE", "1000")
     rc, m1, c1, st = run_emul(emul, oracle_mod, cp, sp, C, offs, cases.RECIPE_OPTS)
     assert rc != 0
+
+
+def test_emulated_scheduler_on_degenerate_inputs(emul, oracle_mod):
+    for name, cp, sp, C, offs in cases.pathological_cases():
+        for opts in (cases.RECIPE_OPTS, cases.PLAIN_OPTS):
+            m0, c0, st0 = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)
+            rc, m1, c1, st = run_emul(emul, oracle_mod, cp, sp, C, offs, opts)
+            assert rc == 0 and st["merges"] == st0["merges"], (name, opts, rc)
+            assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), (name, opts)

@@ -112,6 +112,17 @@ def test_drop_in_matches_oracle_medium(oracle_mod, lib_mod):
         assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), name
 
 
+def test_degenerate_inputs(oracle_mod, lib_mod):
+    """1x1 / one-row images, one class, one or sixteen offsets, constant maps (all priorities tie),
+    all-same / all-different sameness: the drop-in entry against the oracle."""
+    from mergenet_b200 import c_segment
+    for name, cp, sp, C, offs in cases.pathological_cases():
+        for opts in (cases.RECIPE_OPTS, cases.PLAIN_OPTS):
+            m0, c0, _ = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)
+            m1, c1 = c_segment.run_segmentation(cp, sp, C, offs, *opts)
+            assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), (name, opts)
+
+
 def test_same_different_bias_path(oracle_mod, lib_mod):
     from mergenet_b200 import c_segment
     name, cp, sp, C, offs = cases.small_cases()[0]
