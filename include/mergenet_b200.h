@@ -89,6 +89,9 @@ typedef struct {
 /* Bytes of device workspace one image of this shape needs (for sizing max_batch). */
 size_t mn_workspace_bytes_per_image(int height, int width, int num_classes, int num_offsets);
 
+/* Shape limits (MN_STATUS_BAD_ARG beyond them): height * width < 2^24 pixels, height * width * num_offsets <=
+ * 2^25 record slots (record ids share a 32-bit hash word with a 6-bit fingerprint), num_classes < 256,
+ * num_offsets <= 16.  Every BASELINE shape fits (1024 x 2048 x 10 = 21.0 M slots). */
 int mn_plan_create(mn_plan** out, int max_batch, int height, int width, int num_classes,
                    int num_offsets, const int* offset_list /* K x 2 (drow, dcol) */, int device);
 void mn_plan_destroy(mn_plan* plan);
