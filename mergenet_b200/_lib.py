@@ -63,7 +63,7 @@ class ImageStats(ctypes.Structure):
                     "queue_chunks_used", "pixel_pool_used", "tree_nodes_used", "requeues", "hash_overflow", "pixel_pool_collections", "cycles_total")] + [
         ("cycles", ctypes.c_longlong * 16)]
 
-    CYCLE_NAMES = ("select", "plan", "accept", "commit", "hot", "flush", "refill", "split", "solo", "gc",
+    CYCLE_NAMES = ("conflict", "plan", "accept", "commit", "hot", "flush", "refill", "split", "solo", "pairlist",
                    "rf_leaves", "rf_init", "rf_sort", "sel_stage", "sel_class", "sel_pix")
 
     def as_dict(self):

@@ -67,7 +67,7 @@
 #define MN_RANK_MAX 256  // up to this many entries are ordered by brute-force ranking (no barriers)
 // cycle accounting buckets (thread 0, clock64)
 #define MN_NCYC 16
-#define MN_CY_SELECT 0   // stage + classify + work lists
+#define MN_CY_CONFLICT 0 // footprints into the conflict table + conflict check
 #define MN_CY_PLAN 1
 #define MN_CY_ACCEPT 2
 #define MN_CY_COMMIT 3
@@ -76,7 +76,7 @@
 #define MN_CY_REFILL 6
 #define MN_CY_SPLIT 7
 #define MN_CY_SOLO 8
-#define MN_CY_GC 9
+#define MN_CY_PAIRLIST 9 // capacity cut by pairs + pair lists
 #define MN_CY_RF_LEAVES 10  // refill: tree leaves
 #define MN_CY_RF_INIT 11    // refill: initial entries, bound, bulk requeue
 #define MN_CY_RF_SORT 12    // refill: ordering + merge into hot
@@ -1574,6 +1574,9 @@ MN_D void mn_pass_accept(const MnImage& im, MnSm& sm, int ncand, int npr) {
 #else
   unsigned long long runmax = 0;  // pop key of the earliest-popping entry stored by an accepted member
   int cut = ncand, nacc = 0;
+#ifdef MN_EMUL_STATS
+  int runmax_j = -1;
+#endif
   sm.ncp = 0; sm.cp_base[0] = 0;
   const long long s0 = sm.st_invalid, s1 = sm.st_cut_conf, s2 = sm.st_cut_casc, s3 = sm.st_merges, s4 = sm.st_events,
                   s5 = sm.st_restores, s6 = sm.st_requeues;
@@ -1583,9 +1586,18 @@ MN_D void mn_pass_accept(const MnImage& im, MnSm& sm, int ncand, int npr) {
     if (k == MN_K_DROP) { sm.st_invalid++; continue; }
     const bool event = (k == MN_K_RESTORE || k == MN_K_MERGE);
     if (sm.c_conflict[j] && nacc > 0) { cut = j; sm.st_cut_conf++; break; }
-    if (event && runmax != 0 && runmax >= mn_pop_key(sm.c_key[j], sm.c_lo[j], sm.c_hi[j]) && nacc > 0) { cut = j; sm.st_cut_casc++; break; }
+    if (event && runmax != 0 && runmax >= mn_pop_key(sm.c_key[j], sm.c_lo[j], sm.c_hi[j]) && nacc > 0) {
+      cut = j; sm.st_cut_casc++;
+#ifdef MN_EMUL_STATS
+      MN_EMUL_STATS(sm, runmax_j, j);
+#endif
+      break;
+    }
     sm.c_accept[j] = 1;
     nacc++;
+#ifdef MN_EMUL_STATS
+    if (sm.c_maxnew[j] > runmax) runmax_j = j;
+#endif
     if (sm.c_maxnew[j] > runmax) runmax = sm.c_maxnew[j];
     if (k == MN_K_MERGE) { sm.st_merges++; sm.st_events++; mn_alloc_pixels(im, sm, j); }
     else if (k == MN_K_RESTORE) { sm.st_restores++; sm.st_events++; }
@@ -1698,7 +1710,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
       long long t0 = clock64();
       unsigned idx = 12345u;
       for (int i = 0; i < 64; i++) { int2 v = MN_REC_LH(im, idx % (unsigned)E); idx = idx * 1664525u + 1013904223u + (unsigned)v.x; }
-      sm.cyc[MN_CY_GC] = clock64() - t0 + (idx == 7u ? 1 : 0);
+      sm.cyc[MN_CY_PAIRLIST] = clock64() - t0 + (idx == 7u ? 1 : 0);
     }
     MN_SYNC();
     long long t0 = clock64();
@@ -1717,6 +1729,9 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     MN_SYNC();
     if (sm.failed) break;
     if (A.max_rounds > 0 && round >= A.max_rounds) { if (MN_T0) mn_fail(im, MN_ERR_LIMIT); break; }
+#ifdef MN_EMUL_ROUND_HOOK
+    MN_EMUL_ROUND_HOOK(im, sm, A, round);  // (host test builds only)
+#endif
     MN_TIC();
     if (sm.nins > MN_IC - MN_NE - 64) { mn_flush_ins(im, sm); MN_TOC(MN_CY_FLUSH); }
     if (sm.nhot == 0) {
@@ -1764,6 +1779,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
       }
     }
     MN_SYNC();
+    MN_TOC(MN_CY_SEL_PIX);
     mn_pass_capacity(sm, sm.ncand, sm.c_npairs, sm.c_pbase, MN_WL, false);  // capacity cut by pairs
     MN_SYNC();
     if (sm.solo) {
@@ -1790,7 +1806,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
       }
     }
     MN_SYNC();
-    MN_TOC(MN_CY_SEL_PIX);
+    MN_TOC(MN_CY_PAIRLIST);
     // ---- phase 4: plan ----
     mn_plan_pairs(im, sm, A, c_clp, 0, npr);
     MN_SYNC();
@@ -1823,6 +1839,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
       if (s >= 0 && sm.ct_w[s] < sm.w.pr.cand[i]) sm.c_conflict[sm.w.pr.cand[i]] = 1;
     }
     MN_SYNC();
+    MN_TOC(MN_CY_CONFLICT);
     // ---- phase 6: accept the longest provably sequential prefix ----
     mn_pass_accept(im, sm, ncand, npr);
     MN_SYNC();

@@ -83,9 +83,64 @@ def main_full(images=(0, 1)):
         print("full", i, len(cc), "instances")
 
 
+def _save_result(path, cp, sp, C, offs, opts, store_inputs=False, **extra):
+    """Run the unmodified reference and store its canonical mask / classes and the float64 from-scratch
+    log-prob of ITS partition (segment.cc:314-350 as oracle.total_logprob_from_scratch evaluates it)."""
+    import time
+    t0 = time.time()
+    mask, ocls = oracle.ref_run_segmentation(cp, sp, C, offs, *opts)
+    secs = time.time() - t0
+    cm, cc = oracle.canonical_result(mask, ocls)
+    lp = oracle.total_logprob_from_scratch(mask, ocls, cp, sp, offs, opts[1])
+    d = dict(mask=cm.astype(np.int32), cls=np.array(cc, np.int32), opts=np.array(opts, np.float32),
+             logprob=np.float64(lp), ref_seconds=np.float64(secs), **extra)
+    if store_inputs:
+        d.update(class_pred=cp, adj_pred=sp, num_classes=np.int32(C), offsets=np.array(offs, np.int32))
+    np.savez_compressed(path, **d)
+    print(os.path.basename(path), cm.shape, len(cc), "instances, logprob %.6f, reference %.1f s" % (lp, secs), flush=True)
+
+
+def main_matrix(which=None):
+    """The BASELINE.json configurations at their named sizes -> tests/golden/matrix/:
+    cfg1 256x512 (the reference's UNet(9,10); inputs stored once, they cannot be regenerated without the
+    reference tree), cfg3 oracle-mode 256x512 and 1024x2048, cfg4 512x512 C=81 K=16 oracle-mode and soft.
+    Inputs other than cfg1's are regenerated from the seeds by tests/matrix_cases.py."""
+    import matrix_cases
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "matrix")
+    os.makedirs(out, exist_ok=True)
+    for name in matrix_cases.NAMES:
+        if which and name not in which:
+            continue
+        if name.startswith("cfg1"):
+            inp = os.path.join(out, "cfg1_256x512_inputs.npz")
+            if not os.path.exists(inp):
+                cp, sp = unet_cfg1(256, 512)
+                np.savez_compressed(inp, class_pred=cp, adj_pred=sp)
+        cp, sp, C, offs, opts = matrix_cases.load(name)
+        _save_result(os.path.join(out, name + ".npz"), cp, sp, C, offs, opts)
+
+
+def main_full_logprob():
+    """Adds the reference partition's float64 from-scratch log-prob to the tests/golden/full fixtures (the
+    partition is the reference's: recomputed from the stored canonical mask, no reference run needed)."""
+    from mergenet_b200 import synth
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "full")
+    for fn, seed, noise in (("cfg2_1024x2048_seed1000.npz", 1000, 7), ("cfg2_1024x2048_seed1001.npz", 1001, 8),
+                            ("bench_image0_seed1000_noise1007.npz", 1000, 1007)):
+        z = dict(np.load(os.path.join(out, fn)))
+        cp, sp, offs, _ = synth.cfg_cityscapes(1024, 2048, seed=seed, n_shapes=400, rmax=120, soft=True, noise_seed=noise)
+        z["logprob"] = np.float64(oracle.total_logprob_from_scratch(z["mask"], list(z["cls"]), cp, sp, offs, float(z["opts"][1])))
+        np.savez_compressed(os.path.join(out, fn), **z)
+        print(fn, "logprob %.6f" % float(z["logprob"]), flush=True)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "full":
         main_full()
+    elif len(sys.argv) > 1 and sys.argv[1] == "matrix":
+        main_matrix(sys.argv[2:] or None)
+    elif len(sys.argv) > 1 and sys.argv[1] == "full_logprob":
+        main_full_logprob()
     else:
         main()
         main_unet()

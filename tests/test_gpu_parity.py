@@ -335,3 +335,45 @@ def test_full_resolution_properties(oracle_mod, lib_mod):
         t = tot[b]
         assert np.isfinite(t[3]) and abs(t[3] - (t[0] + opts.object_merge_factor * (t[2] + t[1]))) <= 1e-9 * abs(t[3])
     seg.close()
+
+
+def _logprob_close(a, b):
+    return abs(a - b) <= 1e-5 * abs(b)
+
+
+@pytest.mark.parametrize("name", ["cfg1_256x512_recipe", "cfg1_256x512_plain", "cfg3_256x512_oracle",
+                                  "cfg4_512x512_oracle", "cfg4_512x512_soft", "cfg3_1024x2048_oracle"])
+def test_baseline_config_matrix_equals_the_reference(oracle_mod, lib_mod, name):
+    """BASELINE.json's configurations at their NAMED sizes against results of the unmodified compiled reference
+    (tests/golden/matrix/, made by `python tests/golden/make_golden.py matrix` in the build container):
+    cfg1 256x512 from the reference's own UNet (recipe and plain options), cfg3 oracle-mode maps (tie-heavy)
+    at 256x512 and 1024x2048, cfg4 512x512 with 81 classes and 16 offsets (oracle-mode and soft).  Three legs:
+    identical canonical mask, identical per-instance classes, and the float64 from-scratch log-prob of the
+    partition (segment.cc:314-350) within 1e-5 relative of the reference partition's."""
+    import matrix_cases
+    from mergenet_b200 import c_segment
+    cp, sp, C, offs, opts = matrix_cases.load(name)
+    g = np.load(os.path.join(GOLDEN, "matrix", name + ".npz"))
+    assert tuple(float(v) for v in g["opts"]) == tuple(np.float32(o) for o in opts)
+    m1, c1 = c_segment.run_segmentation(cp, sp, C, offs, *opts)
+    cm, cc = oracle_mod.canonical_result(m1, c1)
+    assert len(cc) == len(g["cls"]), (len(cc), len(g["cls"]))
+    assert np.array_equal(cm, g["mask"]) and list(cc) == [int(v) for v in g["cls"]]
+    lp = oracle_mod.total_logprob_from_scratch(m1, c1, cp, sp, offs, opts[1])
+    assert _logprob_close(lp, float(g["logprob"])), (lp, float(g["logprob"]))
+
+
+def test_full_resolution_logprob_within_tolerance(oracle_mod, lib_mod):
+    """North star, third leg at BASELINE's full size: the float64 from-scratch log-prob of the CUDA partition of
+    a 1024x2048 cfg2 image within 1e-5 relative of the reference partition's (stored in tests/golden/full), and
+    the scheduler's own maintained total (fp32 sums in merge order, segment.cc:272-287) within 1e-5 of it too."""
+    from mergenet_b200 import BatchSegmenter, SegmenterOptions, synth
+    h, w = 1024, 2048
+    cp, sp, offs, _ = synth.cfg_cityscapes(h, w, seed=1001, n_shapes=400, rmax=120, soft=True, noise_seed=8)
+    seg = BatchSegmenter(1, h, w, 9, offs)
+    m, oc, n = seg.segment_host(cp[None], sp[None], SegmenterOptions(*cases.RECIPE_OPTS), clip=False)
+    g = np.load(os.path.join(GOLDEN, "full", "cfg2_1024x2048_seed1001.npz"))
+    lp = oracle_mod.total_logprob_from_scratch(m[0], [int(v) for v in oc[0][:n[0]]], cp, sp, offs, 1.0)
+    assert _logprob_close(lp, float(g["logprob"])), (lp, float(g["logprob"]))
+    assert _logprob_close(seg.total_logprob(0)[3], float(g["logprob"]))
+    seg.close()

@@ -68,3 +68,18 @@ def test_from_scratch_logprob_is_partition_function(oracle_mod):
     cm, ccls = oracle_mod.canonical_result(m, oc)
     b = oracle_mod.total_logprob_from_scratch(cm, ccls, cp, sp, offs, 1.0)
     assert abs(a - b) <= 1e-9 * abs(a)
+
+
+@pytest.mark.parametrize("name", ["cfg1_256x512_recipe", "cfg1_256x512_plain", "cfg3_256x512_oracle"])
+def test_oracle_equals_reference_fixtures_at_named_sizes(oracle_mod, name):
+    """The restatement against tests/golden/matrix (results of the unmodified reference at BASELINE.json's
+    named sizes; no reference tree needed at test time): mask, classes, from-scratch log-prob."""
+    import os
+    import matrix_cases
+    cp, sp, C, offs, opts = matrix_cases.load(name)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "matrix", name + ".npz"))
+    m, c, _ = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)
+    cm, cc = oracle_mod.canonical_result(m, c)
+    assert np.array_equal(cm, g["mask"]) and list(cc) == [int(v) for v in g["cls"]]
+    lp = oracle_mod.total_logprob_from_scratch(m, c, cp, sp, offs, opts[1])
+    assert abs(lp - float(g["logprob"])) <= 1e-5 * abs(float(g["logprob"]))
