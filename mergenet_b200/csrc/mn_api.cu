@@ -60,7 +60,9 @@ extern "C" int mn_device_count(void) {
 
 // ------------------------------------------------------------------------------------------------
 // kernels of this file
+#ifndef MN_MERGE_THREADS
 #define MN_MERGE_THREADS 512
+#endif
 __global__ void __launch_bounds__(MN_MERGE_THREADS, 1) mn_merge_kernel(const MnImage* imgs, int nimg, MnMergeArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   MnSm& sm = *reinterpret_cast<MnSm*>(smem_raw);
@@ -678,14 +680,69 @@ extern "C" int mn_plan_timings(mn_plan* p, mn_timings* o) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// drop-in symbol (segment.cc:742-752): one cached plan per thread, re-created when the shape changes
+// drop-in symbol (segment.cc:742-752): one cached plan per thread AND device, re-created when the shape changes
 struct PlanCache {
   mn_plan* plan = nullptr;
-  int H = 0, W = 0, C = 0, K = 0;
+  int H = 0, W = 0, C = 0, K = 0, device = -1;
   int offsets[2 * MN_MAX_K];
-  ~PlanCache() { /* process teardown: the driver may already be gone; leak on purpose */ }
+  void release() {
+    if (!plan) return;
+    // at process teardown the CUDA runtime may already be unloading: its calls then fail with
+    // cudaErrorCudartUnloading and there is nothing left to free; in a live process (a worker thread that
+    // exits, mn_shutdown()) the workspace goes back to the device
+    int d = 0;
+    if (cudaGetDevice(&d) == cudaSuccess) mn_plan_destroy(plan);
+    plan = nullptr;
+  }
+  ~PlanCache() { release(); }
 };
 static thread_local PlanCache g_cache;
+
+// scratch of the host-buffer post-pass entries (mask resize, COCO RLE): per thread, grow-only, own stream
+struct PostScratch {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  void* buf[3] = {nullptr, nullptr, nullptr};
+  size_t cap[3] = {0, 0, 0};
+  void release() {
+    int d = 0;
+    if (cudaGetDevice(&d) == cudaSuccess && device >= 0) {
+      for (int i = 0; i < 3; i++) cudaFree(buf[i]);
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+      if (stream) cudaStreamDestroy(stream);
+    }
+    for (int i = 0; i < 3; i++) { buf[i] = nullptr; cap[i] = 0; }
+    stream = nullptr; e0 = e1 = nullptr; device = -1;
+  }
+  // buffers of at least the given sizes on the caller's current device
+  bool ensure(size_t b0, size_t b1, size_t b2) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) return false;
+    if (device != d) {
+      release();
+      if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) { stream = nullptr; return false; }
+      if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { release(); return false; }
+      device = d;
+    }
+    const size_t need[3] = {b0, b1, b2};
+    for (int i = 0; i < 3; i++) {
+      if (need[i] <= cap[i]) continue;
+      cudaFree(buf[i]); buf[i] = nullptr; cap[i] = 0;
+      if (cudaMalloc(&buf[i], need[i]) != cudaSuccess) return false;
+      cap[i] = need[i];
+    }
+    return true;
+  }
+  ~PostScratch() { release(); }
+};
+static thread_local PostScratch g_post;
+
+extern "C" void mn_shutdown(void) {
+  g_cache.release();
+  g_post.release();
+}
 
 extern "C" void c_run_segmentation(float* class_pred, int class_dim, float* adj_pred, int offset_dim,
                                    int img_width, int img_height, int num_classes, int* offset_list,
@@ -694,32 +751,43 @@ extern "C" void c_run_segmentation(float* class_pred, int class_dim, float* adj_
   const long long N = (long long)img_width * img_height;
   if (output && N > 0) memset(output, 0, sizeof(int) * (size_t)N);
   if (object_class && N > 0) memset(object_class, 0xFF, sizeof(int) * (size_t)N);
+  auto fail = [&](int code) {
+    // The symbol returns void, like the reference's (which exit(1)s on its internal errors, cc:40-43,666-673):
+    // a caller that links it directly cannot see a status, so the failure is also reported on stderr.
+    g_last_error = code;
+    fprintf(stderr, "mergenet_b200: c_run_segmentation failed: %s (status %d); outputs left empty (mask 0, classes -1)\n",
+            mn_status_string(code), code);
+  };
   if (!class_pred || !adj_pred || !offset_list || !output || !object_class || class_dim != num_classes ||
       offset_dim <= 0 || offset_dim > MN_MAX_K) {
-    g_last_error = MN_STATUS_BAD_ARG;
+    fail(MN_STATUS_BAD_ARG);
     return;
   }
+  int device = 0;
+  if (cudaGetDevice(&device) != cudaSuccess) { fail(MN_STATUS_CUDA); return; }  // the caller's current device
   PlanCache& c = g_cache;
-  bool same = c.plan && c.H == img_height && c.W == img_width && c.C == num_classes && c.K == offset_dim &&
+  bool same = c.plan && c.device == device && c.H == img_height && c.W == img_width && c.C == num_classes && c.K == offset_dim &&
               memcmp(c.offsets, offset_list, sizeof(int) * 2 * offset_dim) == 0;
   if (!same) {
-    if (c.plan) { mn_plan_destroy(c.plan); c.plan = nullptr; }
-    int rc = mn_plan_create(&c.plan, 1, img_height, img_width, num_classes, offset_dim, offset_list, 0);
-    if (rc) { c.plan = nullptr; return; }
-    c.H = img_height; c.W = img_width; c.C = num_classes; c.K = offset_dim;
+    c.release();
+    int rc = mn_plan_create(&c.plan, 1, img_height, img_width, num_classes, offset_dim, offset_list, device);
+    if (rc) { c.plan = nullptr; fail(rc); return; }
+    c.H = img_height; c.W = img_width; c.C = num_classes; c.K = offset_dim; c.device = device;
     memcpy(c.offsets, offset_list, sizeof(int) * 2 * offset_dim);
   }
   int ninst = 0;
   mn_segment_batch_host(c.plan, 1, class_pred, adj_pred, output, object_class, &ninst, 0, sdb, omf, mlb);
+  cudaSetDevice(device);  // (the plan's device is the caller's; restated for symmetry with the batch entries)
   if (g_last_error != MN_STATUS_OK) {
     memset(output, 0, sizeof(int) * (size_t)N);
     memset(object_class, 0xFF, sizeof(int) * (size_t)N);
+    fail(g_last_error);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // the step after the path: masks at the image size, COCO RLE (mn_post.cuh)
-static float g_post_ms = 0.f;
+static thread_local float g_post_ms = 0.f;
 extern "C" float mn_post_last_ms(void) { return g_post_ms; }
 
 extern "C" int mn_resize_masks_nearest_device(const int* d_in, int B, int H, int W, int* d_out, int OH, int OW, void* stream) {
@@ -736,20 +804,18 @@ extern "C" int mn_resize_masks_nearest_host(const int* h_in, int B, int H, int W
   if (!h_in || !h_out || B <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0) { g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
-  int *di = nullptr, *dout = nullptr;
   const size_t nin = (size_t)B * H * W * 4, nout = (size_t)B * OH * OW * 4;
-  if (cudaMalloc(&di, nin) != cudaSuccess || cudaMalloc(&dout, nout) != cudaSuccess) { cudaFree(di); g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
-  cudaError_t e = cudaMemcpy(di, h_in, nin, cudaMemcpyHostToDevice);
-  cudaEventRecord(e0, 0);
-  if (e == cudaSuccess) e = mn_resize_nearest_launch(di, B, H, W, dout, OH, OW, 0);
-  cudaEventRecord(e1, 0);
-  if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  if (e == cudaSuccess) e = cudaMemcpy(h_out, dout, nout, cudaMemcpyDeviceToHost);
-  cudaEventElapsedTime(&g_post_ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(di); cudaFree(dout);
+  PostScratch& ps = g_post;  // scratch and stream are kept between calls (per thread, current device)
+  if (!ps.ensure(nin, nout, 0)) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  int* di = (int*)ps.buf[0]; int* dout = (int*)ps.buf[1];
+  cudaStream_t st = ps.stream;
+  cudaError_t e = cudaMemcpyAsync(di, h_in, nin, cudaMemcpyHostToDevice, st);
+  cudaEventRecord(ps.e0, st);
+  if (e == cudaSuccess) e = mn_resize_nearest_launch(di, B, H, W, dout, OH, OW, st);
+  cudaEventRecord(ps.e1, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, dout, nout, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) cudaEventElapsedTime(&g_post_ms, ps.e0, ps.e1);
   if (e != cudaSuccess) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
   return MN_STATUS_OK;
 }
@@ -764,25 +830,19 @@ extern "C" int mn_mask_to_coco_rle_host(const int* h_mask, int H, int W, int n, 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
   const size_t a = (size_t)H * W;
-  int* dm = nullptr; unsigned char* dc = nullptr; long long* dofs = nullptr;
-  if (cudaMalloc(&dm, a * 4) != cudaSuccess || cudaMalloc(&dc, (size_t)(cap > 0 ? cap : 1)) != cudaSuccess ||
-      cudaMalloc(&dofs, ((size_t)n + 1) * 8) != cudaSuccess) {
-    cudaFree(dm); cudaFree(dc); cudaFree(dofs);
-    g_last_error = MN_STATUS_CUDA;
-    return MN_STATUS_CUDA;
-  }
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  PostScratch& ps = g_post;
+  if (!ps.ensure(a * 4, (size_t)(cap > 0 ? cap : 1), ((size_t)n + 1) * 8)) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  int* dm = (int*)ps.buf[0]; unsigned char* dc = (unsigned char*)ps.buf[1]; long long* dofs = (long long*)ps.buf[2];
+  cudaStream_t st = ps.stream;
   long long total = 0;
-  cudaError_t e = cudaMemcpy(dm, h_mask, a * 4, cudaMemcpyHostToDevice);
-  cudaEventRecord(e0, 0);
-  if (e == cudaSuccess) e = mn_coco_rle_device(dm, H, W, n, dc, cap, dofs, &total, 0);
-  cudaEventRecord(e1, 0);
-  if (e == cudaSuccess) e = cudaMemcpy(offsets, dofs, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && total <= cap && total > 0) e = cudaMemcpy(counts, dc, (size_t)total, cudaMemcpyDeviceToHost);
-  cudaEventElapsedTime(&g_post_ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(dm); cudaFree(dc); cudaFree(dofs);
+  cudaError_t e = cudaMemcpyAsync(dm, h_mask, a * 4, cudaMemcpyHostToDevice, st);
+  cudaEventRecord(ps.e0, st);
+  if (e == cudaSuccess) e = mn_coco_rle_device(dm, H, W, n, dc, cap, dofs, &total, st);
+  cudaEventRecord(ps.e1, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(offsets, dofs, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && total <= cap && total > 0) e = cudaMemcpyAsync(counts, dc, (size_t)total, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) cudaEventElapsedTime(&g_post_ms, ps.e0, ps.e1);
   if (e != cudaSuccess) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
   if (total > cap) { offsets[n] = total; g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
   return MN_STATUS_OK;

@@ -152,6 +152,47 @@ struct MnImage {
 #define MN_REC_A(im, r) ((im).rec[2 * (size_t)(r)])
 #define MN_REC_B(im, r) (reinterpret_cast<float4*>((im).rec)[2 * (size_t)(r) + 1])
 #define MN_REC_LH(im, r) (*reinterpret_cast<int2*>(&(im).rec[2 * (size_t)(r)]))
+// One record = one 32-byte sector: both halves with ONE 256-bit request on the device (LDG.E.256 / STG.E.256,
+// sm_100): the scheduler's phases are priced in LSU requests as much as in round trips.
+#ifndef MN_OPT_LD256
+#define MN_OPT_LD256 1
+#endif
+MN_HD void mn_load_rec(const MnImage& im, int r, uint4* a, float4* b) {
+#if defined(__CUDA_ARCH__) && MN_OPT_LD256
+  uint32_t x0, x1, x2, x3, y0, y1, y2, y3;
+  asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3), "=r"(y0), "=r"(y1), "=r"(y2), "=r"(y3)
+               : "l"(im.rec + 2 * (size_t)r));  // (volatile: keeps its place between the block barriers)
+  *a = make_uint4(x0, x1, x2, x3);
+  *b = make_float4(__uint_as_float(y0), __uint_as_float(y1), __uint_as_float(y2), __uint_as_float(y3));
+#else
+  *a = MN_REC_A(im, r);
+  *b = MN_REC_B(im, r);
+#endif
+}
+MN_HD void mn_store_rec(const MnImage& im, int r, uint4 a, float4 b) {
+#if defined(__CUDA_ARCH__) && MN_OPT_LD256
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(im.rec + 2 * (size_t)r), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(__float_as_uint(b.x)),
+                  "r"(__float_as_uint(b.y)), "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w)) : "memory");
+#else
+  MN_REC_A(im, r) = a;
+  MN_REC_B(im, r) = b;
+#endif
+}
+// one 8-slot hash bucket (32 bytes)
+MN_HD void mn_load_bucket(const MnImage& im, uint32_t b, uint32_t* out) {
+#if defined(__CUDA_ARCH__) && MN_OPT_LD256
+  asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(out[0]), "=r"(out[1]), "=r"(out[2]), "=r"(out[3]), "=r"(out[4]), "=r"(out[5]), "=r"(out[6]), "=r"(out[7])
+               : "l"(im.hash + (size_t)b * 8));
+#else
+  const uint4* p = reinterpret_cast<const uint4*>(im.hash + (size_t)b * 8);
+  uint4 x = p[0], y = p[1];
+  out[0] = x.x; out[1] = x.y; out[2] = x.z; out[3] = x.w;
+  out[4] = y.x; out[5] = y.y; out[6] = y.z; out[7] = y.w;
+#endif
+}
 MN_HD uint32_t mn_pack_nc(int npix, int cls) { return (uint32_t)npix | ((uint32_t)cls << 24); }
 MN_HD int mn_nc_npix(uint32_t nc) { return (int)(nc & 0xFFFFFFu); }
 MN_HD int mn_nc_cls(uint32_t nc) { return (int)(nc >> 24); }

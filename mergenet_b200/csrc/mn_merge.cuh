@@ -227,6 +227,20 @@ MN_D void mn_sort_sb(MnSm& sm, int n2) {  // n2 = power of two, pads carry mp = 
 }
 MN_D int mn_pow2_ge(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
+// position from a shared counter, one atomic per group of converged lanes (all of them name the same counter)
+MN_D int mn_agg_inc(int* ctr) {
+#if defined(__CUDA_ARCH__)
+  const unsigned act = __activemask();
+  const int lane = threadIdx.x & 31, leader = __ffs(act) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(ctr, __popc(act));
+  base = __shfl_sync(act, base, leader);
+  return base + __popc(act & ((1u << lane) - 1u));
+#else
+  return MN_ATOMIC_ADD(ctr, 1);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // queue tree
 MN_D int mn_root_of(float mp) {
@@ -459,13 +473,14 @@ MN_D void mn_split_leaf(const MnImage& im, MnSm& sm, int root, int node, int lev
       if (c < 0) { mn_fail(im, MN_ERR_INTERNAL); continue; }
       uint4 e = im.q_ent[(size_t)c * MN_QCH + s];
       int rec = (int)e.y;
-      int2 lh = MN_REC_LH(im, rec);
-      float4 v = MN_REC_B(im, rec);
+      uint4 ra_; float4 v;
+      mn_load_rec(im, rec, &ra_, &v);
+      int2 lh = make_int2((int)ra_.x, (int)ra_.y);
       float emp = mn_u2f(e.x);
       int st = mn_entry_state(emp, (int)e.z, (int)e.w, lh, v);
       if (st == MN_K_UNGUARD) { v.z = -1.0f; MN_REC_B(im, rec) = v; }
       else if (st != MN_K_DROP) {  // the entry keeps its own key (a guard stays where it is)
-        int p = MN_ATOMIC_ADD(&sm.npr, 1);
+        int p = mn_agg_inc(&sm.npr);
         sm.sb_mp[p] = emp; sm.sb_lo[p] = (int)e.z; sm.sb_hi[p] = (int)e.w; sm.sb_rec[p] = rec;
         sm.sb_node[p] = base + mn_digit(root, level + 1, emp, (int)e.z, (int)e.w);
       }
@@ -585,11 +600,26 @@ MN_D int mn_exclusive_scan(MnSm& sm, const int* vals, int* out, int n) {
   for (int i = b; i < e; i++) ssum += vals[i];
   if (t < MN_SB) sm.w.ds.cnt[t] = ssum;
   MN_SYNC();
+#if defined(__CUDA_ARCH__)
+  if (t < 32) {  // warp 0: each lane scans a run of the per-thread sums, the runs are joined by a shuffle scan
+    const int lim = nt < MN_SB ? nt : MN_SB;
+    const int run = (lim + 31) / 32;
+    const int b2 = t * run, e2 = b2 + run < lim ? b2 + run : lim;
+    int s2 = 0;
+    for (int k = b2; k < e2; k++) s2 += sm.w.ds.cnt[k];
+    int incl = s2;
+    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if (t >= d) incl += o; }
+    int acc = incl - s2;
+    for (int k = b2; k < e2; k++) { int v = sm.w.ds.cnt[k]; sm.w.ds.cnt[k] = acc; acc += v; }
+    if (t == 31) sm.tmp3 = incl;
+  }
+#else
   if (MN_T0) {
     int acc = 0;
     for (int k = 0; k < nt && k < MN_SB; k++) { int v = sm.w.ds.cnt[k]; sm.w.ds.cnt[k] = acc; acc += v; }
     sm.tmp3 = acc;
   }
+#endif
   MN_SYNC();
   int acc = t < MN_SB ? sm.w.ds.cnt[t] : 0;
   for (int i = b; i < e; i++) { int v = vals[i]; out[i] = acc; acc += v; }
@@ -597,7 +627,7 @@ MN_D int mn_exclusive_scan(MnSm& sm, const int* vals, int* out, int n) {
   return sm.tmp3;
 }
 
-MN_D void mn_hot_update(const MnImage& im, MnSm& sm, int cut);
+MN_D void mn_hot_update(const MnImage& im, MnSm& sm, int cut, bool lead_sync = true, bool trail_sync = true);
 MN_D void mn_push_entry(MnSm& sm, float mp, int lo, int hi, int rec);
 // Refill the (empty) hot buffer.  Afterwards: hot holds every entry popping before-or-at `bound`.
 MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
@@ -634,13 +664,14 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
         if (c < 0) { mn_fail(im, MN_ERR_INTERNAL); continue; }
         uint4 e = im.q_ent[(size_t)c * MN_QCH + s];
         int rec = (int)e.y;
-        int2 lh = MN_REC_LH(im, rec);
-        float4 v = MN_REC_B(im, rec);
+        uint4 ra_; float4 v;
+        mn_load_rec(im, rec, &ra_, &v);
+        int2 lh = make_int2((int)ra_.x, (int)ra_.y);
         float emp = mn_u2f(e.x);
         int st = mn_entry_state(emp, (int)e.z, (int)e.w, lh, v);
         if (st == MN_K_UNGUARD) { v.z = -1.0f; MN_REC_B(im, rec) = v; }
         else if (st != MN_K_DROP) {
-          int p = MN_ATOMIC_ADD(&sm.npr, 1);
+          int p = mn_agg_inc(&sm.npr);
           if (p < MN_SB) { sm.sb_mp[p] = emp; sm.sb_lo[p] = (int)e.z; sm.sb_hi[p] = (int)e.w; sm.sb_rec[p] = rec; }
         }
       }
@@ -687,7 +718,7 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
       float mp; int lo, hi, rec;
       mn_decode_init(A, im.init_keys[sc + i], &mp, &lo, &hi, &rec);
       bool take = (w < 0) || mn_before(mp, lo, hi, lmp, llo, lhi);
-      if (take) MN_ATOMIC_ADD(&sm.tmp2, 1);
+      if (take) mn_agg_inc(&sm.tmp2);
     }
     MN_SYNC();
     const int ntake = sm.tmp2;
@@ -701,8 +732,9 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
     MN_FOR(i, ntake) {
       float mp; int lo, hi, rec;
       mn_decode_init(A, im.init_keys[sc + i], &mp, &lo, &hi, &rec);
-      int2 lh = MN_REC_LH(im, rec);
-      float4 v = MN_REC_B(im, rec);
+      uint4 ra_; float4 v;
+      mn_load_rec(im, rec, &ra_, &v);
+      int2 lh = make_int2((int)ra_.x, (int)ra_.y);
       int st = mn_entry_state(mp, lo, hi, lh, v);
       if (st == MN_K_UNGUARD) { v.z = -1.0f; MN_REC_B(im, rec) = v; st = MN_K_DROP; }
       int p = nleaf + i;
@@ -740,8 +772,9 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
     MN_FOR(i, nleaf + ntake) {
       if (sm.sb_mp[i] > MN_NEG_INF) {
         const int rec = sm.sb_rec[i];
-        const int2 lh = MN_REC_LH(im, rec);
-        float4 v = MN_REC_B(im, rec);
+        uint4 ra_; float4 v;
+        mn_load_rec(im, rec, &ra_, &v);
+        const int2 lh = make_int2((int)ra_.x, (int)ra_.y);
         if (mn_entry_state(sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i], lh, v) == MN_K_REQUEUE) {
           v.z = v.w;
           MN_REC_B(im, rec) = v;
@@ -900,13 +933,21 @@ MN_D uint32_t mn_own_bits(const MnMergeArgs& A, int pix, int r) {
 MN_D void mn_push_entry(MnSm& sm, float mp, int lo, int hi, int rec) {
   MN_WATCH(rec, "push mp %.9g key %d %d", mp, lo, hi);
   bool cold = !sm.cold_empty && mn_before(sm.b_mp, sm.b_lo, sm.b_hi, mp, lo, hi);
-  if (cold) {
-    int p = MN_ATOMIC_ADD(&sm.nins, 1);
-    sm.ins_mp[p] = mp; sm.ins_lo[p] = lo; sm.ins_hi[p] = hi; sm.ins_rec[p] = rec;
-  } else {
-    int p = MN_ATOMIC_ADD(&sm.nne, 1);
-    sm.ne_mp[p] = mp; sm.ne_lo[p] = lo; sm.ne_hi[p] = hi; sm.ne_rec[p] = rec;
-  }
+#if defined(__CUDA_ARCH__)
+  // the converged lanes split into the cold and the hot-bound group; each group takes its slots with one atomic
+  const unsigned act = __activemask();
+  const unsigned mc = __ballot_sync(act, cold);
+  const unsigned mine = cold ? mc : (act & ~mc);
+  const int lane = threadIdx.x & 31, leader = __ffs(mine) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(cold ? &sm.nins : &sm.nne, __popc(mine));
+  base = __shfl_sync(mine, base, leader);
+  const int p = base + __popc(mine & ((1u << lane) - 1u));
+#else
+  const int p = MN_ATOMIC_ADD(cold ? &sm.nins : &sm.nne, 1);
+#endif
+  if (cold) { sm.ins_mp[p] = mp; sm.ins_lo[p] = lo; sm.ins_hi[p] = hi; sm.ins_rec[p] = rec; }
+  else { sm.ne_mp[p] = mp; sm.ne_lo[p] = lo; sm.ne_hi[p] = hi; sm.ne_rec[p] = rec; }
 }
 // Store priority `mp` on a record whose guard priority is `q` (-1: no queued entry): queue an entry
 // unless an earlier-popping one already guards the record.  Returns the new guard priority.
@@ -919,12 +960,7 @@ MN_D float mn_store_priority(MnSm& sm, float mp, float q, int lo, int hi, int re
 }
 
 // ---- hash bucket helpers on buckets already in registers ------------------------------------------
-MN_D void mn_load_bucket4(const MnImage& im, uint32_t b, uint32_t* out) {
-  const uint4* p = reinterpret_cast<const uint4*>(im.hash + (size_t)b * 8);
-  uint4 x = p[0], y = p[1];
-  out[0] = x.x; out[1] = x.y; out[2] = x.z; out[3] = x.w;
-  out[4] = y.x; out[5] = y.y; out[6] = y.z; out[7] = y.w;
-}
+MN_D void mn_load_bucket4(const MnImage& im, uint32_t b, uint32_t* out) { mn_load_bucket(im, b, out); }
 // global slot index of value `val` in the two loaded buckets (-1: not there)
 MN_D int mn_bucket_find_val(const MnHashPos& p, const uint32_t* bk /*16*/, uint32_t val) {
   for (int s = 0; s < 8; s++) if (bk[s] == val) return (int)(p.b1 * 8 + s);
@@ -946,9 +982,9 @@ MN_D void mn_ovf_erase(MnSm& sm, int rec) {
 MN_D int mn_hash_insert_hint(const MnImage& im, MnSm& sm, int lo, int hi, int rec, int islot) {
   MnHashPos p = mn_hash_pos(im.hash_nbuckets, lo, hi);
   uint32_t val = (p.fp << MN_HASH_FP_SHIFT) | (uint32_t)(rec + 1);
-  if (islot >= 0 && MN_ATOMIC_CAS(&im.hash[islot], 0u, val) == 0u) return islot;
   uint32_t* bk1 = im.hash + (size_t)p.b1 * 8;
   uint32_t* bk2 = im.hash + (size_t)p.b2 * 8;
+  if (islot >= 0 && MN_ATOMIC_CAS(&im.hash[islot], 0u, val) == 0u) return islot;
   for (int w = 0; w < 2; w++) {
     uint32_t* bk = w ? bk2 : bk1;
     for (int s = 0; s < 8; s++)
@@ -976,8 +1012,8 @@ MN_D void mn_plan_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const
     int i = p0 + ii;
     int j = sm.w.pr.cand[i], t = sm.w.pr.t[i];
     int a = sm.c_surv[j], b = sm.c_abs[j];
-    const uint4 ta = MN_REC_A(im, t);  // one 32-byte sector: key, hash slot, sums, priorities
-    const float4 v = MN_REC_B(im, t);
+    uint4 ta; float4 v;
+    mn_load_rec(im, t, &ta, &v);  // one 32-byte sector: key, hash slot, sums, priorities
     const int2 lh = make_int2((int)ta.x, (int)ta.y);
     const float tdiff = mn_u2f(ta.w);
     int x = lh.x == b ? lh.y : lh.x;
@@ -1005,9 +1041,10 @@ MN_D void mn_plan_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const
     }
     float4 uv = make_float4(0.f, 0.f, 0.f, 0.f); float ud = 0.f;
     if (c0 >= 0) {  // fingerprint matches: key and values of (up to) two candidates in one round trip
-      uint4 a0 = MN_REC_A(im, c0); float4 v0 = MN_REC_B(im, c0);
+      uint4 a0; float4 v0;
+      mn_load_rec(im, c0, &a0, &v0);
       uint4 a1 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u); float4 v1 = v0;
-      if (c1 >= 0) { a1 = MN_REC_A(im, c1); v1 = MN_REC_B(im, c1); }
+      if (c1 >= 0) mn_load_rec(im, c1, &a1, &v1);
       if ((int)a0.x == nlo && (int)a0.y == nhi) { u = c0; uv = v0; ud = mn_u2f(a0.w); }
       else if (c1 >= 0 && (int)a1.x == nlo && (int)a1.y == nhi) { u = c1; uv = v1; ud = mn_u2f(a1.w); }
     }
@@ -1069,8 +1106,8 @@ MN_D void mn_commit_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, int
       MN_WATCH(t, "adopt mp %.9g q_old %.9g q_new %.9g key %d %d", mp, sm.w.pr.q[i], q, sm.w.pr.lo[i], sm.w.pr.hi[i]);
       MN_REC_LH(im, t) = make_int2(sm.w.pr.lo[i], sm.w.pr.hi[i]);  // (the hash verifies keys through the record)
       const int hs = mn_hash_insert_hint(im, sm, sm.w.pr.lo[i], sm.w.pr.hi[i], t, sm.w.pr.islot[i]);
-      MN_REC_A(im, t) = make_uint4((uint32_t)sm.w.pr.lo[i], (uint32_t)sm.w.pr.hi[i], (uint32_t)hs, mn_f2u(sm.w.pr.diff[i]));
-      MN_REC_B(im, t) = make_float4(sm.w.pr.oml[i], sm.w.pr.same[i], q, mp);
+      mn_store_rec(im, t, make_uint4((uint32_t)sm.w.pr.lo[i], (uint32_t)sm.w.pr.hi[i], (uint32_t)hs, mn_f2u(sm.w.pr.diff[i])),
+                   make_float4(sm.w.pr.oml[i], sm.w.pr.same[i], q, mp));
     }
   }
 }
@@ -1092,25 +1129,31 @@ MN_D void mn_commit_merge_object(const MnImage& im, MnSm& sm, const MnMergeArgs&
 // Merge the new hot-bound entries (ne_*) into hot after dropping the first `cut` hot entries.
 // Output goes to the other hot buffer; what does not fit spills to the insert buffer and the bound
 // moves up to the last kept entry.
-MN_D void mn_hot_update(const MnImage& im, MnSm& sm, int cut) {
-  MN_SYNC();
+// lead_sync / trail_sync: whether the caller needs the barrier before / after (the round loop has its own on
+// both sides: the commit phase ends with one, the loop starts with one)
+MN_D void mn_hot_update(const MnImage& im, MnSm& sm, int cut, bool lead_sync, bool trail_sync) {
+  if (lead_sync) MN_SYNC();
   const int m = sm.nne;
   const int nh = sm.nhot - cut;
   if (m == 0 && cut == 0) return;
   if (m > 0) {
-    if (m <= MN_RANK_MAX) {  // rank by brute force
+    if (m <= MN_RANK_MAX) {  // rank by brute force; the ranked entry goes straight to its place (ne is read-only here)
       MN_FOR(i, m) {
+        const float mp = sm.ne_mp[i]; const int lo = sm.ne_lo[i], hi = sm.ne_hi[i];
+        const unsigned long long ti = mn_tie(lo, hi);
         int rk = 0;
         for (int q = 0; q < m; q++) {
-          if (q == i) continue;
-          bool qb = mn_before(sm.ne_mp[q], sm.ne_lo[q], sm.ne_hi[q], sm.ne_mp[i], sm.ne_lo[i], sm.ne_hi[i]);
-          bool ib = mn_before(sm.ne_mp[i], sm.ne_lo[i], sm.ne_hi[i], sm.ne_mp[q], sm.ne_lo[q], sm.ne_hi[q]);
-          if (qb || (!ib && q < i)) rk++;
+          const float qmp = sm.ne_mp[q];
+          // q pops before i: higher priority, or the same priority and the smaller tie (ties of equal keys: index)
+          bool before = qmp > mp;
+          if (qmp == mp) {
+            const unsigned long long tq = mn_tie(sm.ne_lo[q], sm.ne_hi[q]);
+            before = tq < ti || (tq == ti && q < i);
+          }
+          rk += before ? 1 : 0;
         }
-        sm.ne_pos[i] = rk;
+        sm.sb_mp[rk] = mp; sm.sb_lo[rk] = lo; sm.sb_hi[rk] = hi; sm.sb_rec[rk] = sm.ne_rec[i];
       }
-      MN_SYNC();
-      MN_FOR(i, m) { int p = sm.ne_pos[i]; sm.sb_mp[p] = sm.ne_mp[i]; sm.sb_lo[p] = sm.ne_lo[i]; sm.sb_hi[p] = sm.ne_hi[i]; sm.sb_rec[p] = sm.ne_rec[i]; }
       MN_SYNC();
     } else {
       int n2 = mn_pow2_ge(m);
@@ -1155,7 +1198,7 @@ MN_D void mn_hot_update(const MnImage& im, MnSm& sm, int cut) {
     }
     sm.nne = 0;
   }
-  MN_SYNC();
+  if (trail_sync) MN_SYNC();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1168,8 +1211,9 @@ MN_D void mn_stage_candidates(const MnImage& im, MnSm& sm, const MnMergeArgs& A,
     const int j = w >> 2, role = w & 3;
     const int rec = HOT_REC(j), lo = HOT_LO(j), hi = HOT_HI(j);
     if (role == 0) {  // the record: one 32-byte sector
-      const uint4 ra = MN_REC_A(im, rec);
-      sm.c_val[j] = MN_REC_B(im, rec);
+      uint4 ra; float4 rb;
+      mn_load_rec(im, rec, &ra, &rb);
+      sm.c_val[j] = rb;
       sm.c_lh[j] = make_int2((int)ra.x, (int)ra.y); sm.c_eslot[j] = (int)ra.z; sm.c_rdiff[j] = mn_u2f(ra.w);
       sm.c_rec[j] = rec; sm.c_key[j] = HOT_MP(j); sm.c_lo[j] = lo; sm.c_hi[j] = hi;
       sm.c_kind[j] = MN_K_DROP; sm.c_npairs[j] = 0; sm.c_pfill[j] = 0; sm.c_maxnew[j] = 0; sm.c_conflict[j] = 0;
@@ -1181,7 +1225,8 @@ MN_D void mn_stage_candidates(const MnImage& im, MnSm& sm, const MnMergeArgs& A,
       const float mp = HOT_MP(j);
       int d = 0;
       for (int i = 0; i < j; i++) {
-        const bool same = HOT_REC(i) == rec && HOT_MP(i) == mp;
+        if (HOT_REC(i) != rec) continue;  // (one shared-memory read per earlier entry; the rest only on a hit)
+        const bool same = HOT_MP(i) == mp;
         d |= same ? (1 | ((HOT_LO(i) == lo && HOT_HI(i) == hi) ? 2 : 0)) : 0;
       }
       sm.c_dup[j] = d;
@@ -1746,65 +1791,108 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     MN_FOR(i, MN_CT) { sm.ct_obj[i] = -1; sm.ct_w[i] = INT_MAX; sm.ct_r[i] = INT_MAX; }
     MN_SYNC();
     MN_TOC(MN_CY_SEL_STAGE);
+#if defined(__CUDA_ARCH__)
+    // classify (one lane per candidate) and the capacity cut by pixels run back to back in warp 0: no block
+    // barrier between them
+    if (threadIdx.x < 32) {
+      if ((int)threadIdx.x < ncand0) mn_classify(im, sm, A, c_clp, (int)threadIdx.x);
+      __syncwarp();
+    }
+#else
     MN_FOR(j, ncand0) mn_classify(im, sm, A, c_clp, j);
-    MN_SYNC();
-    // ---- phase 2: merged class vectors; capacity cut by pixels ----
-    mn_stage_merged_clp(sm, A, c_clp, ncand0);
+#endif
+    // ---- phase 2: capacity cut by pixels ----
     mn_pass_capacity(sm, ncand0, sm.c_nb, sm.c_pwbase, MN_PW, true);
     MN_SYNC();
     if (sm.solo) {
       const int f = sm.first;
       if (mn_solo_needs_gc(im, sm, A, f)) continue;
       mn_consume_unguard(im, sm, f);
+      mn_stage_merged_clp(sm, A, c_clp, ncand0);
       mn_solo_merge(im, sm, A, c_clp, f);
       MN_TOC(MN_CY_SOLO);
       continue;
     }
     MN_TOC(MN_CY_SEL_CLASS);
-    // ---- phase 3: pixels of the absorbed objects, their live masks, pair counts ----
+    // ---- phase 3: pixels of the absorbed objects, their live masks, and -- optimistically -- the pair list
+    //      itself: slots come from one counter (a warp takes its slots with one atomic); only when the pairs
+    //      of the window exceed the work list does the capacity cut by pairs (below) redo the list ----
     {
       const int npw = sm.npw, nm = sm.nm;
-      MN_FOR(i, npw) {
-        int a = 0, bnd = nm;  // last e with m_base[e] <= i
-        while (a + 1 < bnd) { int mid = (a + bnd) >> 1; if (sm.m_base[mid] <= i) a = mid; else bnd = mid; }
-        const int j = sm.m_list[a], idx = i - sm.m_base[a];
-        const int b = sm.c_abs[j];
-        int pix; uint32_t m;
-        if (sm.c_nb[j] == 1) { pix = b; m = sm.c_obj[j][b == sm.c_lo[j] ? 0 : 1].w; }
-        else { pix = im.pix_pool[sm.c_ptrb[j] + idx]; m = im.obj[pix].w; }
-        m &= ~mn_own_bits(A, pix, sm.c_rec[j]);
-        const int cnt = MN_POPC(m);
-        sm.pw_pix[i] = pix; sm.pw_mask[i] = m; sm.pw_cand[i] = j; sm.pw_cnt[i] = cnt;
-        if (cnt) MN_ATOMIC_ADD(&sm.c_npairs[j], cnt);
+#if defined(__CUDA_ARCH__)
+      const int lane = threadIdx.x & 31;
+      for (int i0 = (int)(threadIdx.x & ~31u); i0 < npw; i0 += MN_NT) {
+        const int i = i0 + lane;
+#else
+      for (int i = 0; i < npw; i++) {
+#endif
+        int cnt = 0, pix = 0, j = 0; uint32_t m = 0;
+        if (i < npw) {
+          int a = 0, bnd = nm;  // last e with m_base[e] <= i
+          while (a + 1 < bnd) { int mid = (a + bnd) >> 1; if (sm.m_base[mid] <= i) a = mid; else bnd = mid; }
+          j = sm.m_list[a];
+          const int idx = i - sm.m_base[a];
+          const int b = sm.c_abs[j];
+          if (sm.c_nb[j] == 1) { pix = b; m = sm.c_obj[j][b == sm.c_lo[j] ? 0 : 1].w; }
+          else { pix = im.pix_pool[sm.c_ptrb[j] + idx]; m = im.obj[pix].w; }
+          m &= ~mn_own_bits(A, pix, sm.c_rec[j]);
+          cnt = MN_POPC(m);
+          sm.pw_pix[i] = pix; sm.pw_mask[i] = m; sm.pw_cand[i] = j; sm.pw_cnt[i] = cnt;
+          if (cnt) MN_ATOMIC_ADD(&sm.c_npairs[j], cnt);
+        }
+#if defined(__CUDA_ARCH__)
+        const int incl = mn_wscan_incl(cnt, lane);
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == 31 && total) base = atomicAdd(&sm.npr, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int slot = base + incl - cnt;
+#else
+        int slot = sm.npr; sm.npr += cnt;
+#endif
+        if (cnt && slot + cnt <= MN_WL) {
+          while (m) {
+            int bit = 31 - MN_CLZ(m);
+            m &= ~(1u << bit);
+            sm.w.pr.cand[slot] = j; sm.w.pr.t[slot] = mn_rec_of_bit(A, pix, bit);
+            slot++;
+          }
+        }
       }
+      mn_stage_merged_clp(sm, A, c_clp, ncand0);
     }
     MN_SYNC();
     MN_TOC(MN_CY_SEL_PIX);
-    mn_pass_capacity(sm, sm.ncand, sm.c_npairs, sm.c_pbase, MN_WL, false);  // capacity cut by pairs
-    MN_SYNC();
-    if (sm.solo) {
-      const int f = sm.first;
-      if (mn_solo_needs_gc(im, sm, A, f)) continue;
-      mn_consume_unguard(im, sm, f);
-      mn_solo_merge(im, sm, A, c_clp, f);
-      MN_TOC(MN_CY_SOLO);
-      continue;
+    if (sm.npr > MN_WL) {  // (rare: 1-2 % of the rounds) the window's pairs do not fit: cut it, list the pairs again
+      MN_SYNC();
+      mn_pass_capacity(sm, sm.ncand, sm.c_npairs, sm.c_pbase, MN_WL, false);  // capacity cut by pairs
+      MN_SYNC();
+      if (sm.solo) {
+        const int f = sm.first;
+        if (mn_solo_needs_gc(im, sm, A, f)) continue;
+        mn_consume_unguard(im, sm, f);
+        mn_solo_merge(im, sm, A, c_clp, f);
+        MN_TOC(MN_CY_SOLO);
+        continue;
+      }
+      const int ncand_c = sm.ncand, npw = sm.npw;
+      MN_FOR(i, npw) {
+        const int j = sm.pw_cand[i];
+        if (j >= ncand_c) continue;
+        uint32_t m = sm.pw_mask[i];
+        const int cnt = sm.pw_cnt[i];
+        if (!cnt) continue;
+        int slot = sm.c_pbase[j] + MN_ATOMIC_ADD(&sm.c_pfill[j], cnt);
+        while (m) {
+          int bit = 31 - MN_CLZ(m);
+          m &= ~(1u << bit);
+          sm.w.pr.cand[slot] = j; sm.w.pr.t[slot] = mn_rec_of_bit(A, sm.pw_pix[i], bit);
+          slot++;
+        }
+      }
+      MN_SYNC();
     }
     const int ncand = sm.ncand, npr = sm.npr, npw = sm.npw;
-    MN_FOR(i, npw) {
-      const int j = sm.pw_cand[i];
-      if (j >= ncand) continue;
-      uint32_t m = sm.pw_mask[i];
-      const int cnt = sm.pw_cnt[i];
-      if (!cnt) continue;
-      int slot = sm.c_pbase[j] + MN_ATOMIC_ADD(&sm.c_pfill[j], cnt);
-      while (m) {
-        int bit = 31 - MN_CLZ(m);
-        m &= ~(1u << bit);
-        sm.w.pr.cand[slot] = j; sm.w.pr.t[slot] = mn_rec_of_bit(A, sm.pw_pix[i], bit);
-        slot++;
-      }
-    }
     MN_SYNC();
     MN_TOC(MN_CY_PAIRLIST);
     // ---- phase 4: plan ----
@@ -1886,7 +1974,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     MN_SYNC();
     MN_TOC(MN_CY_COMMIT);
     // ---- phase 8: queue maintenance ----
-    mn_hot_update(im, sm, sm.cutpos);
+    mn_hot_update(im, sm, sm.cutpos, false, false);  // (barriers: the one above, and the one the loop starts with)
     MN_TOC(MN_CY_HOT);
   }
   MN_SYNC();
