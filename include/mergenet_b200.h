@@ -40,14 +40,23 @@ enum {
  *   offset_list  offset_dim x 2 int32 (row delta, col delta)   (segment.cc:166-169)
  *   output       H x W int32, fully overwritten: 0 = class-0 objects, 1..n = instances
  *   object_class H*W int32: -1 everywhere, then the class of label k at [k-1] (segment.cc:497-509)
- * All buffers are HOST memory owned by the caller.  Returns nothing, like the reference; unlike
- * the reference it never calls exit(): on failure the outputs are left as (0, -1) and the code is
- * readable through mn_last_error().  Nothing is printed.
+ * All buffers are HOST memory owned by the caller.  The work runs on the calling thread's CURRENT CUDA
+ * device (cudaGetDevice), with one workspace cached per thread and reused while the shape stays the same
+ * (freed when the thread exits, or by mn_shutdown()).  Returns nothing, like the reference; unlike the
+ * reference it never calls exit() (segment.cc:40-43,666-673): on failure the outputs are left as (0, -1),
+ * the code is readable through mn_last_error(), and -- because a caller that links this void symbol directly
+ * (the reference's own c_segment.pyx) cannot see a status -- one line naming the status goes to stderr.
+ * Nothing is printed on success (the reference's progress lines, segment.cc:540-569, are not reproduced).
+ * Shape limits: those of mn_plan_create below.
  */
 void c_run_segmentation(float* class_pred, int class_dim, float* adj_pred, int offset_dim,
                         int img_width, int img_height, int num_classes, int* offset_list,
                         int* output, int* object_class, float same_different_bias,
                         float object_merge_factor, float merge_logprob_bias);
+
+/* Frees what the calling thread cached for the host-buffer entries above and below (the drop-in's workspace,
+ * the post-pass scratch).  Optional: thread exit does the same. */
+void mn_shutdown(void);
 
 /* Status of the last call on this thread, and a static description of a status code. */
 int mn_last_error(void);

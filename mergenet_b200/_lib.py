@@ -16,7 +16,7 @@ SOURCES = ["mn_api.cu", "mn_edge.cuh", "mn_merge.cuh", "mn_post.cuh", "mn_layout
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-fmad=false"]
 
-EXPORTS = ["c_run_segmentation", "mn_last_error", "mn_status_string", "mn_device_count",
+EXPORTS = ["c_run_segmentation", "mn_shutdown", "mn_last_error", "mn_status_string", "mn_device_count",
            "mn_workspace_bytes_per_image", "mn_plan_create", "mn_plan_destroy",
            "mn_segment_batch_device", "mn_segment_batch_host", "mn_plan_image_stats",
            "mn_plan_timings", "mn_plan_image_logprob", "mn_debug_edge_dump", "mn_debug_libm", "mn_debug_edge_bench",
@@ -98,6 +98,8 @@ def lib():
     L.c_run_segmentation.restype = None
     L.c_run_segmentation.argtypes = [_F, ctypes.c_int, _F, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, _I, _I, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float]
+    L.mn_shutdown.restype = None
+    L.mn_shutdown.argtypes = []
     L.mn_last_error.restype = ctypes.c_int
     L.mn_status_string.restype = ctypes.c_char_p
     L.mn_status_string.argtypes = [ctypes.c_int]

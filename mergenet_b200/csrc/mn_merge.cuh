@@ -40,13 +40,17 @@
 #include "mn_common.h"
 #include "mn_layout.h"
 
-#define MN_H 32          // candidates per round
+#ifndef MN_H
+#define MN_H 32          // candidates per round (<= 64)
+#endif
 #define MN_PW 1024       // pixel work-list capacity
 #define MN_CW 64         // queue-chunk work-list capacity
 #define MN_WL 960        // (candidate, record) pair work-list capacity
 #define MN_HC 1024       // hot capacity
-#define MN_IC 2048       // insert-buffer capacity
 #define MN_NE 1024       // new hot-bound entries per round (>= MN_WL + MN_H, <= MN_SB)
+#ifndef MN_IC
+#define MN_IC 2048       // insert-buffer capacity
+#endif
 #define MN_SB 1024       // sort buffer capacity
 #ifndef MN_LEAFCAP
 #define MN_LEAFCAP 512   // tree leaves larger than this are split before they are loaded
@@ -1474,14 +1478,24 @@ MN_D void mn_consume_unguard(const MnImage& im, MnSm& sm, int n) {
 // On the device they run on warp 0 with one lane per candidate (ballots and shuffles: a thread-0
 // loop over shared memory costs ~30 cycles per access); on the host they are plain loops.
 #if defined(__CUDA_ARCH__)
+// Warp 0 runs the scans with MN_NH candidates per lane: lane l holds the candidates l, l + 32, ...; masks over
+// the window are 64 bits wide.
+#define MN_NH ((MN_H + 31) / 32)
+#if MN_NH > 2
+#error "the accept / capacity passes hold at most two candidates per lane (MN_H <= 64)"
+#endif
+typedef unsigned long long mn_wmask;
+MN_D mn_wmask mn_ballot_w(const bool* p) {
+  mn_wmask m = 0;
+#pragma unroll
+  for (int h = 0; h < MN_NH; h++) m |= (mn_wmask)__ballot_sync(0xffffffffu, p[h]) << (32 * h);
+  return m;
+}
+MN_D int mn_ffs_w(mn_wmask m) { return __ffsll((long long)m) - 1; }  // -1: empty
+MN_D mn_wmask mn_below_w(int n) { return n >= 64 ? ~0ull : ((1ull << n) - 1ull); }
 MN_D int mn_wscan_incl(int v, int lane) {
   for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += o; }
   return v;
-}
-MN_D unsigned long long mn_wscan_max_excl(unsigned long long v, int lane) {  // exclusive prefix maximum
-  for (int d = 1; d < 32; d <<= 1) { unsigned long long o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d && o > v) v = o; }
-  unsigned long long e = __shfl_up_sync(0xffffffffu, v, 1);
-  return lane == 0 ? 0ull : e;
 }
 #endif
 
@@ -1495,31 +1509,48 @@ MN_D void mn_pass_capacity(MnSm& sm, int n0, const int* vals, int* base, int cap
 #if defined(__CUDA_ARCH__)
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
-  const int k = lane < n0 ? sm.c_kind[lane] : MN_K_DROP;
-  const bool isM = k == MN_K_MERGE;
-  const int v = isM ? vals[lane] : 0;
-  const int incl = mn_wscan_incl(v, lane);
-  const uint32_t evm = __ballot_sync(0xffffffffu, k == MN_K_RESTORE || k == MN_K_MERGE);
-  const uint32_t rqm = __ballot_sync(0xffffffffu, k == MN_K_REQUEUE);
-  const uint32_t mm = __ballot_sync(0xffffffffu, isM);
-  const uint32_t om = __ballot_sync(0xffffffffu, isM && incl > cap);
-  const int f = pixels ? (evm ? __ffs(evm) - 1 : -1) : sm.first;
+  int k[MN_NH], v[MN_NH], incl[MN_NH];
+  bool isM[MN_NH], ev[MN_NH], rq[MN_NH], ov[MN_NH];
+  int carry = 0;
+#pragma unroll
+  for (int h = 0; h < MN_NH; h++) {
+    const int j = lane + 32 * h;
+    k[h] = j < n0 ? sm.c_kind[j] : MN_K_DROP;
+    isM[h] = k[h] == MN_K_MERGE;
+    v[h] = isM[h] ? vals[j] : 0;
+    incl[h] = mn_wscan_incl(v[h], lane) + carry;
+    carry = __shfl_sync(0xffffffffu, incl[h], 31);
+    ev[h] = k[h] == MN_K_RESTORE || k[h] == MN_K_MERGE;
+    rq[h] = k[h] == MN_K_REQUEUE;
+    ov[h] = isM[h] && incl[h] > cap;
+  }
+  const mn_wmask evm = mn_ballot_w(ev), rqm = mn_ballot_w(rq), mm = mn_ballot_w(isM), om = mn_ballot_w(ov);
+  const int f = pixels ? mn_ffs_w(evm) : sm.first;
   int n = n0, solo = 0;
   if (om) {
-    const int jo = __ffs(om) - 1;
+    const int jo = mn_ffs_w(om);
     n = jo;
-    const int nrq = __popc(rqm & ((1u << jo) - 1u));
+    const int nrq = __popcll(rqm & mn_below_w(jo));
     solo = (jo == f && nrq == 0) ? 1 : 0;
   }
-  const uint32_t below = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
-  const int tot = n > 0 ? __shfl_sync(0xffffffffu, incl, n - 1) : 0;
-  if (isM && lane < n) {
-    base[lane] = incl - v;
-    if (pixels) { const int mi = __popc(mm & ((1u << lane) - 1u)); sm.m_list[mi] = lane; sm.m_base[mi] = incl - v; }
+  int tot = 0;  // pixels / pairs of the members below the cut
+#pragma unroll
+  for (int h = 0; h < MN_NH; h++) {
+    const int src = n - 1 - 32 * h;
+    const int t = __shfl_sync(0xffffffffu, incl[h], src & 31);
+    if (src >= 0 && src < 32) tot = t;
+  }
+#pragma unroll
+  for (int h = 0; h < MN_NH; h++) {
+    const int j = lane + 32 * h;
+    if (isM[h] && j < n) {
+      base[j] = incl[h] - v[h];
+      if (pixels) { const int mi = __popcll(mm & mn_below_w(j)); sm.m_list[mi] = j; sm.m_base[mi] = incl[h] - v[h]; }
+    }
   }
   if (lane == 0) {
     if (pixels) {
-      const int nm = __popc(mm & below);
+      const int nm = __popcll(mm & mn_below_w(n));
       sm.m_base[nm] = tot; sm.nm = nm; sm.first = f; sm.npw = tot; sm.npr = 0;
     } else {
       if (n < n0) sm.st_cut_cap++;
@@ -1554,62 +1585,91 @@ MN_D void mn_pass_accept(const MnImage& im, MnSm& sm, int ncand, int npr) {
 #if defined(__CUDA_ARCH__)
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
-  const int k = lane < ncand ? sm.c_kind[lane] : MN_K_DROP;
-  const bool member = k != MN_K_DROP;
-  const bool event = k == MN_K_RESTORE || k == MN_K_MERGE;
-  const uint32_t memm = __ballot_sync(0xffffffffu, member);
-  const uint32_t lt = (1u << lane) - 1u;
-  const unsigned long long exmax = mn_wscan_max_excl(member ? sm.c_maxnew[lane] : 0ull, lane);
-  const bool before = (memm & lt) != 0;
-  const bool cconf = member && before && sm.c_conflict[lane] != 0;
-  // rule (b), in the full pop order (mp, then tie): an entry stored by an earlier member pops before this event
-  const bool ccasc = member && before && !cconf && event && exmax != 0 &&
-                     exmax >= mn_pop_key(sm.c_key[lane], sm.c_lo[lane], sm.c_hi[lane]);
-  const uint32_t cm = __ballot_sync(0xffffffffu, cconf || ccasc);
-  const int cut = cm ? __ffs(cm) - 1 : ncand;
-  const bool acc = member && lane < cut;
-  if (lane < ncand) sm.c_accept[lane] = acc ? 1 : 0;
-  const uint32_t below = cut >= 32 ? 0xffffffffu : ((1u << cut) - 1u);
-  const uint32_t accm = memm & below;
-  const uint32_t mergem = __ballot_sync(0xffffffffu, acc && k == MN_K_MERGE);
-  const uint32_t restm = __ballot_sync(0xffffffffu, acc && k == MN_K_RESTORE);
-  const uint32_t reqm = __ballot_sync(0xffffffffu, acc && k == MN_K_REQUEUE);
-  const uint32_t ungm = __ballot_sync(0xffffffffu, acc && k == MN_K_UNGUARD);
-  const uint32_t dropm = __ballot_sync(0xffffffffu, lane < cut && lane < ncand && k == MN_K_DROP);
-  const uint32_t confcut = __ballot_sync(0xffffffffu, cconf && lane == cut);
-  // pixel arrays
-  int need = 0, n_a = 0;
-  if (acc && k == MN_K_MERGE) {
-    const int na = sm.c_na[lane];
-    n_a = na - sm.c_nb[lane];
-    const int capn = mn_pix_cap(na), capo = mn_pix_cap(n_a);
-    if (capn != capo) need = capn;
+  int k[MN_NH];
+  bool member[MN_NH], event[MN_NH], cc[MN_NH], cconf[MN_NH];
+  unsigned long long exmax[MN_NH];
+  unsigned long long carry = 0;  // running maximum of the pop keys stored by the members of the earlier halves
+#pragma unroll
+  for (int h = 0; h < MN_NH; h++) {
+    const int j = lane + 32 * h;
+    k[h] = j < ncand ? sm.c_kind[j] : MN_K_DROP;
+    member[h] = k[h] != MN_K_DROP;
+    event[h] = k[h] == MN_K_RESTORE || k[h] == MN_K_MERGE;
   }
-  const int need_incl = mn_wscan_incl(need, lane);
-  const int cp_incl = mn_wscan_incl(need ? n_a : 0, lane);
-  const uint32_t needm = __ballot_sync(0xffffffffu, need != 0);
-  const int total_need = __shfl_sync(0xffffffffu, need_incl, 31);
-  const int total_cp = __shfl_sync(0xffffffffu, cp_incl, 31);
+  const mn_wmask memm = mn_ballot_w(member);
+#pragma unroll
+  for (int h = 0; h < MN_NH; h++) {
+    const int j = lane + 32 * h;
+    unsigned long long x = member[h] ? sm.c_maxnew[j] : 0ull;
+    for (int d = 1; d < 32; d <<= 1) { unsigned long long o = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d && o > x) x = o; }
+    unsigned long long e = __shfl_up_sync(0xffffffffu, x, 1);  // inclusive -> exclusive
+    if (lane == 0) e = 0ull;
+    exmax[h] = e > carry ? e : carry;
+    const unsigned long long tot = __shfl_sync(0xffffffffu, x, 31);
+    if (tot > carry) carry = tot;
+    const bool before = (memm & mn_below_w(j)) != 0;
+    cconf[h] = member[h] && before && sm.c_conflict[j] != 0;
+    // rule (b), in the full pop order (mp, then tie): an entry stored by an earlier member pops before this event
+    const bool ccasc = member[h] && before && !cconf[h] && event[h] && exmax[h] != 0 &&
+                       exmax[h] >= mn_pop_key(sm.c_key[j], sm.c_lo[j], sm.c_hi[j]);
+    cc[h] = cconf[h] || ccasc;
+  }
+  const mn_wmask cm = mn_ballot_w(cc);
+  const int cut = cm ? mn_ffs_w(cm) : ncand;
+  bool acc[MN_NH], am[MN_NH], ar[MN_NH], aq[MN_NH], au[MN_NH], ad[MN_NH], cf[MN_NH], nd[MN_NH];
+  int need[MN_NH], n_a[MN_NH], need_incl[MN_NH], cp_incl[MN_NH];
+  int need_carry = 0, cp_carry = 0;
+#pragma unroll
+  for (int h = 0; h < MN_NH; h++) {
+    const int j = lane + 32 * h;
+    acc[h] = member[h] && j < cut;
+    if (j < ncand) sm.c_accept[j] = acc[h] ? 1 : 0;
+    am[h] = acc[h] && k[h] == MN_K_MERGE; ar[h] = acc[h] && k[h] == MN_K_RESTORE;
+    aq[h] = acc[h] && k[h] == MN_K_REQUEUE; au[h] = acc[h] && k[h] == MN_K_UNGUARD;
+    ad[h] = j < cut && j < ncand && k[h] == MN_K_DROP;
+    cf[h] = cconf[h] && j == cut;
+    // pixel arrays
+    need[h] = 0; n_a[h] = 0;
+    if (am[h]) {
+      const int na = sm.c_na[j];
+      n_a[h] = na - sm.c_nb[j];
+      const int capn = mn_pix_cap(na), capo = mn_pix_cap(n_a[h]);
+      if (capn != capo) need[h] = capn;
+    }
+    nd[h] = need[h] != 0;
+    need_incl[h] = mn_wscan_incl(need[h], lane) + need_carry;
+    cp_incl[h] = mn_wscan_incl(need[h] ? n_a[h] : 0, lane) + cp_carry;
+    need_carry = __shfl_sync(0xffffffffu, need_incl[h], 31);
+    cp_carry = __shfl_sync(0xffffffffu, cp_incl[h], 31);
+  }
+  const mn_wmask accm = memm & mn_below_w(cut);
+  const mn_wmask mergem = mn_ballot_w(am), restm = mn_ballot_w(ar), reqm = mn_ballot_w(aq), ungm = mn_ballot_w(au),
+                 dropm = mn_ballot_w(ad), confcut = mn_ballot_w(cf), needm = mn_ballot_w(nd);
+  const int total_need = need_carry, total_cp = cp_carry;
   const int bump = sm.pix_bump;
   const bool fits = bump + total_need <= sm.pix_hi;
-  if (acc && k == MN_K_MERGE) {
-    if (need) {
-      const int ci = __popc(needm & lt);
-      sm.c_newptr[lane] = fits ? bump + need_incl - need : 0;
-      sm.cp_list[ci] = lane; sm.cp_base[ci] = cp_incl - n_a;
-    } else {
-      sm.c_newptr[lane] = sm.c_ptra[lane];
+#pragma unroll
+  for (int h = 0; h < MN_NH; h++) {
+    const int j = lane + 32 * h;
+    if (am[h]) {
+      if (need[h]) {
+        const int ci = __popcll(needm & mn_below_w(j));
+        sm.c_newptr[j] = fits ? bump + need_incl[h] - need[h] : 0;
+        sm.cp_list[ci] = j; sm.cp_base[ci] = cp_incl[h] - n_a[h];
+      } else {
+        sm.c_newptr[j] = sm.c_ptra[j];
+      }
     }
   }
   if (lane == 0) {
-    const int ncp = __popc(needm);
+    const int ncp = __popcll(needm);
     sm.ncp = ncp; sm.cp_base[ncp] = total_cp;
-    sm.cutpos = cut; sm.nacc = __popc(accm);
+    sm.cutpos = cut; sm.nacc = __popcll(accm);
     if (fits) {
       sm.pix_bump = bump + total_need;
-      sm.st_merges += __popc(mergem); sm.st_restores += __popc(restm); sm.st_requeues += __popc(reqm);
-      sm.st_events += __popc(mergem) + __popc(restm);
-      sm.st_invalid += __popc(ungm) + __popc(dropm);
+      sm.st_merges += __popcll(mergem); sm.st_restores += __popcll(restm); sm.st_requeues += __popcll(reqm);
+      sm.st_events += __popcll(mergem) + __popcll(restm);
+      sm.st_invalid += __popcll(ungm) + __popcll(dropm);
       if (cm) { if (confcut) sm.st_cut_conf++; else sm.st_cut_casc++; }
       sm.st_rounds++; sm.st_pairs += npr;
     } else {
@@ -1792,11 +1852,15 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     MN_SYNC();
     MN_TOC(MN_CY_SEL_STAGE);
 #if defined(__CUDA_ARCH__)
-    // classify (one lane per candidate) and the capacity cut by pixels run back to back in warp 0: no block
+    // classify (one thread per candidate) and the capacity cut by pixels (warp 0) run back to back: no block
     // barrier between them
-    if (threadIdx.x < 32) {
+    if (threadIdx.x < 32 * MN_NH) {
       if ((int)threadIdx.x < ncand0) mn_classify(im, sm, A, c_clp, (int)threadIdx.x);
+#if MN_NH == 1
       __syncwarp();
+#else
+      asm volatile("bar.sync 1, %0;" :: "n"(32 * MN_NH) : "memory");  // the classifying warps only
+#endif
     }
 #else
     MN_FOR(j, ncand0) mn_classify(im, sm, A, c_clp, j);
