@@ -113,7 +113,9 @@ void mn_plan_destroy(mn_plan* plan);
  *   (c_segment.pyx:53-55) on the fly; MN_INPUT_LOGITS says the maps are the network's raw outputs:
  *   the edge pass applies F.sigmoid (utils/inference_utils.py:43-44,95-96: 1 / (1 + exp(-x)) in fp32,
  *   as torch evaluates it on the device) and the clip while it reads them, so the probability maps
- *   never exist in memory.  0 = probabilities, already clipped (what c_run_segmentation receives).
+ *   never exist in memory.  0 = probabilities the caller has ALREADY clipped (a contract: values must lie in
+ *   [2^-126, 1); only c_run_segmentation, which like the reference symbol takes any floats, checks the domain
+ *   and falls back to the kernel that honours libm's special values for 0, 1, negatives and NaN).
  *   stream: a cudaStream_t (NULL = the plan's own stream).  The call returns after the work has
  *   completed (it synchronises the stream to read the per-image status words).
  */

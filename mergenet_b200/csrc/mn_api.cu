@@ -202,6 +202,7 @@ __global__ void mn_libm_kernel(int which, uint32_t first_bits, uint32_t n, float
 
 // ------------------------------------------------------------------------------------------------
 #define MN_COPY_EVENTS 64
+#define MN_INPUT_CHECK_DOMAIN 16  // internal input flag of the drop-in entry: maps may lie outside [2^-126, 1)
 struct mn_plan {
   int device, max_batch, H, W, C, K, N;
   long long E;
@@ -226,6 +227,7 @@ struct mn_plan {
   int edge_tp, edge_smem, merge_smem, merge_H;
   int edge2_ncons, edge2_ctas, edge2_smem, edge2_stages;  // warp-pipeline edge kernel: consumer warps per CTA (0: not usable), CTAs per SM
   std::vector<MnCtl> h_ctl;
+  int* d_domain_flag;           // raised by mn_domain_check_kernel (drop-in entry: unclipped maps)
   double* d_logprob;            // [max_batch][4] class / sameness / differentness terms
   std::vector<double> h_logprob;
   float last_omf;
@@ -327,7 +329,7 @@ extern "C" void mn_plan_destroy(mn_plan* p) {
     for (int i = 0; i < MN_COPY_EVENTS; i++) cudaEventDestroy(p->copy_ev[i]);
     cudaStreamDestroy(p->copy_stream);
   }
-  cudaFree(p->d_ws); cudaFree(p->d_imgs); cudaFree(p->d_keys_scratch); cudaFree(p->d_cub_temp); cudaFree(p->d_logprob);
+  cudaFree(p->d_ws); cudaFree(p->d_imgs); cudaFree(p->d_keys_scratch); cudaFree(p->d_cub_temp); cudaFree(p->d_logprob); cudaFree(p->d_domain_flag);
   cudaFree(p->d_in_class); cudaFree(p->d_in_adj); cudaFree(p->d_out_mask); cudaFree(p->d_out_cls);
   cudaFree(p->d_out_ninst);
   for (int i = 0; i < 9; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
@@ -363,7 +365,7 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
   memset(&p->timings, 0, sizeof(p->timings));
   p->device = device; p->max_batch = max_batch; p->H = H; p->W = W; p->C = C; p->K = K; p->N = H * W;
   p->E = (long long)p->N * K;
-  p->d_ws = nullptr; p->d_imgs = nullptr; p->d_keys_scratch = nullptr; p->d_cub_temp = nullptr; p->d_logprob = nullptr; p->last_omf = 1.0f;
+  p->d_ws = nullptr; p->d_imgs = nullptr; p->d_keys_scratch = nullptr; p->d_cub_temp = nullptr; p->d_logprob = nullptr; p->d_domain_flag = nullptr; p->last_omf = 1.0f;
   p->d_in_class = nullptr; p->d_in_adj = nullptr; p->d_out_mask = nullptr; p->d_out_cls = nullptr; p->d_out_ninst = nullptr;
   p->staging_batch = 0; p->stream = nullptr;
   for (int i = 0; i < 9; i++) p->ev[i] = nullptr;
@@ -387,6 +389,7 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
   if (cudaMalloc(&p->d_imgs, sizeof(MnImage) * max_batch) != cudaSuccess) return fail(MN_STATUS_CUDA);
   if (cudaMalloc(&p->d_keys_scratch, (size_t)p->E * 8) != cudaSuccess) return fail(MN_STATUS_CUDA);
   if (cudaMalloc(&p->d_logprob, sizeof(double) * 4 * max_batch) != cudaSuccess) return fail(MN_STATUS_CUDA);
+  if (cudaMalloc(&p->d_domain_flag, sizeof(int)) != cudaSuccess) return fail(MN_STATUS_CUDA);
   p->h_logprob.assign((size_t)4 * max_batch, 0.0);
   p->h_imgs.resize(max_batch);
   for (int b = 0; b < max_batch; b++) {
@@ -458,7 +461,16 @@ static int launch_edge(mn_plan* p, int b0, int B, const float* d_class, float* d
   P.logits = (clip & MN_INPUT_LOGITS) ? 1 : 0;
   P.clip = ((clip & MN_INPUT_CLIP) || P.logits) ? 1 : 0;  // (sigmoid saturates to 0 / 1 in fp32: logits are always clipped)
   P.sdb = sdb;
+  P.only_if = nullptr;
   const bool warp_pipeline = p->edge2_ncons > 0 && P.use_tma && sdb == 0.0f;
+  // the drop-in symbol takes whatever floats the caller hands in (the reference computes libm's special values
+  // for them): check the domain of the fast kernel's log recipes and let the general kernel redo the batch if needed
+  const bool check_domain = warp_pipeline && !P.clip && (clip & MN_INPUT_CHECK_DOMAIN);
+  if (check_domain) {
+    MN_CUDA_OK(cudaMemsetAsync(p->d_domain_flag, 0, sizeof(int), s));
+    mn_domain_check_kernel<<<p->num_sms * 8, 256, 0, s>>>(d_class, (size_t)B * C * N, d_adj, (size_t)B * K * N, p->d_domain_flag);
+    p->timings.other_launches++;
+  }
   if (warp_pipeline) {
     P.TP = 32 * p->edge2_ncons;
     P.stages = p->edge2_stages;
@@ -474,6 +486,16 @@ static int launch_edge(mn_plan* p, int b0, int B, const float* d_class, float* d
     if (P.logits) mn_edge_warp_kernel<2><<<grid, threads, p->edge2_smem, s>>>(P);
     else if (P.clip) mn_edge_warp_kernel<1><<<grid, threads, p->edge2_smem, s>>>(P);
     else mn_edge_warp_kernel<0><<<grid, threads, p->edge2_smem, s>>>(P);
+    if (check_domain) {  // fix-up: the general kernel, which returns at once unless the flag was raised
+      MnEdgeParams Q = P;
+      Q.TP = p->edge_tp;
+      Q.tiles_per_image = (N + Q.TP - 1) / Q.TP;
+      Q.only_if = p->d_domain_flag;
+      const long long qt = (long long)B * Q.tiles_per_image;
+      int qgrid = (int)std::min<long long>(qt, (long long)p->num_sms * MN_EDGE_CTAS_PER_SM);
+      mn_edge_pass_kernel<<<qgrid, MN_EDGE_THREADS, p->edge_smem, s>>>(Q);
+      p->timings.edge_launches++;
+    }
   } else {
     int grid = (int)std::min<long long>(tiles, (long long)p->num_sms * MN_EDGE_CTAS_PER_SM);
     mn_edge_pass_kernel<<<grid, MN_EDGE_THREADS, p->edge_smem, s>>>(P);
@@ -776,7 +798,7 @@ extern "C" void c_run_segmentation(float* class_pred, int class_dim, float* adj_
     memcpy(c.offsets, offset_list, sizeof(int) * 2 * offset_dim);
   }
   int ninst = 0;
-  mn_segment_batch_host(c.plan, 1, class_pred, adj_pred, output, object_class, &ninst, 0, sdb, omf, mlb);
+  mn_segment_batch_host(c.plan, 1, class_pred, adj_pred, output, object_class, &ninst, MN_INPUT_CHECK_DOMAIN, sdb, omf, mlb);
   cudaSetDevice(device);  // (the plan's device is the caller's; restated for symmetry with the batch entries)
   if (g_last_error != MN_STATUS_OK) {
     memset(output, 0, sizeof(int) * (size_t)N);

@@ -145,8 +145,17 @@ struct MnLogfTab {
 };
 
 // tab: 16 entries of {invc, logc} (shared memory on the device).
+// Inputs outside the positive normal range take glibc's own special cases (logf(0) = -inf, negative / NaN ->
+// NaN, +inf -> +inf, subnormals rescaled by 2^23): a caller of the raw C ABI may hand in unclipped maps, and
+// the same_different_bias transform can round a probability to exactly 1 or 0 (cc:183-195).
 MN_HD float mn_logf_exact(float x, const MnLogfTab* tab) {
   uint32_t ix = mn_f2u(x);
+  if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+    if (ix * 2u == 0u) return mn_u2f(0xff800000u);                       // log(+-0) = -inf
+    if (ix == 0x7f800000u) return x;                                     // log(inf) = inf
+    if ((ix & 0x80000000u) || ix * 2u >= 0xff000000u) return mn_u2f(0x7fc00000u);  // negative or NaN
+    ix = mn_f2u(x * 8388608.0f) - (23u << 23);                           // subnormal: normalise
+  }
   uint32_t tmp = ix - 0x3f330000u;
   int i = (tmp >> 19) & 15;
   int k = (int32_t)tmp >> 23;

@@ -96,6 +96,7 @@ __device__ __forceinline__ double mn_f32bits_to_f64(uint32_t b) {  // b = bits o
 __device__ __forceinline__ double mn_small_int_to_f64(int k) { return (double)k; }  // (one XU op; exact)
 __device__ __forceinline__ float mn_logf_fast(float x, const MnLogfTab* tab) {
   const uint32_t ix = __float_as_uint(x);
+  if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) return mn_logf_exact(x, tab);  // 0, negative, subnormal, inf, NaN
   const uint32_t tmp = ix - 0x3f330000u;
   const int i = (tmp >> 19) & 15;
   const int k = (int32_t)tmp >> 23;
@@ -121,6 +122,9 @@ struct MnLog1mTab {
 __constant__ MnLogfTab mn_logf_table_c[16] = {MN_LOGF_TABLE};
 __constant__ MnLog1mTab mn_log1m_table[128] = {MN_LOG1M_TABLE};
 __device__ __forceinline__ float mn_log1m_fast(float s, const MnLog1mTab* tab) {
+  // outside [2^-126, 1) (an unclipped caller; a biased probability rounded to 0 or 1): the libm expression itself,
+  // with its special values (log(0) = -inf, log of a negative = NaN)
+  if (__float_as_uint(s) - 0x00800000u >= 0x3f800000u - 0x00800000u) return (float)log(1.0 - (double)s);
   const double x = __dadd_rn(1.0, -mn_f32bits_to_f64(__float_as_uint(s)));  // exact
   const uint32_t hx = (uint32_t)__double2hiint(x);
   const uint32_t tmp = hx - (uint32_t)(MN_LOG1M_OFF >> 32);  // (the low word of OFF is zero)
@@ -157,6 +161,7 @@ __constant__ unsigned long long mn_exp2f_tab[32] = {
     0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
     0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
 __device__ __forceinline__ float mn_expf_exact(float x) {
+  if (!(fabsf(x) < 87.0f)) return expf(x);  // overflow / underflow / NaN: the special values (a saturated logit)
   const double InvLn2N = 0x1.71547652b82fep+0 * 32.0, SHIFT = 0x1.8p+52;
   const double C0 = 0x1.c6af84b912394p-5 / 32768.0, C1 = 0x1.ebfce50fac4f3p-3 / 1024.0, C2 = 0x1.62e42ff0c52d6p-1 / 32.0;
   double z = __dmul_rn(InvLn2N, (double)x);
@@ -201,7 +206,27 @@ struct MnEdgeParams {
   int* ws0_cls;
   size_t ws_stride;  // bytes
   int stages;        // input ring depth (2..4)
+  const int* only_if;  // tile kernel: when set, do nothing unless *only_if != 0 (the fix-up launch after the domain check)
 };
+
+// Raw C-ABI callers (clip = 0) may hand in values outside [2^-126, 1): the warp-pipeline kernel's log recipes assume
+// that range.  One streaming pass raises a flag; the general kernel (whose logs honour libm's special values) then
+// redoes the batch -- launched right behind, it returns at once when the flag is down (no host round trip).
+__global__ void __launch_bounds__(256) mn_domain_check_kernel(const float* a, size_t na, const float* b, size_t nb, int* flag) {
+  unsigned bad = 0;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  const uint4* a4 = reinterpret_cast<const uint4*>(a);
+  const uint4* b4 = reinterpret_cast<const uint4*>(b);
+  for (size_t i = tid; i < na / 4; i += nth) {
+    const uint4 v = a4[i];
+    bad |= (v.x - 0x00800000u >= 0x3f000000u) | (v.y - 0x00800000u >= 0x3f000000u) | (v.z - 0x00800000u >= 0x3f000000u) | (v.w - 0x00800000u >= 0x3f000000u);
+  }
+  for (size_t i = tid; i < nb / 4; i += nth) {
+    const uint4 v = b4[i];
+    bad |= (v.x - 0x00800000u >= 0x3f000000u) | (v.y - 0x00800000u >= 0x3f000000u) | (v.z - 0x00800000u >= 0x3f000000u) | (v.w - 0x00800000u >= 0x3f000000u);
+  }
+  if (__any_sync(0xffffffffu, bad != 0) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
 
 // dynamic smem layout: [bar0, bar1][pad to 128][in0][in1][out0: clp|same|diff][out1][logf tab][log1m tab]
 // two CTAs of 512 threads per SM (tiles of 256 pixels, ~100 KB of shared memory each): while one waits
@@ -210,6 +235,7 @@ struct MnEdgeParams {
 #define MN_EDGE_CTAS_PER_SM 2
 __global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_pass_kernel(MnEdgeParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (P.only_if && *P.only_if == 0) return;
   const int C = P.C, K = P.K, TP = P.TP, NPL = C + K;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float* in0 = reinterpret_cast<float*>(smem_raw + 128);

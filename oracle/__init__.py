@@ -114,10 +114,30 @@ def _ip(a):
     return a.ctypes.data_as(_I)
 
 
+_CLIP = True  # tests of the raw C ABI (unclipped maps, what a caller that skips the .pyx glue hands in) switch it off
+
+
+class raw_abi:
+    """with oracle.raw_abi(): ... -- call the checkers like the C symbol itself, without the wrapper's clip."""
+
+    def __enter__(self):
+        global _CLIP
+        self._saved, _CLIP = _CLIP, False
+
+    def __exit__(self, *a):
+        global _CLIP
+        _CLIP = self._saved
+
+
 def _glue(class_pred, adj_pred, offset_list):
     """c_segment.pyx:53-67 -- clip, offsets -> int32, allocate outputs."""
-    class_pred = np.ascontiguousarray(np.asarray(class_pred, dtype=np.float32).clip(EPS, 1.0 - EPS))
-    adj_pred = np.ascontiguousarray(np.asarray(adj_pred, dtype=np.float32).clip(EPS, 1.0 - EPS))
+    class_pred = np.asarray(class_pred, dtype=np.float32)
+    adj_pred = np.asarray(adj_pred, dtype=np.float32)
+    if _CLIP:
+        class_pred = class_pred.clip(EPS, 1.0 - EPS)
+        adj_pred = adj_pred.clip(EPS, 1.0 - EPS)
+    class_pred = np.ascontiguousarray(class_pred).copy()
+    adj_pred = np.ascontiguousarray(adj_pred).copy()
     off = np.ascontiguousarray(np.array(offset_list).astype(np.int32))
     k, h, w = adj_pred.shape
     mask = np.zeros((h, w), dtype=np.int32)

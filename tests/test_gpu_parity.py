@@ -377,3 +377,30 @@ def test_full_resolution_logprob_within_tolerance(oracle_mod, lib_mod):
     assert _logprob_close(lp, float(g["logprob"])), (lp, float(g["logprob"]))
     assert _logprob_close(seg.total_logprob(0)[3], float(g["logprob"]))
     seg.close()
+
+
+def test_saturated_maps_take_libm_special_values(oracle_mod, lib_mod):
+    """(a) same_different_bias = 2 on oracle-mode maps rounds every "same" probability to exactly 1.0f
+    (log(1 - s) = -inf, priority +inf: cc:183-195,34); (b) a caller of the raw C symbol hands in unclipped class
+    maps holding exact 0 and 1 (logf(0) = -inf).  The drop-in entry checks the domain of its fast log recipes and
+    lets the general edge kernel, which honours libm's special values, redo such a batch."""
+    import test_oracle_vs_reference as t
+    from mergenet_b200 import c_segment
+    L = lib_mod.lib()
+    F = ctypes.POINTER(ctypes.c_float); I = ctypes.POINTER(ctypes.c_int)
+    for name, cp, sp, C, offs, opts, clip in t._saturating_cases():
+        if clip:
+            m0, c0, _ = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)
+            m1, c1 = c_segment.run_segmentation(cp, sp.copy(), C, offs, *opts)
+        else:
+            with oracle_mod.raw_abi():
+                m0, c0, _ = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)
+            K, H, W = sp.shape
+            cpc = np.ascontiguousarray(cp, np.float32).copy(); spc = np.ascontiguousarray(sp, np.float32).copy()
+            off = np.ascontiguousarray(np.array(offs, np.int32))
+            m1 = np.zeros((H, W), np.int32); oc = np.zeros((1, H * W), np.int32)
+            L.c_run_segmentation(cpc.ctypes.data_as(F), C, spc.ctypes.data_as(F), K, W, H, C, off.ctypes.data_as(I),
+                                 m1.ctypes.data_as(I), oc.ctypes.data_as(I), *[ctypes.c_float(o) for o in opts])
+            assert L.mn_last_error() == 0
+            c1 = oracle_mod._trim(oc)
+        assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), name

@@ -83,3 +83,28 @@ def test_oracle_equals_reference_fixtures_at_named_sizes(oracle_mod, name):
     assert np.array_equal(cm, g["mask"]) and list(cc) == [int(v) for v in g["cls"]]
     lp = oracle_mod.total_logprob_from_scratch(m, c, cp, sp, offs, opts[1])
     assert abs(lp - float(g["logprob"])) <= 1e-5 * abs(float(g["logprob"]))
+
+
+def _saturating_cases():
+    """Maps on which libm's special values appear: (a) oracle-mode maps with same_different_bias = 2:
+    the biased probability of every "same" pair rounds to exactly 1.0f, so log(1 - s) = -inf and the priority
+    is +inf (cc:183-195,34); (b) unclipped class maps holding exact 0 and 1 handed to the raw C ABI."""
+    name, cp, sp, C, offs = cases.small_cases()[1]  # city_oracle_48x64
+    out = [("bias2_oracle_mode", cp, sp, C, offs, (2.0, 1.0, 0.03), True)]
+    cp2 = cp.copy()
+    cp2[cp2 > 0.5] = 1.0
+    cp2[cp2 < 0.5] = 0.0
+    out.append(("unclipped_class_0_1", cp2, sp, C, offs, cases.RECIPE_OPTS, False))
+    return out
+
+
+def test_oracle_matches_reference_on_saturated_maps(oracle_mod):
+    if not oracle_mod.have_reference():
+        pytest.skip("reference .so absent")
+    for name, cp, sp, C, offs, opts, clip in _saturating_cases():
+        import contextlib
+        ctx = contextlib.nullcontext() if clip else oracle_mod.raw_abi()
+        with ctx:
+            ref = oracle_mod.ref_run_segmentation(cp, sp, C, offs, *opts)
+            ora = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)[:2]
+        assert cases.same_result(oracle_mod, ref, ora), name
