@@ -29,7 +29,8 @@ enum {
   MN_STATUS_HASH_FULL = 5,
   MN_STATUS_INTERNAL = 6,
   MN_STATUS_CUDA = 7,
-  MN_STATUS_LIMIT = 8
+  MN_STATUS_LIMIT = 8,
+  MN_STATUS_NO_BACKGROUND = 9 /* Mode B only: prune() found no class-0 object (utils/segmenter.py:351-375 raises) */
 };
 
 /*
@@ -138,6 +139,24 @@ int mn_plan_timings(mn_plan* plan, mn_timings* out);
  * records of differentness, class + object_merge_factor * (differentness + sameness)}.  Computed on
  * the GPU by an aggregation pass over the statistics the merges maintained. */
 int mn_plan_image_logprob(mn_plan* plan, int image, double* out4);
+
+/* ---- Mode B: the semantics of the reference's pure-Python segmenter ------------------------------------------ */
+/*
+ * utils/segmenter.py::ObjectSegmenter.run_segmentation (py:432-483) for ONE image, host buffers: priority
+ * (oml * omf + cdl + mlb) / (n1 * n2) (py:189-193), merge when the recomputed priority >= the popped one (py:470),
+ * float64 class accumulators (py:51), heapq's own order among equal priorities, prune(prune_threshold) (py:351-375;
+ * the reference always uses 200), labels in ascending surviving id, int64 mask (py:377-389).  The three inputs are
+ * the LOGARITHMS the reference takes with NumPy -- np.log(class_probs) [C][H][W], np.log(same) and
+ * np.log(1.0 - same) [K][H][W], float32 -- computed by the caller's NumPy so that they carry the reference's bits
+ * (mergenet_b200/segmenter.py does this).  Strictly sequential (one GPU thread replays heapq and the dict orders):
+ * the small-image mode the Python reference itself is (practical to ~128 x 256), not the hot path.
+ * Returns MN_STATUS_NO_BACKGROUND where the reference raises UnboundLocalError (no class-0 object to prune into).
+ * stats4 (optional): heap pops, merges, heap pushes, pruned objects.
+ */
+int mn_modeb_segment_host(const float* h_log_class, const float* h_log_same, const float* h_log_diff, int num_classes,
+                          int num_offsets, int height, int width, const int* offset_list, double object_merge_factor,
+                          double merge_logprob_bias, double prune_threshold, long long* h_mask, int* h_object_class,
+                          int* n_instances, long long* stats4);
 
 /* ---- the step after the path: masks back at the image size, COCO run-length encoding ---- */
 /*

@@ -22,6 +22,7 @@
 #include "mn_post.cuh"
 #include "mn_layout.h"
 #include "mn_merge.cuh"
+#include "mn_modeb.cuh"
 
 // ------------------------------------------------------------------------------------------------
 static thread_local int g_last_error = MN_STATUS_OK;
@@ -49,6 +50,7 @@ extern "C" const char* mn_status_string(int s) {
     case MN_STATUS_INTERNAL: return "internal invariant failed";
     case MN_STATUS_CUDA: return "CUDA error / no usable device";
     case MN_STATUS_LIMIT: return "iteration guard tripped";
+    case MN_STATUS_NO_BACKGROUND: return "Mode B prune: no class-0 object to fold into (the reference raises UnboundLocalError)";
   }
   return "unknown";
 }
@@ -868,6 +870,80 @@ extern "C" int mn_mask_to_coco_rle_host(const int* h_mask, int H, int W, int n, 
   if (e != cudaSuccess) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
   if (total > cap) { offsets[n] = total; g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
   return MN_STATUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mode B: the reference's pure-Python segmenter semantics (utils/segmenter.py), strictly sequential (mn_modeb.cuh)
+__global__ void mn_modeb_kernel(MnModeB m) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) mnb_run(m);
+}
+
+extern "C" int mn_modeb_segment_host(const float* h_logc, const float* h_lsame, const float* h_ldiff, int C, int K, int H,
+                                     int W, const int* offset_list, double omf, double mlb, double prune_threshold,
+                                     long long* h_mask, int* h_object_class, int* n_instances, long long* stats4) {
+  g_last_error = MN_STATUS_OK;
+  if (!h_logc || !h_lsame || !h_ldiff || !offset_list || !h_mask || !h_object_class || !n_instances || C <= 0 ||
+      C >= MN_MAX_C || K <= 0 || K > MN_MAX_K || H <= 0 || W <= 0 || (long long)H * W * K > (1ll << 26)) {
+    g_last_error = MN_STATUS_BAD_ARG;
+    return MN_STATUS_BAD_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  const size_t N = (size_t)H * W, E = N * K;
+  MnModeB m;
+  memset(&m, 0, sizeof(m));
+  m.C = C; m.K = K; m.H = H; m.W = W; m.N = (int)N; m.E = (long long)E;
+  for (int k = 0; k < K; k++) { m.off_r[k] = offset_list[2 * k]; m.off_c[k] = offset_list[2 * k + 1]; }
+  m.omf = omf; m.mlb = mlb; m.omf32 = (float)omf; m.mlb32 = (float)mlb; m.prune_threshold = prune_threshold;
+  unsigned hm = 1;
+  while ((size_t)hm < 2 * E + 16) hm <<= 1;
+  m.h_mask = hm - 1;
+  m.q_cap = (long long)(8 * E + 1024);
+  // one allocation, carved up (256-byte aligned pieces)
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) / 256 * 256; return at; };
+  const size_t a_logc = take(N * C * 4), a_ls = take(E * 4), a_ld = take(E * 4), a_npix = take(N * 4), a_cls = take(N * 4),
+               a_clp = take(N * C * 8), a_osame = take(N * 4), a_alive = take(N), a_head = take(N * 4), a_tail = take(N * 4),
+               a_pnext = take(N * 4), a_ptail = take(N * 4), a_o1 = take(E * 4), a_o2 = take(E * 4), a_oml = take(E * 4),
+               a_same = take(E * 4), a_diff = take(E * 4), a_mp = take(E * 8), a_link = take(E * 24),
+               a_hk = take((size_t)hm * 8), a_hv = take((size_t)hm * 4), a_qk = take((size_t)m.q_cap * 8),
+               a_qr = take((size_t)m.q_cap * 4), a_mask = take(N * 8), a_ocls = take(N * 4), a_n = take(4),
+               a_status = take(4), a_stats = take(64);
+  unsigned char* d = nullptr;
+  if (cudaMalloc(&d, o) != cudaSuccess) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  auto done = [&](int code) { cudaFree(d); g_last_error = code; return code; };
+  m.logc = (const float*)(d + a_logc); m.lsame = (const float*)(d + a_ls); m.ldiff = (const float*)(d + a_ld);
+  m.npix = (int*)(d + a_npix); m.cls = (int*)(d + a_cls); m.clp = (double*)(d + a_clp); m.osame = (float*)(d + a_osame);
+  m.alive = d + a_alive; m.adj_head = (int*)(d + a_head); m.adj_tail = (int*)(d + a_tail);
+  m.pix_next = (int*)(d + a_pnext); m.pix_tail = (int*)(d + a_ptail);
+  m.r_o1 = (int*)(d + a_o1); m.r_o2 = (int*)(d + a_o2); m.r_oml = (float*)(d + a_oml); m.r_same = (float*)(d + a_same);
+  m.r_diff = (float*)(d + a_diff); m.r_mp = (double*)(d + a_mp); m.r_link = (int*)(d + a_link);
+  m.h_key = (unsigned long long*)(d + a_hk); m.h_val = (int*)(d + a_hv);
+  m.q_key = (double*)(d + a_qk); m.q_rec = (int*)(d + a_qr); m.q_n = 0;
+  m.out_mask = (long long*)(d + a_mask); m.out_cls = (int*)(d + a_ocls); m.out_n = (int*)(d + a_n);
+  m.status = (int*)(d + a_status); m.stats = (long long*)(d + a_stats);
+  cudaError_t e = cudaMemcpy((void*)m.logc, h_logc, N * C * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy((void*)m.lsame, h_lsame, E * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy((void*)m.ldiff, h_ldiff, E * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(m.h_key, 0xFF, (size_t)hm * 8);
+  if (e == cudaSuccess) e = cudaMemset(d + a_n, 0, 4 + 252 + 4 + 252 + 64);  // n, status, stats (adjacent pieces)
+  if (e == cudaSuccess) e = cudaMemset(m.out_cls, 0xFF, N * 4);
+  if (e != cudaSuccess) return done(MN_STATUS_CUDA);
+  mn_modeb_kernel<<<1, 32>>>(m);
+  int status = 0;
+  long long st[8] = {0};
+  e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(&status, m.status, 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(st, m.stats, 32, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(n_instances, m.out_n, 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(h_mask, m.out_mask, N * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(h_object_class, m.out_cls, N * 4, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return done(MN_STATUS_CUDA);
+  if (stats4) for (int i = 0; i < 4; i++) stats4[i] = st[i];
+  if (status == 1) return done(MN_STATUS_Q_POOL);
+  if (status == 2) return done(MN_STATUS_HASH_FULL);
+  if (status == 3) return done(MN_STATUS_NO_BACKGROUND);
+  return done(MN_STATUS_OK);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,12 +1,16 @@
 """Host-side mirror of the reference's Python segmenter API (``utils/segmenter.py``).
 
 ``SegmenterOptions`` (segmenter.py:21-24) and ``ObjectSegmenter(...).run_segmentation()``
-(segmenter.py:225-260, 432-483) keep their names, arguments and shape checks.  The merge itself
-runs on the GPU with the csegment ("Mode A") semantics -- the variant the Cityscapes recipe uses
-(egs/cityscape/local/segment.py:138-143).  The reference's pure-Python variant differs from its own
-C++ port in the priority formula, accept rule and pruning; that Mode B is a
-"next" row of the scope table and is not implemented: asking for it raises NotImplementedError
-rather than silently returning Mode-A results.
+(segmenter.py:225-260, 432-483) keep their names, arguments and shape checks.  Two semantics:
+
+* ``mode="segmenter"`` (the default, "Mode B"): what the reference CLASS itself computes -- priority
+  ``(oml*omf + cdl + mlb) / (n1*n2)`` (py:189-193), merge on ``>=`` (py:470), float64 class accumulators
+  (py:51), heapq's own order among equal priorities, ``prune(200)`` (py:351-375, incl. the
+  UnboundLocalError when there is no class-0 object), int64 mask with labels in ascending surviving id
+  (py:377-389).  A drop-in for ``egs/coco/local/segment.py:155-164``.  Strictly sequential on the GPU
+  (mn_modeb.cuh): the small-image mode the pure-Python reference is, not the hot path.
+* ``mode="csegment"`` ("Mode A"): the semantics of the reference's C++ port, which the Cityscapes recipe
+  calls (egs/cityscape/local/segment.py:138-143) -- the hot path of this library.
 
 ``BatchSegmenter`` is the additive batched interface (device tensors in, device tensors out).
 """
@@ -23,16 +27,28 @@ SegmenterOptions = namedtuple('SegmenterOptions',
 
 class ObjectSegmenter:
     def __init__(self, nnet_class_probs, nnet_sameness_probs, num_classes, offsets, opts=None,
-                 mode="csegment"):
-        if mode != "csegment":
-            raise NotImplementedError("only the csegment (Mode A) semantics are implemented")
+                 mode="segmenter"):
+        if mode not in ("segmenter", "csegment"):
+            raise ValueError("mode must be 'segmenter' (utils/segmenter.py semantics) or 'csegment'")
+        self.mode = mode
         self.opts = opts
         if self.opts is None:
             self.opts = self.default_options()
-        self.class_probs = np.ascontiguousarray(nnet_class_probs, dtype=np.float32)
-        self.sameness_probs = np.ascontiguousarray(nnet_sameness_probs, dtype=np.float32)
         self.num_classes = num_classes
         self.offsets = offsets  # should be a list of tuples
+        if mode == "segmenter":
+            # segmenter.py:230-241, with the reference's own NumPy arithmetic (float32 maps stay float32 under
+            # NumPy 2; the device consumes the logarithms, so they carry exactly the reference's bits)
+            epsilon = np.finfo(np.float32).eps
+            self.class_probs = np.asarray(nnet_class_probs, dtype=np.float32).clip(epsilon, 1.0 - epsilon)
+            self.sameness_probs = np.asarray(nnet_sameness_probs, dtype=np.float32).clip(epsilon, 1.0 - epsilon)
+            if self.opts.same_different_bias != 0.0:
+                sameness_probs_biased_logit = (np.log(self.sameness_probs) - np.log(1.0 - self.sameness_probs) +
+                                               self.opts.same_different_bias)
+                self.sameness_probs = 1.0 / (1.0 + np.exp(-sameness_probs_biased_logit))
+        else:
+            self.class_probs = np.ascontiguousarray(nnet_class_probs, dtype=np.float32)
+            self.sameness_probs = np.ascontiguousarray(nnet_sameness_probs, dtype=np.float32)
         class_dim, self.img_height, self.img_width = self.class_probs.shape
         offset_dim, img_height, img_width = self.sameness_probs.shape
         # segmenter.py:245-250
@@ -40,17 +56,44 @@ class ObjectSegmenter:
         assert offset_dim == len(self.offsets)
         assert self.img_height == img_height
         assert self.img_width == img_width
+        self.stats = None
 
     def default_options(self):
         # segmenter.py:257-260
         return SegmenterOptions(same_different_bias=0.0, object_merge_factor=1.0, merge_logprob_bias=0.0)
 
-    def run_segmentation(self):
-        """(mask int[H,W], object_class list) -- segmenter.py:432-483 (csegment semantics)."""
-        return c_segment.run_segmentation(self.class_probs, self.sameness_probs, self.num_classes,
-                                          [tuple(o) for o in self.offsets],
-                                          self.opts.same_different_bias, self.opts.object_merge_factor,
-                                          self.opts.merge_logprob_bias)
+    def run_segmentation(self, prune_threshold=200.0):
+        """(mask [H,W], object_class list) -- segmenter.py:432-483.  mode "segmenter": int64 mask, labels in
+        ascending surviving object id, after prune(prune_threshold) (the reference always prunes at 200.0);
+        raises UnboundLocalError where the reference does.  mode "csegment": the C++ port's result (int32)."""
+        if self.mode == "csegment":
+            return c_segment.run_segmentation(self.class_probs, self.sameness_probs, self.num_classes,
+                                              [tuple(o) for o in self.offsets],
+                                              self.opts.same_different_bias, self.opts.object_merge_factor,
+                                              self.opts.merge_logprob_bias)
+        _lib.require_device()
+        return self._run_modeb(_lib.lib().mn_modeb_segment_host, prune_threshold)
+
+    def _run_modeb(self, entry, prune_threshold):
+        h, w = self.img_height, self.img_width
+        log_class = np.ascontiguousarray(np.log(self.class_probs), dtype=np.float32)           # py:305
+        log_same = np.ascontiguousarray(np.log(self.sameness_probs), dtype=np.float32)         # py:135
+        log_diff = np.ascontiguousarray(np.log(1.0 - self.sameness_probs), dtype=np.float32)   # py:136
+        off = np.ascontiguousarray(np.array([tuple(o) for o in self.offsets], dtype=np.int32))
+        mask = np.zeros((h, w), dtype=np.int64)
+        ocls = np.full(h * w, -1, dtype=np.int32)
+        n = ctypes.c_int(0)
+        st = (ctypes.c_longlong * 4)()
+        rc = entry(log_class.ctypes.data, log_same.ctypes.data, log_diff.ctypes.data, int(self.num_classes),
+                   len(self.offsets), h, w, off.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                   float(self.opts.object_merge_factor), float(self.opts.merge_logprob_bias), float(prune_threshold),
+                   mask.ctypes.data, ocls.ctypes.data, ctypes.byref(n), st)
+        self.stats = dict(zip(("pops", "merges", "pushes", "pruned"), list(st)))
+        if rc == 9:  # MN_STATUS_NO_BACKGROUND
+            raise UnboundLocalError("cannot access local variable 'background_obj' where it is not associated with a value")
+        if rc != 0:
+            raise _lib.MergeNetError(rc, "mn_modeb_segment_host")
+        return mask, [int(c) for c in ocls[:n.value]]
 
 
 class BatchSegmenter:

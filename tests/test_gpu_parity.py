@@ -150,7 +150,7 @@ def test_python_class_facade(oracle_mod, lib_mod):
     from mergenet_b200 import ObjectSegmenter, SegmenterOptions
     name, cp, sp, C, offs = cases.small_cases()[1]
     opts = SegmenterOptions(0.0, 1.0, 0.03)
-    m1, c1 = ObjectSegmenter(cp, sp, C, offs, opts).run_segmentation()
+    m1, c1 = ObjectSegmenter(cp, sp, C, offs, opts, mode="csegment").run_segmentation()
     m0, c0, _ = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)
     assert cases.same_result(oracle_mod, (m0, c0), (m1, c1))
 
