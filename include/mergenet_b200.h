@@ -134,10 +134,12 @@ int mn_segment_batch_host(mn_plan* plan, int batch, const float* h_class, float*
 int mn_plan_image_stats(mn_plan* plan, int image, mn_image_stats* out);
 int mn_plan_timings(mn_plan* plan, mn_timings* out);
 /* Total log-probability of the last run's segmentation of `image`, the quantity the reference prints
- * in ShowStats (segment.cc:236-287: ComputeTotalLogprob) and does not return: out4 = {sum over
- * surviving objects of their class log-prob, sum of the sameness inside objects, sum over surviving
- * records of differentness, class + object_merge_factor * (differentness + sameness)}.  Computed on
- * the GPU by an aggregation pass over the statistics the merges maintained. */
+ * (segment.cc:314-350, ComputeTotalLogprobFromScratch; the maintained variant cc:272-287 prints the same number up
+ * to float rounding) and does not return: out4 = {class term: sum over pixels of log p(class of the pixel's
+ * instance; class 0 for background), sameness term: sum of log(s) over the in-image (pixel, offset) pairs inside one
+ * instance, differentness term: sum of log(1 - s) over the pairs across two, class + object_merge_factor *
+ * (differentness + sameness)}.  Evaluated on the GPU in float64 from the maps the run saw and its label mask (all
+ * background pixels count as one region, as the mask shows them) by a streaming partition-statistics pass. */
 int mn_plan_image_logprob(mn_plan* plan, int image, double* out4);
 
 /* ---- Mode B: the semantics of the reference's pure-Python segmenter ------------------------------------------ */

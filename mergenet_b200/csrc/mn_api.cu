@@ -1,10 +1,11 @@
 // mn_api.cu -- host driver and C ABI of libmergenet_b200.so (see include/mergenet_b200.h).
 //
 // Pipeline for a batch of B images of one shape, all on one CUDA stream:
-//   1. mn_edge_pass_kernel      whole GPU, HBM-bound, TMA-staged            (mn_edge.cuh)
+//   1. mn_edge_warp_kernel (fast path) / mn_edge_pass_kernel (general): whole GPU, HBM-bound, TMA-staged (mn_edge.cuh)
 //   2. per image: mn_record_init_kernel -> radix sort of the initial queue keys (cub, library call)
 //   3. mn_merge_kernel          persistent, one CTA per image, order-exact scheduler (mn_merge.cuh)
 //   4. labels: root flags -> exclusive scan (cub) -> mask / object_class     (this file)
+//   5. mn_partition_logprob_kernel: total log-prob of the final partition, HBM-bound streaming pass (this file)
 // There is no CPU implementation behind this API: without a CUDA device every call fails.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -137,39 +138,84 @@ __global__ void mn_label_write_kernel(const MnImage* imgs, int nimg, int N, int*
   }
 }
 
-// Aggregation pass (cc:272-287, ComputeTotalLogprob): the sufficient statistics the merges maintained
-// -- per surviving object its class log-prob and the sameness inside it, per surviving record its
-// differentness -- summed per image.  A pure HBM-bound streaming reduction over obj[N] (16 B), the
-// class vectors of the roots, and the record sectors rec[E] (first half, 16 B of each 32 B); fp32
-// accumulators are added up in fp64 (block tree, then one atomicAdd per block and term).
-__global__ void __launch_bounds__(256) mn_logprob_kernel(const MnImage* imgs, int nimg, int N, int C, long long E,
-                                                         double* out /* [nimg][4] */) {
-  __shared__ double red[3][256];
-  for (int b = blockIdx.y; b < nimg; b += gridDim.y) {
-    const MnImage im = imgs[b];
-    double tc = 0.0, ts = 0.0, td = 0.0;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
-    for (long long p = tid; p < N; p += nth) {
-      if (im.parent[p] == (int)p) {
-        const uint4 o = im.obj[p];
-        tc += (double)im.clp[(size_t)p * C + mn_nc_cls(o.x)];
-        ts += (double)mn_u2f(o.y);
+// Partition statistics pass (cc:314-350, ComputeTotalLogprobFromScratch; SURVEY 8 a12 names this definition the
+// parity number): the total log-probability of the FINAL partition, evaluated from the maps and the label mask in
+// float64 -- class term over every pixel (the class of its instance, 0 for background), sameness term over the
+// in-image (pixel, offset) pairs that ended inside one instance, differentness term over those that ended across
+// two.  A pure HBM-bound streaming pass: K sameness planes + the label mask + one class value per pixel read once
+// (neighbour labels come from L1/L2), per-thread fp64 partial sums folded by warp shuffles, one partial triple per
+// block, folded in a fixed order by mn_partition_logprob_fold_kernel (deterministic, no global atomics).
+struct MnLogprobParams {
+  const float* d_class; const float* d_adj; const int* d_mask; const int* d_object_class;
+  double* partial;  // [nimg][gridDim.x][3]
+  int nimg, H, W, C, K, N, input;  // input: MN_INPUT_* flags of the run (the values the edge pass saw)
+  int off_r[MN_MAX_K], off_c[MN_MAX_K];
+};
+__device__ __forceinline__ float mn_logprob_input(float v, int input) {
+  if (input & MN_INPUT_LOGITS) v = mn_sigmoid_f32(v);
+  if (input & (MN_INPUT_LOGITS | MN_INPUT_CLIP)) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
+  return v;
+}
+// log(a) + log(b) = log(a * b): a thread multiplies its probabilities in float64 (each factor >= 2^-24 after the clip,
+// 2^-126 by the contract of unclipped inputs; 1.0 - (double)s is exact) and takes one log per MN_LP_FMAX factors, so
+// the pass is bound by its loads, not by the fp64 pipe.  The result equals the sum of the logs to float64 rounding.
+struct MnLogAcc {
+  double prod, sum; int n, fmax;
+  __device__ __forceinline__ void init(int fm) { prod = 1.0; sum = 0.0; n = 0; fmax = fm; }
+  __device__ __forceinline__ void mul(double f) {
+    if (n >= fmax) { sum += log(prod); prod = 1.0; n = 0; }
+    prod *= f; n++;
+  }
+  __device__ __forceinline__ double total() { return sum + log(prod); }
+};
+__global__ void __launch_bounds__(256) mn_partition_logprob_kernel(MnLogprobParams P) {
+  __shared__ double red[3][8];
+  const int N = P.N, W = P.W, H = P.H, K = P.K;
+  // factors one product may take before it could leave the double range: 2^-24 each when clipped (40 * 24 = 960 bits)
+  const int fmax = (P.input & (MN_INPUT_LOGITS | MN_INPUT_CLIP)) ? 40 : 8;
+  for (int b = blockIdx.y; b < P.nimg; b += gridDim.y) {
+    const int* mask = P.d_mask + (size_t)b * N;
+    const int* ocls = P.d_object_class + (size_t)b * N;
+    const float* cp = P.d_class + (size_t)b * P.C * N;
+    const float* ap = P.d_adj + (size_t)b * K * N;
+    MnLogAcc ac, as, ad;
+    ac.init(fmax); as.init(fmax); ad.init(fmax);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+      const int row = p / W, col = p - row * W;
+      const int lab = mask[p];
+      int cls = lab > 0 ? ocls[lab - 1] : 0;
+      cls = cls < 0 ? 0 : (cls >= P.C ? P.C - 1 : cls);  // (only a failed image can hold anything else)
+      ac.mul((double)mn_logprob_input(cp[(size_t)cls * N + p], P.input));
+#pragma unroll 5
+      for (int k = 0; k < K; k++) {
+        const int r2 = row + P.off_r[k], c2 = col + P.off_c[k];
+        if (r2 < 0 || r2 >= H || c2 < 0 || c2 >= W) continue;
+        const double s = (double)mn_logprob_input(ap[(size_t)k * N + p], P.input);
+        if (mask[r2 * W + c2] == lab) as.mul(s); else ad.mul(1.0 - s);
       }
     }
-    for (long long r = tid; r < E; r += nth) {
-      const uint4 a = im.rec[2 * r];
-      if ((int)a.x >= 0) td += (double)mn_u2f(a.w);
+    double tc = ac.total(), ts = as.total(), td = ad.total();
+    for (int o = 16; o > 0; o >>= 1) {
+      tc += __shfl_xor_sync(0xffffffffu, tc, o); ts += __shfl_xor_sync(0xffffffffu, ts, o); td += __shfl_xor_sync(0xffffffffu, td, o);
     }
-    red[0][threadIdx.x] = tc; red[1][threadIdx.x] = ts; red[2][threadIdx.x] = td;
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = tc; red[1][threadIdx.x >> 5] = ts; red[2][threadIdx.x >> 5] = td; }
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-      if ((int)threadIdx.x < s)
-        for (int k = 0; k < 3; k++) red[k][threadIdx.x] += red[k][threadIdx.x + s];
-      __syncthreads();
+    if (threadIdx.x < 3) {
+      double t = 0.0;
+      for (int w = 0; w < 8; w++) t += red[threadIdx.x][w];
+      P.partial[((size_t)b * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = t;
     }
-    if (threadIdx.x < 3) atomicAdd(&out[(size_t)b * 4 + threadIdx.x], red[threadIdx.x][0]);
     __syncthreads();
   }
+}
+// one warp per image and term: the block partials in index order (fixed summation tree)
+__global__ void mn_partition_logprob_fold_kernel(const double* partial, int nimg, int nblk, double* out /* [nimg][4] */) {
+  const int b = blockIdx.x, term = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (b >= nimg || term >= 3) return;
+  double t = 0.0;
+  for (int i = lane; i < nblk; i += 32) t += partial[((size_t)b * nblk + i) * 3 + term];
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane == 0) out[(size_t)b * 4 + term] = t;
 }
 
 __global__ void mn_libm_kernel(int which, uint32_t first_bits, uint32_t n, float bias, float* out) {
@@ -204,6 +250,7 @@ __global__ void mn_libm_kernel(int which, uint32_t first_bits, uint32_t n, float
 
 // ------------------------------------------------------------------------------------------------
 #define MN_COPY_EVENTS 64
+#define MN_LOGPROB_BLOCKS 512  // blocks per image of mn_partition_logprob_kernel (upper bound)
 #define MN_INPUT_CHECK_DOMAIN 16  // internal input flag of the drop-in entry: maps may lie outside [2^-126, 1)
 struct mn_plan {
   int device, max_batch, H, W, C, K, N;
@@ -231,6 +278,7 @@ struct mn_plan {
   std::vector<MnCtl> h_ctl;
   int* d_domain_flag;           // raised by mn_domain_check_kernel (drop-in entry: unclipped maps)
   double* d_logprob;            // [max_batch][4] class / sameness / differentness terms
+  double* d_logprob_partial;    // [max_batch][MN_LOGPROB_BLOCKS][3] block partials of the partition statistics pass
   std::vector<double> h_logprob;
   float last_omf;
   mn_timings timings;
@@ -264,7 +312,7 @@ static WsLayout ws_layout(int H, int W, int C, int K) {
   L.obj = take(N * 16);
   L.parent = take(N * 4);
   L.pix_pool = take((size_t)L.pix_cap * 4);
-  L.rec = take(E * 32);
+  L.rec = take(E * 16);
   L.arena = take(std::max(E * 8, (size_t)L.qc_cap * MN_QCH * 16));
   L.hash = take((size_t)L.hash_nbuckets * 8 * 4);
   L.hash_ovf = take((size_t)L.hash_ovf_cap * 4);
@@ -331,7 +379,7 @@ extern "C" void mn_plan_destroy(mn_plan* p) {
     for (int i = 0; i < MN_COPY_EVENTS; i++) cudaEventDestroy(p->copy_ev[i]);
     cudaStreamDestroy(p->copy_stream);
   }
-  cudaFree(p->d_ws); cudaFree(p->d_imgs); cudaFree(p->d_keys_scratch); cudaFree(p->d_cub_temp); cudaFree(p->d_logprob); cudaFree(p->d_domain_flag);
+  cudaFree(p->d_ws); cudaFree(p->d_imgs); cudaFree(p->d_keys_scratch); cudaFree(p->d_cub_temp); cudaFree(p->d_logprob); cudaFree(p->d_logprob_partial); cudaFree(p->d_domain_flag);
   cudaFree(p->d_in_class); cudaFree(p->d_in_adj); cudaFree(p->d_out_mask); cudaFree(p->d_out_cls);
   cudaFree(p->d_out_ninst);
   for (int i = 0; i < 9; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
@@ -367,7 +415,7 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
   memset(&p->timings, 0, sizeof(p->timings));
   p->device = device; p->max_batch = max_batch; p->H = H; p->W = W; p->C = C; p->K = K; p->N = H * W;
   p->E = (long long)p->N * K;
-  p->d_ws = nullptr; p->d_imgs = nullptr; p->d_keys_scratch = nullptr; p->d_cub_temp = nullptr; p->d_logprob = nullptr; p->d_domain_flag = nullptr; p->last_omf = 1.0f;
+  p->d_ws = nullptr; p->d_imgs = nullptr; p->d_keys_scratch = nullptr; p->d_cub_temp = nullptr; p->d_logprob = nullptr; p->d_logprob_partial = nullptr; p->d_domain_flag = nullptr; p->last_omf = 1.0f;
   p->d_in_class = nullptr; p->d_in_adj = nullptr; p->d_out_mask = nullptr; p->d_out_cls = nullptr; p->d_out_ninst = nullptr;
   p->staging_batch = 0; p->stream = nullptr;
   for (int i = 0; i < 9; i++) p->ev[i] = nullptr;
@@ -391,6 +439,7 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
   if (cudaMalloc(&p->d_imgs, sizeof(MnImage) * max_batch) != cudaSuccess) return fail(MN_STATUS_CUDA);
   if (cudaMalloc(&p->d_keys_scratch, (size_t)p->E * 8) != cudaSuccess) return fail(MN_STATUS_CUDA);
   if (cudaMalloc(&p->d_logprob, sizeof(double) * 4 * max_batch) != cudaSuccess) return fail(MN_STATUS_CUDA);
+  if (cudaMalloc(&p->d_logprob_partial, sizeof(double) * 3 * MN_LOGPROB_BLOCKS * max_batch) != cudaSuccess) return fail(MN_STATUS_CUDA);
   if (cudaMalloc(&p->d_domain_flag, sizeof(int)) != cudaSuccess) return fail(MN_STATUS_CUDA);
   p->h_logprob.assign((size_t)4 * max_batch, 0.0);
   p->h_imgs.resize(max_batch);
@@ -538,7 +587,8 @@ static int run_front(mn_plan* p, int b0, int B, const float* d_class, float* d_a
   return MN_STATUS_OK;
 }
 
-static int run_back(mn_plan* p, int B, int* d_mask, int* d_object_class, int* d_ninst, float omf, float mlb, cudaStream_t s);
+static int run_back(mn_plan* p, int B, const float* d_class, const float* d_adj, int clip, int* d_mask, int* d_object_class, int* d_ninst,
+                    float omf, float mlb, cudaStream_t s);
 
 extern "C" int mn_segment_batch_device(mn_plan* p, int B, const float* d_class, float* d_adj, int* d_mask,
                                        int* d_object_class, int* d_ninst, int clip, float sdb, float omf,
@@ -553,11 +603,12 @@ extern "C" int mn_segment_batch_device(mn_plan* p, int B, const float* d_class, 
   p->timings.edge_launches = 0; p->timings.other_launches = 0;
   int rc = run_front(p, 0, B, d_class, d_adj, clip, sdb, omf, mlb, s, true);
   if (rc) return rc;
-  return run_back(p, B, d_mask, d_object_class, d_ninst, omf, mlb, s);
+  return run_back(p, B, d_class, d_adj, clip, d_mask, d_object_class, d_ninst, omf, mlb, s);
 }
 
-// merge scheduler + aggregation + labels for images [0, B), whose front end has been enqueued on s
-static int run_back(mn_plan* p, int B, int* d_mask, int* d_object_class, int* d_ninst, float omf, float mlb, cudaStream_t s) {
+// merge scheduler + labels + partition statistics for images [0, B), whose front end has been enqueued on s
+static int run_back(mn_plan* p, int B, const float* d_class, const float* d_adj, int clip, int* d_mask, int* d_object_class, int* d_ninst,
+                    float omf, float mlb, cudaStream_t s) {
   const int N = p->N;
   MnMergeArgs A;
   memset(&A, 0, sizeof(A));
@@ -566,15 +617,6 @@ static int run_back(mn_plan* p, int B, int* d_mask, int* d_object_class, int* d_
   mn_merge_kernel<<<grid, MN_MERGE_THREADS, p->merge_smem, s>>>(p->d_imgs, B, A);
   p->timings.other_launches++;
   MN_CUDA_OK(cudaEventRecord(p->ev[4], s));
-  // aggregation pass: total log-prob terms from the maintained sums
-  {
-    MN_CUDA_OK(cudaMemsetAsync(p->d_logprob, 0, sizeof(double) * 4 * B, s));
-    dim3 g((unsigned)std::max(1, std::min(2 * p->num_sms / std::max(1, std::min(B, 8)), (int)((p->E + 255) / 256))), (unsigned)std::min(B, 65535));
-    mn_logprob_kernel<<<g, 256, 0, s>>>(p->d_imgs, B, N, p->C, p->E, p->d_logprob);
-    p->timings.other_launches++;
-    p->last_omf = omf;
-  }
-  MN_CUDA_OK(cudaEventRecord(p->ev[8], s));
   // labels
   {
     dim3 g((unsigned)std::min(1024, (N + 255) / 256), (unsigned)std::min(B, 65535));
@@ -587,6 +629,20 @@ static int run_back(mn_plan* p, int B, int* d_mask, int* d_object_class, int* d_
     mn_label_write_kernel<<<g, 256, 0, s>>>(p->d_imgs, B, N, d_mask, d_object_class, d_ninst);
     p->timings.other_launches += 2;
   }
+  MN_CUDA_OK(cudaEventRecord(p->ev[8], s));
+  // partition statistics pass: total log-prob of the final partition, from the maps and the label mask
+  {
+    MnLogprobParams L;
+    L.d_class = d_class; L.d_adj = d_adj; L.d_mask = d_mask; L.d_object_class = d_object_class; L.partial = p->d_logprob_partial;
+    L.nimg = B; L.H = p->H; L.W = p->W; L.C = p->C; L.K = p->K; L.N = N; L.input = clip & (MN_INPUT_CLIP | MN_INPUT_LOGITS);
+    for (int k = 0; k < p->K; k++) { L.off_r[k] = p->offsets[2 * k]; L.off_c[k] = p->offsets[2 * k + 1]; }
+    const int gx = std::max(1, std::min(MN_LOGPROB_BLOCKS, (N + 1023) / 1024));
+    dim3 g((unsigned)gx, (unsigned)std::min(B, 65535));
+    mn_partition_logprob_kernel<<<g, 256, 0, s>>>(L);
+    mn_partition_logprob_fold_kernel<<<B, 96, 0, s>>>(p->d_logprob_partial, B, gx, p->d_logprob);
+    p->timings.other_launches += 2;
+    p->last_omf = omf;
+  }
   MN_CUDA_OK(cudaEventRecord(p->ev[5], s));
   MN_CUDA_OK(cudaGetLastError());
   // per-image status / statistics
@@ -598,8 +654,8 @@ static int run_back(mn_plan* p, int B, int* d_mask, int* d_object_class, int* d_
   cudaEventElapsedTime(&ms, p->ev[1], p->ev[2]); p->timings.edge_ms = ms;
   cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); p->timings.record_init_sort_ms = ms;
   cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->timings.merge_ms = ms;
-  cudaEventElapsedTime(&ms, p->ev[4], p->ev[8]); p->timings.aggregate_ms = ms;
-  cudaEventElapsedTime(&ms, p->ev[8], p->ev[5]); p->timings.label_ms = ms;
+  cudaEventElapsedTime(&ms, p->ev[4], p->ev[8]); p->timings.label_ms = ms;
+  cudaEventElapsedTime(&ms, p->ev[8], p->ev[5]); p->timings.aggregate_ms = ms;
   cudaEventElapsedTime(&ms, p->ev[1], p->ev[5]); p->timings.total_ms = ms;
   int worst = MN_STATUS_OK;
   for (int b = 0; b < B; b++)
@@ -660,7 +716,7 @@ extern "C" int mn_segment_batch_host(mn_plan* p, int B, const float* h_class, fl
   }
   MN_CUDA_OK(cudaEventRecord(p->ev[2], s));  // (chunked: edge_ms covers the whole front end, record_init_sort_ms is 0)
   MN_CUDA_OK(cudaEventRecord(p->ev[3], s));
-  rc = run_back(p, B, p->d_out_mask, p->d_out_cls, p->d_out_ninst, omf, mlb, s);
+  rc = run_back(p, B, p->d_in_class, p->d_in_adj, clip, p->d_out_mask, p->d_out_cls, p->d_out_ninst, omf, mlb, s);
   MN_CUDA_OK(cudaEventRecord(p->ev[6], s));
   MN_CUDA_OK(cudaMemcpyAsync(h_mask, p->d_out_mask, (size_t)B * N * 4, cudaMemcpyDeviceToHost, s));
   MN_CUDA_OK(cudaMemcpyAsync(h_object_class, p->d_out_cls, (size_t)B * N * 4, cudaMemcpyDeviceToHost, s));
@@ -694,7 +750,7 @@ extern "C" int mn_plan_image_logprob(mn_plan* p, int image, double* out4) {
   if (!p || !out4 || image < 0 || image >= p->max_batch) return MN_STATUS_BAD_ARG;
   const double* t = &p->h_logprob[(size_t)4 * image];
   out4[0] = t[0]; out4[1] = t[1]; out4[2] = t[2];
-  out4[3] = t[0] + (double)p->last_omf * (t[2] + t[1]);  // cc:272-287
+  out4[3] = t[0] + (double)p->last_omf * (t[2] + t[1]);  // cc:314-350
   return MN_STATUS_OK;
 }
 extern "C" int mn_plan_timings(mn_plan* p, mn_timings* o) {
@@ -962,20 +1018,22 @@ extern "C" int mn_debug_edge_dump(int H, int W, int C, int K, const int* offset_
   cudaMemcpyAsync(p->d_in_adj, h_adj, (size_t)K * N * 4, cudaMemcpyHostToDevice, s);
   rc = run_front(p, 0, 1, p->d_in_class, p->d_in_adj, 0, sdb, omf, mlb, s, false);
   if (rc) return done(rc);
-  std::vector<uint4> rec(2 * E);
+  std::vector<uint4> rec(E);
+  std::vector<float> esame(E), ediff(E);
   const MnImage& im = p->h_imgs[0];
   cudaMemcpyAsync(clp, im.clp, N * C * 4, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(cls, im.cls, N * 4, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(rec.data(), im.rec, E * 32, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(rec.data(), im.rec, E * 16, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(esame.data(), im.rec_same, E * 4, cudaMemcpyDeviceToHost, s);  // (edge-pass outputs: no sort has reused the arena)
+  cudaMemcpyAsync(ediff.data(), im.rec_diff, E * 4, cudaMemcpyDeviceToHost, s);
   if (sdb != 0.0f) cudaMemcpyAsync(h_adj, p->d_in_adj, (size_t)K * N * 4, cudaMemcpyDeviceToHost, s);
   if (cudaStreamSynchronize(s) != cudaSuccess) return done(MN_STATUS_CUDA);
   for (size_t r = 0; r < E; r++) {
-    const uint4 a = rec[2 * r];
-    const float4 b = *reinterpret_cast<const float4*>(&rec[2 * r + 1]);
-    lo[r] = (int)a.x; hi[r] = (int)a.y;
+    const uint4 a = rec[r];
+    lo[r] = mn_rec_lo(a.x); hi[r] = mn_rec_hi(a.y);
     bool v = lo[r] >= 0;
     if (!v) { lo[r] = -1; hi[r] = -1; }
-    oml[r] = v ? b.x : 0.f; same[r] = v ? b.y : 0.f; diff[r] = v ? mn_u2f(a.w) : 0.f; mp[r] = v ? b.w : 0.f;
+    oml[r] = v ? mn_u2f(a.z) : 0.f; same[r] = v ? esame[r] : 0.f; diff[r] = v ? ediff[r] : 0.f; mp[r] = v ? mn_u2f(a.w) : 0.f;
   }
   return done(MN_STATUS_OK);
 }

@@ -726,22 +726,21 @@ __global__ void __launch_bounds__(256) mn_record_init_kernel(MnRecInitParams P) 
     if (r2 >= 0 && r2 < P.H && c2 >= 0 && c2 < P.W) {
       const int q = r2 * P.W + c2;
       const int lo = p < q ? p : q, hi = p < q ? q : p;  // cc:49-56
-      const float same = im.rec_same[r], diff = im.rec_diff[r];
-      const float oml = MN_FSUB(same, diff);  // cc:36
+      const float oml = MN_FSUB(im.rec_same[r], im.rec_diff[r]);  // cc:36
       const int cl = im.cls[lo], ch = im.cls[hi];
       const float mp = mn_priority(oml, P.omf, P.mlb, P.C, 1, cl, im.clp + (size_t)lo * P.C, 1, ch,
                                    im.clp + (size_t)hi * P.C, nullptr);  // cc:45
-      MN_REC_LH(im, r) = make_int2(lo, hi);  // (the hash verifies keys through the record)
+      const MnHashPos hp = mn_hash_pos(im.hash_nbuckets, lo, hi);
+      const uint32_t g = mp >= 0.0f ? MN_G_EXACT : MN_G_NONE;  // the initial entry is queued iff mp >= 0 (cc:225-227)
+      mn_store_rec(im, r, make_uint4(mn_rec_pack_x(lo, MN_HS_NONE, g), (uint32_t)hi, mn_f2u(oml), mn_f2u(mp)));  // (the hash verifies keys through the record)
       const int hslot = mn_hash_insert(im, lo, hi, r);
-      MN_REC_A(im, r) = make_uint4((uint32_t)lo, (uint32_t)hi, (uint32_t)hslot, mn_f2u(diff));
-      MN_REC_B(im, r) = make_float4(oml, same, mp >= 0.0f ? mp : -1.0f, mp);
+      MN_REC(im, r).x = mn_rec_pack_x(lo, mn_hs_of_slot(hp, hslot), g);
       if (mp >= 0.0f) {  // cc:225-227
         uint32_t ord = (mn_tie_u(lo, hi) << 4) | (uint32_t)P.rank_of_k[k];
         key = ((uint64_t)(~mn_f2u(mp == 0.0f ? 0.0f : mp)) << MN_ORD_BITS) | ord;
       }
     } else {
-      MN_REC_A(im, r) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
-      MN_REC_B(im, r) = make_float4(0.f, 0.f, -1.0f, -1.0f);
+      mn_store_rec(im, r, make_uint4(MN_REC_DEAD, 0u, 0u, mn_f2u(-1.0f)));
     }
     P.keys_out[r] = key;
   }

@@ -5,8 +5,9 @@
 //   objects   clp[N*C] f32 | obj[N] uint4 (npix | cls<<24, sameness sum, pixel-array offset, -) |
 //             parent[N] | live_mask[N] | pix_pool: one contiguous pixel array per multi-pixel
 //             object, capacity = next power of two >= npix (>= 4)          (Object, h:85-137)
-//   records   rec[E] 32 B: (lo, hi, hash slot, diff | oml, same, qmp, mp); lo = -1 = dead
-//             (AdjacencyRecord, h:175-232)
+//   records   rec[E] 16 B: (lo | hash slot << 24 | guard state << 29, hi, oml, mp); lo field all ones = dead
+//             (AdjacencyRecord, h:175-232; the sameness / differentness sums of h:131,186-187 feed only the printed
+//             total log-prob, which mn_logprob_scratch_kernel evaluates from the final partition instead)
 //   hash      2-choice, 8-slot buckets of u32 (fingerprint<<26 | rec+1): (lo,hi) -> record
 //             (replaces the per-object unordered_map lookups of cc:685-688)
 //   queue     init_keys[E] u64, sorted: the initial priority-queue entries (cc:225-227);
@@ -123,9 +124,8 @@ struct MnImage {
   int* parent;
   int* pix_pool;
   // records
-  uint4* rec;       // one 32-byte sector per record slot r: rec[2r] = (lo, hi, hash slot, differentness sum),
-                    // rec[2r+1] = (oml, sameness sum, qmp = priority of the record's earliest queued entry
-                    // or -1, mp); lo = -1: dead                                         (h:175-232)
+  uint4* rec;       // one 16-byte record per slot r: x = lo (24 bits) | hash position (5 bits) << 24 | guard state
+                    // (2 bits) << 29, y = hi, z = bits of oml, w = bits of mp; lo field all ones: dead   (h:175-232)
   float* rec_same;  // edge-pass outputs; dead after record init, then aliased by q_ent
   float* rec_diff;
   // hash
@@ -149,40 +149,34 @@ struct MnImage {
   MnCtl* ctl;
 };
 
-#define MN_REC_A(im, r) ((im).rec[2 * (size_t)(r)])
-#define MN_REC_B(im, r) (reinterpret_cast<float4*>((im).rec)[2 * (size_t)(r) + 1])
-#define MN_REC_LH(im, r) (*reinterpret_cast<int2*>(&(im).rec[2 * (size_t)(r)]))
-// One record = one 32-byte sector: both halves with ONE 256-bit request on the device (LDG.E.256 / STG.E.256,
-// sm_100): the scheduler's phases are priced in LSU requests as much as in round trips.
-#ifndef MN_OPT_LD256
-#define MN_OPT_LD256 1
-#endif
-MN_HD void mn_load_rec(const MnImage& im, int r, uint4* a, float4* b) {
-#if defined(__CUDA_ARCH__) && MN_OPT_LD256
-  uint32_t x0, x1, x2, x3, y0, y1, y2, y3;
-  asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3), "=r"(y0), "=r"(y1), "=r"(y2), "=r"(y3)
-               : "l"(im.rec + 2 * (size_t)r));  // (volatile: keeps its place between the block barriers)
-  *a = make_uint4(x0, x1, x2, x3);
-  *b = make_float4(__uint_as_float(y0), __uint_as_float(y1), __uint_as_float(y2), __uint_as_float(y3));
-#else
-  *a = MN_REC_A(im, r);
-  *b = MN_REC_B(im, r);
-#endif
-}
-MN_HD void mn_store_rec(const MnImage& im, int r, uint4 a, float4 b) {
-#if defined(__CUDA_ARCH__) && MN_OPT_LD256
-  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-               :: "l"(im.rec + 2 * (size_t)r), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(__float_as_uint(b.x)),
-                  "r"(__float_as_uint(b.y)), "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w)) : "memory");
-#else
-  MN_REC_A(im, r) = a;
-  MN_REC_B(im, r) = b;
-#endif
+// ---- the 16-byte record --------------------------------------------------------------------------
+// Guard state of a record = what is queued for it (the queue is lazy, see mn_merge.cuh):
+//   NONE   no entry is expected (fresh, or its guard was consumed);
+//   EXACT  an entry at exactly the stored priority (and key) is queued;
+//   ABOVE  some entry with a priority strictly above the stored one is queued (the stored priority was lowered, or
+//          went negative, after that entry was pushed): the first such entry to surface re-queues the record.
+#define MN_G_NONE 0u
+#define MN_G_EXACT 1u
+#define MN_G_ABOVE 2u
+#define MN_HS_OVF 16u    // hash position: 0..7 slot of bucket b1, 8..15 slot of bucket b2, 16 the overflow area
+#define MN_HS_NONE 31u
+#define MN_REC_DEAD 0xFFFFFFFFu
+#define MN_REC(im, r) ((im).rec[(size_t)(r)])
+MN_HD uint32_t mn_rec_pack_x(int lo, uint32_t hs, uint32_t g) { return (uint32_t)lo | (hs << 24) | (g << 29); }
+MN_HD int mn_rec_lo(uint32_t x) { const uint32_t l = x & 0xFFFFFFu; return l == 0xFFFFFFu ? -1 : (int)l; }
+MN_HD int mn_rec_hi(uint32_t y) { return (int)(y & 0xFFFFFFu); }
+MN_HD uint32_t mn_rec_hs(uint32_t x) { return (x >> 24) & 31u; }
+MN_HD uint32_t mn_rec_guard(uint32_t x) { return (x >> 29) & 3u; }
+MN_HD uint32_t mn_rec_with_guard(uint32_t x, uint32_t g) { return (x & ~(3u << 29)) | (g << 29); }
+MN_HD uint4 mn_load_rec(const MnImage& im, int r) { return im.rec[(size_t)r]; }
+MN_HD void mn_store_rec(const MnImage& im, int r, uint4 v) { im.rec[(size_t)r] = v; }
+MN_HD int2 mn_rec_key(const MnImage& im, int r) {  // (lo, hi); lo = -1: dead
+  const uint2 k = *reinterpret_cast<const uint2*>(&im.rec[(size_t)r]);
+  return make_int2(mn_rec_lo(k.x), mn_rec_hi(k.y));
 }
 // one 8-slot hash bucket (32 bytes)
 MN_HD void mn_load_bucket(const MnImage& im, uint32_t b, uint32_t* out) {
-#if defined(__CUDA_ARCH__) && MN_OPT_LD256
+#if defined(__CUDA_ARCH__)
   asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(out[0]), "=r"(out[1]), "=r"(out[2]), "=r"(out[3]), "=r"(out[4]), "=r"(out[5]), "=r"(out[6]), "=r"(out[7])
                : "l"(im.hash + (size_t)b * 8));
@@ -226,6 +220,15 @@ MN_HD MnHashPos mn_hash_pos(uint32_t nbuckets, int lo, int hi) {
   p.fp = (uint32_t)(h >> 58);
   return p;
 }
+// 5-bit hash position kept in the record <-> global slot index (-1: the overflow area)
+MN_HD uint32_t mn_hs_of_slot(const MnHashPos& p, int slot) {
+  if (slot < 0) return MN_HS_OVF;
+  return ((uint32_t)slot >> 3) == p.b1 ? ((uint32_t)slot & 7u) : (8u + ((uint32_t)slot & 7u));
+}
+MN_HD int mn_slot_of_hs(const MnHashPos& p, uint32_t hs) {
+  if (hs >= MN_HS_OVF) return -1;
+  return (int)((hs < 8u ? p.b1 : p.b2) * 8u + (hs & 7u));
+}
 // returns record id or -1
 MN_HD int mn_hash_find(const MnImage& im, int lo, int hi) {
   MnHashPos p = mn_hash_pos(im.hash_nbuckets, lo, hi);
@@ -235,7 +238,7 @@ MN_HD int mn_hash_find(const MnImage& im, int lo, int hi) {
       uint32_t v = bk[s];
       if (v != 0 && (v >> MN_HASH_FP_SHIFT) == p.fp) {
         int r = (int)(v & ((1u << MN_HASH_FP_SHIFT) - 1)) - 1;
-        int2 lh = MN_REC_LH(im, r);
+        int2 lh = mn_rec_key(im, r);
         if (lh.x == lo && lh.y == hi) return r;
       }
     }
@@ -245,7 +248,7 @@ MN_HD int mn_hash_find(const MnImage& im, int lo, int hi) {
     uint32_t v = im.hash_ovf[i];
     if (v != 0) {
       int r = (int)v - 1;
-      int2 lh = MN_REC_LH(im, r);
+      int2 lh = mn_rec_key(im, r);
       if (lh.x == lo && lh.y == hi) return r;
     }
   }

@@ -1,7 +1,7 @@
 // mn_merge.cuh -- order-exact merge scheduler: one persistent CTA per image (sm_100a).
 //
 // Reproduces the reference's RunSegmentation / Merge loop (cc:539-573, cc:602-727) exactly, up to
-// the tie order among equal priorities (deterministic here: mp desc, lo asc, hi asc).
+// the tie order among equal priorities (deterministic here: mp desc, then the (u, D) scatter rule of mn_common.h).
 //
 // The reference's lazy heap is observationally an indexed map  record -> stored priority  holding
 // the records with stored mp >= 0 (cc:554-565).  A ROUND takes the next MN_H queue entries in pop
@@ -26,9 +26,13 @@
 // later, a lazily split radix tree of unsorted chunks keyed by (mp bits, lo, hi).  The queue is lazy
 // in two ways.  Like the reference's heap, an entry that no longer describes its record is dropped
 // when it surfaces (cc:554-559).  Unlike it, a record whose priority is re-stored LATER in pop order
-// than an entry it already has gets no new entry: rec[2r+1].z (`qmp`) remembers the priority of the
-// record's earliest queued entry (the "guard"); when the guard surfaces and the stored priority is
-// lower, an exact entry is queued then ("requeue").  Invariant: every live record with stored
+// than an entry it already has gets no new entry: two bits of the record (its GUARD STATE, mn_layout.h)
+// remember whether an entry at exactly the stored priority is queued (EXACT) or only one strictly
+// above it (ABOVE, the "guard"); when a guard surfaces and the stored priority is lower, an exact
+// entry is queued then ("requeue").  A priority is stored with a new entry only when it RISES (or when
+// the record has no queued entry, or is re-keyed without falling): every queued entry of a record was
+// pushed at a priority the record had, so the one pushed at its running maximum since the last push
+// is still queued whenever the state is not NONE.  Invariant: every live record with stored
 // mp >= 0 has a queued entry popping before-or-at its true position, so no pop can be missed, and
 // the sequence of EXACT pops -- the only ones with side effects -- is the reference's.
 //
@@ -120,12 +124,12 @@ struct MnSm {
   int peak_entries, peak_chunks;
   // candidates: staged loads
   int c_rec[MN_H]; float c_key[MN_H]; int c_lo[MN_H]; int c_hi[MN_H]; int c_kind[MN_H];
-  float4 c_val[MN_H]; int2 c_lh[MN_H]; uint4 c_obj[MN_H][2];
-  float c_rdiff[MN_H]; int c_dup[MN_H];
+  uint4 c_recw[MN_H]; int2 c_lh[MN_H]; uint4 c_obj[MN_H][2];  // the staged record (raw words), its key, both objects
+  int c_dup[MN_H];
   // candidates: classification
   float c_newmp[MN_H]; int c_merged[MN_H]; int c_surv[MN_H]; int c_abs[MN_H]; int c_na[MN_H]; int c_nb[MN_H];
   int c_ptra[MN_H]; int c_ptrb[MN_H]; int c_newptr[MN_H]; int c_cpbase[MN_H];
-  float c_same[MN_H]; int c_eslot[MN_H];
+  int c_eslot[MN_H];
   int c_pwbase[MN_H]; int c_npairs[MN_H]; int c_pbase[MN_H]; int c_pfill[MN_H];
   unsigned long long c_maxnew[MN_H];  // pop-order key (mn_pop_key) of the earliest-popping entry the candidate stores; 0: none
   int c_conflict[MN_H]; int c_accept[MN_H];
@@ -137,7 +141,8 @@ struct MnSm {
   union {
     struct {
       int cand[MN_WL]; int t[MN_WL]; int x[MN_WL]; int u[MN_WL];
-      float oml[MN_WL]; float same[MN_WL]; float diff[MN_WL]; float mp[MN_WL]; float q[MN_WL];
+      float oml[MN_WL]; int g[MN_WL]; float mpold[MN_WL];  // g / mpold: guard state and stored priority of the record that takes the sum
+      float mp[MN_WL];   // (refill parks its sorted leaf run in mp / lo / hi / eslot: keep them beyond w.ds)
       int lo[MN_WL]; int hi[MN_WL]; int eslot[MN_WL]; int islot[MN_WL];
     } pr;
     // distribute(): per entry (group << 16 | index in group); per group node / count / old tail /
@@ -413,19 +418,20 @@ MN_D void mn_flush_ins(const MnImage& im, MnSm& sm) {
   MN_SYNC();
 }
 
-// What a queue entry (emp, elo, ehi) is against its record (key lh, values v = oml, same, qmp, mp):
-//   DROP     the record is dead, or another entry guards it (emp != qmp), or it was re-keyed at the
-//            same priority (a fresh entry was queued then);
-//   exact    emp == qmp == mp and the key matches: the reference's valid pop (cc:554-559);
-//   REQUEUE  emp == qmp > mp >= 0: the guard of a record whose priority was re-stored lower;
-//   UNGUARD  emp == qmp and mp < 0: the guard of a record that went dormant.
+// What a queue entry (emp, elo, ehi) is against its record (raw words rw, mn_layout.h):
+//   DROP     the record is dead, or no entry is expected (NONE), or it is not the expected one;
+//   exact    state EXACT, emp == mp and the key matches: the reference's valid pop (cc:554-559);
+//   REQUEUE  state ABOVE, emp > mp >= 0: a guard of a record whose priority was re-stored lower;
+//   UNGUARD  state ABOVE, mp < 0: a guard of a record that went dormant.
 // Returns MN_K_DROP / MN_K_RESTORE (meaning "exact") / MN_K_REQUEUE / MN_K_UNGUARD.
-MN_D int mn_entry_state(float emp, int elo, int ehi, int2 lh, float4 v) {
-  if (lh.x < 0) return MN_K_DROP;
-  if (!(v.z == emp)) return MN_K_DROP;
-  if (v.w == emp) return (lh.x == elo && lh.y == ehi) ? MN_K_RESTORE : MN_K_DROP;
-  if (v.w >= 0.0f) return MN_K_REQUEUE;
-  return MN_K_UNGUARD;
+MN_D int mn_entry_state(float emp, int elo, int ehi, uint4 rw) {
+  const int lo = mn_rec_lo(rw.x);
+  if (lo < 0) return MN_K_DROP;
+  const uint32_t g = mn_rec_guard(rw.x);
+  const float mp = mn_u2f(rw.w);
+  if (g == MN_G_EXACT) return (mp == emp && lo == elo && mn_rec_hi(rw.y) == ehi) ? MN_K_RESTORE : MN_K_DROP;
+  if (g == MN_G_ABOVE && emp > mp) return mp >= 0.0f ? MN_K_REQUEUE : MN_K_UNGUARD;
+  return MN_K_DROP;
 }
 
 // chunk ids [k0, k0 + n) of leaf `node` into sm.cw_chunk (thread 0 follows the chain past the directory;
@@ -477,12 +483,10 @@ MN_D void mn_split_leaf(const MnImage& im, MnSm& sm, int root, int node, int lev
       if (c < 0) { mn_fail(im, MN_ERR_INTERNAL); continue; }
       uint4 e = im.q_ent[(size_t)c * MN_QCH + s];
       int rec = (int)e.y;
-      uint4 ra_; float4 v;
-      mn_load_rec(im, rec, &ra_, &v);
-      int2 lh = make_int2((int)ra_.x, (int)ra_.y);
+      const uint4 rw = mn_load_rec(im, rec);
       float emp = mn_u2f(e.x);
-      int st = mn_entry_state(emp, (int)e.z, (int)e.w, lh, v);
-      if (st == MN_K_UNGUARD) { v.z = -1.0f; MN_REC_B(im, rec) = v; }
+      int st = mn_entry_state(emp, (int)e.z, (int)e.w, rw);
+      if (st == MN_K_UNGUARD) MN_REC(im, rec).x = mn_rec_with_guard(rw.x, MN_G_NONE);
       else if (st != MN_K_DROP) {  // the entry keeps its own key (a guard stays where it is)
         int p = mn_agg_inc(&sm.npr);
         sm.sb_mp[p] = emp; sm.sb_lo[p] = (int)e.z; sm.sb_hi[p] = (int)e.w; sm.sb_rec[p] = rec;
@@ -668,12 +672,10 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
         if (c < 0) { mn_fail(im, MN_ERR_INTERNAL); continue; }
         uint4 e = im.q_ent[(size_t)c * MN_QCH + s];
         int rec = (int)e.y;
-        uint4 ra_; float4 v;
-        mn_load_rec(im, rec, &ra_, &v);
-        int2 lh = make_int2((int)ra_.x, (int)ra_.y);
+        const uint4 rw = mn_load_rec(im, rec);
         float emp = mn_u2f(e.x);
-        int st = mn_entry_state(emp, (int)e.z, (int)e.w, lh, v);
-        if (st == MN_K_UNGUARD) { v.z = -1.0f; MN_REC_B(im, rec) = v; }
+        int st = mn_entry_state(emp, (int)e.z, (int)e.w, rw);
+        if (st == MN_K_UNGUARD) MN_REC(im, rec).x = mn_rec_with_guard(rw.x, MN_G_NONE);
         else if (st != MN_K_DROP) {
           int p = mn_agg_inc(&sm.npr);
           if (p < MN_SB) { sm.sb_mp[p] = emp; sm.sb_lo[p] = (int)e.z; sm.sb_hi[p] = (int)e.w; sm.sb_rec[p] = rec; }
@@ -736,11 +738,9 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
     MN_FOR(i, ntake) {
       float mp; int lo, hi, rec;
       mn_decode_init(A, im.init_keys[sc + i], &mp, &lo, &hi, &rec);
-      uint4 ra_; float4 v;
-      mn_load_rec(im, rec, &ra_, &v);
-      int2 lh = make_int2((int)ra_.x, (int)ra_.y);
-      int st = mn_entry_state(mp, lo, hi, lh, v);
-      if (st == MN_K_UNGUARD) { v.z = -1.0f; MN_REC_B(im, rec) = v; st = MN_K_DROP; }
+      const uint4 rw = mn_load_rec(im, rec);
+      int st = mn_entry_state(mp, lo, hi, rw);
+      if (st == MN_K_UNGUARD) { MN_REC(im, rec).x = mn_rec_with_guard(rw.x, MN_G_NONE); st = MN_K_DROP; }
       int p = nleaf + i;
       sm.sb_mp[p] = st != MN_K_DROP ? mp : MN_NEG_INF; sm.sb_lo[p] = lo; sm.sb_hi[p] = hi; sm.sb_rec[p] = rec;
     }
@@ -776,14 +776,11 @@ MN_D void mn_refill(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
     MN_FOR(i, nleaf + ntake) {
       if (sm.sb_mp[i] > MN_NEG_INF) {
         const int rec = sm.sb_rec[i];
-        uint4 ra_; float4 v;
-        mn_load_rec(im, rec, &ra_, &v);
-        const int2 lh = make_int2((int)ra_.x, (int)ra_.y);
-        if (mn_entry_state(sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i], lh, v) == MN_K_REQUEUE) {
-          v.z = v.w;
-          MN_REC_B(im, rec) = v;
+        const uint4 rw = mn_load_rec(im, rec);
+        if (mn_entry_state(sm.sb_mp[i], sm.sb_lo[i], sm.sb_hi[i], rw) == MN_K_REQUEUE) {
+          MN_REC(im, rec).x = mn_rec_with_guard(rw.x, MN_G_EXACT);
           MN_ATOMIC_ADD(&sm.tmp1, 1);
-          mn_push_entry(sm, v.w, lh.x, lh.y, rec);  // cold -> insert buffer; still hot-bound -> ne, merged below
+          mn_push_entry(sm, mn_u2f(rw.w), mn_rec_lo(rw.x), mn_rec_hi(rw.y), rec);  // cold -> insert buffer; still hot-bound -> ne, merged below
           sm.sb_mp[i] = MN_NEG_INF;
         }
       }
@@ -953,14 +950,18 @@ MN_D void mn_push_entry(MnSm& sm, float mp, int lo, int hi, int rec) {
   if (cold) { sm.ins_mp[p] = mp; sm.ins_lo[p] = lo; sm.ins_hi[p] = hi; sm.ins_rec[p] = rec; }
   else { sm.ne_mp[p] = mp; sm.ne_lo[p] = lo; sm.ne_hi[p] = hi; sm.ne_rec[p] = rec; }
 }
-// Store priority `mp` on a record whose guard priority is `q` (-1: no queued entry): queue an entry
-// unless an earlier-popping one already guards the record.  Returns the new guard priority.
-MN_D float mn_store_priority(MnSm& sm, float mp, float q, int lo, int hi, int rec) {
-  if (mp >= 0.0f && !(q > mp)) {
+// Store priority `mp` on a record whose stored priority was `mp_old` and whose guard state was `g_old`
+// (MN_G_NONE: no queued entry): queue an entry unless one popping before-or-at the new position is known to be
+// queued -- that is, unless the priority did not rise (a re-keyed record: fell; its old entries carry the old
+// key, which orders equal priorities).  Returns the new guard state.
+MN_D uint32_t mn_store_priority(MnSm& sm, float mp, float mp_old, uint32_t g_old, bool rekey, int lo, int hi, int rec) {
+  if (!(mp >= 0.0f)) return g_old == MN_G_NONE ? MN_G_NONE : MN_G_ABOVE;  // dormant; a queued entry stays queued
+  const bool push = g_old == MN_G_NONE || (rekey ? mp >= mp_old : mp > mp_old);
+  if (push) {
     mn_push_entry(sm, mp, lo, hi, rec);
-    return mp;
+    return MN_G_EXACT;
   }
-  return q;
+  return (g_old == MN_G_EXACT && mp == mp_old) ? MN_G_EXACT : MN_G_ABOVE;
 }
 
 // ---- hash bucket helpers on buckets already in registers ------------------------------------------
@@ -1016,15 +1017,13 @@ MN_D void mn_plan_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const
     int i = p0 + ii;
     int j = sm.w.pr.cand[i], t = sm.w.pr.t[i];
     int a = sm.c_surv[j], b = sm.c_abs[j];
-    uint4 ta; float4 v;
-    mn_load_rec(im, t, &ta, &v);  // one 32-byte sector: key, hash slot, sums, priorities
-    const int2 lh = make_int2((int)ta.x, (int)ta.y);
-    const float tdiff = mn_u2f(ta.w);
+    const uint4 tw = mn_load_rec(im, t);  // key, hash position, guard state, oml, mp
+    const int2 lh = make_int2(mn_rec_lo(tw.x), mn_rec_hi(tw.y));
     int x = lh.x == b ? lh.y : lh.x;
     if ((lh.x != b && lh.y != b) || x == a || x < 0) {  // cc:665-673
       mn_fail(im, MN_ERR_INTERNAL);
       sm.w.pr.x[i] = a; sm.w.pr.u[i] = -1; sm.w.pr.mp[i] = -1.0f; sm.w.pr.eslot[i] = -1; sm.w.pr.islot[i] = -1;
-      sm.w.pr.lo[i] = 0; sm.w.pr.hi[i] = 0; sm.w.pr.oml[i] = 0; sm.w.pr.same[i] = 0; sm.w.pr.diff[i] = 0; sm.w.pr.q[i] = -1.0f;
+      sm.w.pr.lo[i] = 0; sm.w.pr.hi[i] = 0; sm.w.pr.oml[i] = 0; sm.w.pr.g[i] = 0; sm.w.pr.mpold[i] = -1.0f;
       continue;
     }
     int nlo = a < x ? a : x, nhi = a < x ? x : a;
@@ -1032,6 +1031,8 @@ MN_D void mn_plan_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const
     uint32_t bn[16];
     mn_load_bucket4(im, pn.b1, bn); mn_load_bucket4(im, pn.b2, bn + 8);
     uint4 ox = im.obj[x];
+    // where t sits in the hash under its old key (cc:680 erases it)
+    const int eslot = mn_slot_of_hs(mn_hash_pos(im.hash_nbuckets, lh.x, lh.y), mn_rec_hs(tw.x));
     // partner record u = (a, x) if the survivor is already linked to x (cc:685-686)
     int u = -1, islot = -1, f1 = 0, f2 = 0;
     for (int s = 0; s < 8; s++) { f1 += bn[s] == 0; f2 += bn[8 + s] == 0; }
@@ -1043,36 +1044,37 @@ MN_D void mn_plan_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const
         if (c0 < 0) c0 = r; else if (c1 < 0) c1 = r; else { srest = s; break; }
       }
     }
-    float4 uv = make_float4(0.f, 0.f, 0.f, 0.f); float ud = 0.f;
+    uint4 uw = make_uint4(MN_REC_DEAD, 0u, 0u, 0u);
     if (c0 >= 0) {  // fingerprint matches: key and values of (up to) two candidates in one round trip
-      uint4 a0; float4 v0;
-      mn_load_rec(im, c0, &a0, &v0);
-      uint4 a1 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u); float4 v1 = v0;
-      if (c1 >= 0) mn_load_rec(im, c1, &a1, &v1);
-      if ((int)a0.x == nlo && (int)a0.y == nhi) { u = c0; uv = v0; ud = mn_u2f(a0.w); }
-      else if (c1 >= 0 && (int)a1.x == nlo && (int)a1.y == nhi) { u = c1; uv = v1; ud = mn_u2f(a1.w); }
+      const uint4 w0 = mn_load_rec(im, c0);
+      uint4 w1 = make_uint4(MN_REC_DEAD, 0u, 0u, 0u);
+      if (c1 >= 0) w1 = mn_load_rec(im, c1);
+      if (mn_rec_lo(w0.x) == nlo && mn_rec_hi(w0.y) == nhi) { u = c0; uw = w0; }
+      else if (c1 >= 0 && mn_rec_lo(w1.x) == nlo && mn_rec_hi(w1.y) == nhi) { u = c1; uw = w1; }
     }
     for (int s = srest; s < 16 && u < 0; s++) {  // (a third fingerprint match: practically never)
       uint32_t hv = bn[s];
       if (hv != 0 && (hv >> MN_HASH_FP_SHIFT) == pn.fp) {
         int r = (int)(hv & ((1u << MN_HASH_FP_SHIFT) - 1)) - 1;
-        uint4 a2 = MN_REC_A(im, r);
-        if ((int)a2.x == nlo && (int)a2.y == nhi) { u = r; uv = MN_REC_B(im, r); ud = mn_u2f(a2.w); }
+        const uint4 w2 = mn_load_rec(im, r);
+        if (mn_rec_lo(w2.x) == nlo && mn_rec_hi(w2.y) == nhi) { u = r; uw = w2; }
       }
     }
     if (u < 0 && novf > 0) {
       u = mn_ovf_find(sm, novf, nlo, nhi);
-      if (u >= 0) { uv = MN_REC_B(im, u); ud = mn_u2f(MN_REC_A(im, u).w); }
+      if (u >= 0) uw = mn_load_rec(im, u);
     }
     if (u < 0) {  // free slot for the re-keyed record: the emptier bucket first
       int first = (f1 >= f2) ? 0 : 8;
       for (int s = 0; s < 8 && islot < 0; s++) if (bn[first + s] == 0) islot = (int)((first ? pn.b2 : pn.b1) * 8 + s);
       for (int s = 0; s < 8 && islot < 0; s++) if (bn[(8 - first) + s] == 0) islot = (int)((first ? pn.b1 : pn.b2) * 8 + s);
     }
-    float oml = v.x, same = v.y, diff = tdiff, q = v.z;
-    if (u >= 0) {  // cc:690-692: that += this
-      oml = MN_FADD(uv.x, v.x); diff = MN_FADD(ud, tdiff); same = MN_FADD(uv.y, v.y);
-      q = uv.z;
+    // the record that carries the pair from now on: u (cc:690-692: that += this) or the re-keyed t
+    float oml = mn_u2f(tw.z), mpold = mn_u2f(tw.w);
+    uint32_t g = mn_rec_guard(tw.x);
+    if (u >= 0) {
+      oml = MN_FADD(mn_u2f(uw.z), oml);
+      mpold = mn_u2f(uw.w); g = mn_rec_guard(uw.x) | (mn_rec_hs(uw.x) << 2);  // (u keeps its hash position)
     }
     int nx = mn_nc_npix(ox.x), cx = mn_nc_cls(ox.x);
     const float* clpa = c_clp + (size_t)(j * 3 + 2) * A.C;
@@ -1080,9 +1082,9 @@ MN_D void mn_plan_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const
     float mp;
     if (a < x) mp = mn_priority(oml, A.omf, A.mlb, A.C, sm.c_na[j], sm.c_merged[j], clpa, nx, cx, clpx, nullptr);
     else mp = mn_priority(oml, A.omf, A.mlb, A.C, nx, cx, clpx, sm.c_na[j], sm.c_merged[j], clpa, nullptr);
-    sm.w.pr.x[i] = x; sm.w.pr.u[i] = u; sm.w.pr.oml[i] = oml; sm.w.pr.same[i] = same; sm.w.pr.diff[i] = diff;
-    sm.w.pr.mp[i] = mp; sm.w.pr.lo[i] = nlo; sm.w.pr.hi[i] = nhi; sm.w.pr.q[i] = q;
-    sm.w.pr.eslot[i] = (int)ta.z; sm.w.pr.islot[i] = islot;
+    sm.w.pr.x[i] = x; sm.w.pr.u[i] = u; sm.w.pr.oml[i] = oml; sm.w.pr.g[i] = (int)g; sm.w.pr.mpold[i] = mpold;
+    sm.w.pr.mp[i] = mp; sm.w.pr.lo[i] = nlo; sm.w.pr.hi[i] = nhi;
+    sm.w.pr.eslot[i] = eslot; sm.w.pr.islot[i] = islot;
     if (mp >= 0.0f) MN_ATOMIC_MAX(&sm.c_maxnew[j], mn_pop_key(mp, nlo, nhi));
   }
 }
@@ -1096,22 +1098,23 @@ MN_D void mn_commit_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, int
     int t = sm.w.pr.t[i], u = sm.w.pr.u[i];
     if (sm.w.pr.eslot[i] >= 0) im.hash[sm.w.pr.eslot[i]] = 0;  // cc:680
     else mn_ovf_erase(sm, t);
-    float mp = sm.w.pr.mp[i];
+    const float mp = sm.w.pr.mp[i];
+    const int lo = sm.w.pr.lo[i], hi = sm.w.pr.hi[i];
+    const uint32_t gw = (uint32_t)sm.w.pr.g[i];
     if (u >= 0) {  // cc:690-698: fold t into u, t dies
-      float q = mn_store_priority(sm, mp, sm.w.pr.q[i], sm.w.pr.lo[i], sm.w.pr.hi[i], u);
-      MN_WATCH(u, "fold-into mp %.9g q_old %.9g q_new %.9g key %d %d (t=%d)", mp, sm.w.pr.q[i], q, sm.w.pr.lo[i], sm.w.pr.hi[i], t);
+      const uint32_t g = mn_store_priority(sm, mp, sm.w.pr.mpold[i], gw & 3u, false, lo, hi, u);
+      MN_WATCH(u, "fold-into mp %.9g mp_old %.9g g_old %u g_new %u key %d %d (t=%d)", mp, sm.w.pr.mpold[i], gw & 3u, g, lo, hi, t);
       MN_WATCH(t, "folded (dies) into %d", u);
-      MN_REC_B(im, u) = make_float4(sm.w.pr.oml[i], sm.w.pr.same[i], q, mp);
-      reinterpret_cast<float*>(&MN_REC_A(im, u))[3] = sm.w.pr.diff[i];
-      MN_REC_LH(im, t) = make_int2(-1, -1);  // cc:694
+      mn_store_rec(im, u, make_uint4(mn_rec_pack_x(lo, gw >> 2, g), (uint32_t)hi, mn_f2u(sm.w.pr.oml[i]), mn_f2u(mp)));
+      MN_REC(im, t).x = MN_REC_DEAD;  // cc:694
       mn_clear_live(im, A, t);
     } else {  // cc:659-664,677,700-706: t is re-keyed to (survivor, x)
-      float q = mn_store_priority(sm, mp, sm.w.pr.q[i], sm.w.pr.lo[i], sm.w.pr.hi[i], t);
-      MN_WATCH(t, "adopt mp %.9g q_old %.9g q_new %.9g key %d %d", mp, sm.w.pr.q[i], q, sm.w.pr.lo[i], sm.w.pr.hi[i]);
-      MN_REC_LH(im, t) = make_int2(sm.w.pr.lo[i], sm.w.pr.hi[i]);  // (the hash verifies keys through the record)
-      const int hs = mn_hash_insert_hint(im, sm, sm.w.pr.lo[i], sm.w.pr.hi[i], t, sm.w.pr.islot[i]);
-      mn_store_rec(im, t, make_uint4((uint32_t)sm.w.pr.lo[i], (uint32_t)sm.w.pr.hi[i], (uint32_t)hs, mn_f2u(sm.w.pr.diff[i])),
-                   make_float4(sm.w.pr.oml[i], sm.w.pr.same[i], q, mp));
+      const uint32_t g = mn_store_priority(sm, mp, sm.w.pr.mpold[i], gw & 3u, true, lo, hi, t);
+      MN_WATCH(t, "adopt mp %.9g mp_old %.9g g_old %u g_new %u key %d %d", mp, sm.w.pr.mpold[i], gw & 3u, g, lo, hi);
+      *reinterpret_cast<uint2*>(&MN_REC(im, t)) = make_uint2(mn_rec_pack_x(lo, MN_HS_NONE, g), (uint32_t)hi);  // (the hash verifies keys through the record)
+      const int hs = mn_hash_insert_hint(im, sm, lo, hi, t, sm.w.pr.islot[i]);
+      mn_store_rec(im, t, make_uint4(mn_rec_pack_x(lo, mn_hs_of_slot(mn_hash_pos(im.hash_nbuckets, lo, hi), hs), g), (uint32_t)hi,
+                                     mn_f2u(sm.w.pr.oml[i]), mn_f2u(mp)));
     }
   }
 }
@@ -1120,12 +1123,12 @@ MN_D void mn_commit_pairs(const MnImage& im, MnSm& sm, const MnMergeArgs& A, int
 MN_D void mn_commit_merge_object(const MnImage& im, MnSm& sm, const MnMergeArgs& A, int j) {
   int a = sm.c_surv[j], b = sm.c_abs[j], r = sm.c_rec[j];
   // cc:635-642 (obj.w, the live mask of pixel a, is updated concurrently by atomics: leave it alone)
-  *reinterpret_cast<uint2*>(&im.obj[a]) = make_uint2(mn_pack_nc(sm.c_na[j], sm.c_merged[j]), mn_f2u(sm.c_same[j]));
+  im.obj[a].x = mn_pack_nc(sm.c_na[j], sm.c_merged[j]);
   im.obj[a].z = (uint32_t)sm.c_newptr[j];
   im.parent[b] = a;                                        // cc:724-725
   if (sm.c_eslot[j] >= 0) im.hash[sm.c_eslot[j]] = 0;      // cc:645-647
   else mn_ovf_erase(sm, r);
-  MN_REC_LH(im, r) = make_int2(-1, -1);                    // cc:726
+  MN_REC(im, r).x = MN_REC_DEAD;                           // cc:726
   mn_clear_live(im, A, r);
 }
 
@@ -1214,24 +1217,22 @@ MN_D void mn_stage_candidates(const MnImage& im, MnSm& sm, const MnMergeArgs& A,
   MN_FOR(w, n * 4) {
     const int j = w >> 2, role = w & 3;
     const int rec = HOT_REC(j), lo = HOT_LO(j), hi = HOT_HI(j);
-    if (role == 0) {  // the record: one 32-byte sector
-      uint4 ra; float4 rb;
-      mn_load_rec(im, rec, &ra, &rb);
-      sm.c_val[j] = rb;
-      sm.c_lh[j] = make_int2((int)ra.x, (int)ra.y); sm.c_eslot[j] = (int)ra.z; sm.c_rdiff[j] = mn_u2f(ra.w);
+    if (role == 0) {  // the record: 16 bytes
+      const uint4 rw = mn_load_rec(im, rec);
+      sm.c_recw[j] = rw;
+      sm.c_lh[j] = make_int2(mn_rec_lo(rw.x), mn_rec_hi(rw.y));
       sm.c_rec[j] = rec; sm.c_key[j] = HOT_MP(j); sm.c_lo[j] = lo; sm.c_hi[j] = hi;
       sm.c_kind[j] = MN_K_DROP; sm.c_npairs[j] = 0; sm.c_pfill[j] = 0; sm.c_maxnew[j] = 0; sm.c_conflict[j] = 0;
       sm.c_nb[j] = 0; sm.c_accept[j] = 0; sm.c_cpbase[j] = -1;
     } else if (role == 1) sm.c_obj[j][0] = im.obj[lo];
     else if (role == 2) sm.c_obj[j][1] = im.obj[hi];
     else {
-      // duplicates of an earlier window entry: bit 0 same record and priority, bit 1 also the same key
+      // an earlier window entry of the same record: bit 0; bit 1: also the same priority and key
       const float mp = HOT_MP(j);
       int d = 0;
       for (int i = 0; i < j; i++) {
         if (HOT_REC(i) != rec) continue;  // (one shared-memory read per earlier entry; the rest only on a hit)
-        const bool same = HOT_MP(i) == mp;
-        d |= same ? (1 | ((HOT_LO(i) == lo && HOT_HI(i) == hi) ? 2 : 0)) : 0;
+        d |= 1 | ((HOT_MP(i) == mp && HOT_LO(i) == lo && HOT_HI(i) == hi) ? 2 : 0);
       }
       sm.c_dup[j] = d;
     }
@@ -1261,13 +1262,14 @@ MN_D void mn_stage_candidates(const MnImage& im, MnSm& sm, const MnMergeArgs& A,
 MN_D void mn_classify(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const float* c_clp, int j) {
   const float mp = sm.c_key[j]; const int lo = sm.c_lo[j], hi = sm.c_hi[j];
   const int2 lh = sm.c_lh[j];
-  const float4 v = sm.c_val[j];
-  int st = mn_entry_state(mp, lo, hi, lh, v);
-  // a duplicate of an earlier window entry (same record, same priority; same key if exact)?
+  const uint4 rw = sm.c_recw[j];
+  int st = mn_entry_state(mp, lo, hi, rw);
+  // a second entry of a record in one window: an exact duplicate (same priority and key) of an exact entry, or --
+  // the earlier one then is a guard too, and guards the record alone -- any later entry of a guarded record
   if (st != MN_K_DROP && (sm.c_dup[j] & (st == MN_K_RESTORE ? 2 : 1))) st = MN_K_DROP;
   if (st != MN_K_RESTORE) {
     sm.c_kind[j] = st;
-    if (st == MN_K_REQUEUE) sm.c_maxnew[j] = mn_pop_key(v.w, lh.x, lh.y);
+    if (st == MN_K_REQUEUE) sm.c_maxnew[j] = mn_pop_key(mn_u2f(rw.w), lh.x, lh.y);
     // a guard touches its record, whose endpoints may have moved since the entry was queued
     if (st != MN_K_DROP) { sm.c_lo[j] = lh.x; sm.c_hi[j] = lh.y; }
     return;
@@ -1275,7 +1277,7 @@ MN_D void mn_classify(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const f
   const uint4 o1 = sm.c_obj[j][0], o2 = sm.c_obj[j][1];
   const int n1 = mn_nc_npix(o1.x), n2 = mn_nc_npix(o2.x), cl1 = mn_nc_cls(o1.x), cl2 = mn_nc_cls(o2.x);
   int merged;
-  const float nmp = mn_priority(v.x, A.omf, A.mlb, A.C, n1, cl1, c_clp + (size_t)(j * 3) * A.C, n2, cl2,
+  const float nmp = mn_priority(mn_u2f(rw.z), A.omf, A.mlb, A.C, n1, cl1, c_clp + (size_t)(j * 3) * A.C, n2, cl2,
                                 c_clp + (size_t)(j * 3 + 1) * A.C, &merged);  // cc:560
   sm.c_newmp[j] = nmp;
   sm.c_merged[j] = merged;
@@ -1286,7 +1288,8 @@ MN_D void mn_classify(const MnImage& im, MnSm& sm, const MnMergeArgs& A, const f
     sm.c_na[j] = n1 + n2; sm.c_nb[j] = swap ? n1 : n2;
     const uint4 oa = swap ? o2 : o1, ob = swap ? o1 : o2;
     sm.c_ptra[j] = (int)oa.z; sm.c_ptrb[j] = (int)ob.z;
-    sm.c_same[j] = MN_FADD(mn_u2f(oa.y), MN_FADD(v.y, mn_u2f(ob.y)));  // cc:641-642
+    // where the record sits in the hash (cc:645-647 erases it)
+    sm.c_eslot[j] = mn_slot_of_hs(mn_hash_pos(im.hash_nbuckets, lh.x, lh.y), mn_rec_hs(rw.x));
   } else {  // cc:563-565
     sm.c_kind[j] = MN_K_RESTORE;
     if (nmp >= 0.0f) sm.c_maxnew[j] = mn_pop_key(nmp, lo, hi);
@@ -1369,7 +1372,7 @@ MN_D void mn_solo_merge(const MnImage& im, MnSm& sm, const MnMergeArgs& A, float
       sm.c_rec[0] = sm.c_rec[f]; sm.c_key[0] = sm.c_key[f]; sm.c_lo[0] = sm.c_lo[f]; sm.c_hi[0] = sm.c_hi[f];
       sm.c_newmp[0] = sm.c_newmp[f]; sm.c_merged[0] = sm.c_merged[f];
       sm.c_surv[0] = sm.c_surv[f]; sm.c_abs[0] = sm.c_abs[f]; sm.c_na[0] = sm.c_na[f]; sm.c_nb[0] = sm.c_nb[f];
-      sm.c_ptra[0] = sm.c_ptra[f]; sm.c_ptrb[0] = sm.c_ptrb[f]; sm.c_same[0] = sm.c_same[f]; sm.c_eslot[0] = sm.c_eslot[f];
+      sm.c_ptra[0] = sm.c_ptra[f]; sm.c_ptrb[0] = sm.c_ptrb[f]; sm.c_eslot[0] = sm.c_eslot[f];
     }
   }
   MN_SYNC();
@@ -1466,11 +1469,7 @@ MN_D bool mn_solo_needs_gc(const MnImage& im, MnSm& sm, const MnMergeArgs& A, in
 // consume the non-event entries of the window prefix [0, n): forget guards of dormant records
 MN_D void mn_consume_unguard(const MnImage& im, MnSm& sm, int n) {
   MN_FOR(j, n) {
-    if (sm.c_kind[j] == MN_K_UNGUARD) {
-      float4 v = sm.c_val[j];
-      v.z = -1.0f;
-      MN_REC_B(im, sm.c_rec[j]) = v;
-    }
+    if (sm.c_kind[j] == MN_K_UNGUARD) MN_REC(im, sm.c_rec[j]).x = mn_rec_with_guard(sm.c_recw[j].x, MN_G_NONE);
   }
 }
 
@@ -1799,7 +1798,7 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     else MN_FOR(i, n) {
       const int rec = (int)im.hash_ovf[i] - 1;
       int2 lh = make_int2(-1, -1);
-      if (rec >= 0) lh = MN_REC_LH(im, rec);
+      if (rec >= 0) lh = mn_rec_key(im, rec);
       sm.ovf_lo[i] = lh.x; sm.ovf_hi[i] = lh.y; sm.ovf_rec[i] = rec;
     }
   }
@@ -1814,14 +1813,14 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
     if (MN_T0) {
       long long t0 = clock64();
       unsigned idx = 12345u;
-      for (int i = 0; i < 64; i++) { int2 v = MN_REC_LH(im, idx % (unsigned)E); idx = idx * 1664525u + 1013904223u + (unsigned)v.x; }
+      for (int i = 0; i < 64; i++) { int2 v = mn_rec_key(im, (int)(idx % (unsigned)E)); idx = idx * 1664525u + 1013904223u + (unsigned)v.x; }
       sm.cyc[MN_CY_PAIRLIST] = clock64() - t0 + (idx == 7u ? 1 : 0);
     }
     MN_SYNC();
     long long t0 = clock64();
     unsigned idx = 777u * (MN_TID + 1);
     for (int i = 0; i < 16; i++) {
-      int2 v = MN_REC_LH(im, idx % (unsigned)E);
+      int2 v = mn_rec_key(im, (int)(idx % (unsigned)E));
       idx = idx * 1664525u + 1013904223u + (unsigned)v.x;
       sm.ct_obj[MN_TID % MN_CT] = (int)idx;
       MN_SYNC();
@@ -2011,22 +2010,19 @@ MN_D void mn_merge_image(const MnImage& im, MnSm& sm, const MnMergeArgs& A, floa
       if (!sm.c_accept[j]) continue;
       const int k = sm.c_kind[j];
       const int rec = sm.c_rec[j];
-      MN_WATCH(rec, "commit cand j=%d kind %d key %.9g (%d,%d) val mp %.9g q %.9g newmp %.9g", j, k, sm.c_key[j], sm.c_lo[j], sm.c_hi[j], sm.c_val[j].w, sm.c_val[j].z, sm.c_newmp[j]);
-      if (k == MN_K_RESTORE) {  // cc:563-565: the consumed entry was the record's guard
-        float4 v = sm.c_val[j];
-        v.w = sm.c_newmp[j];
-        v.z = mn_store_priority(sm, v.w, -1.0f, sm.c_lo[j], sm.c_hi[j], rec);
-        MN_REC_B(im, rec) = v;
+      MN_WATCH(rec, "commit cand j=%d kind %d key %.9g (%d,%d) mp %.9g guard %u newmp %.9g", j, k, sm.c_key[j], sm.c_lo[j], sm.c_hi[j], mn_u2f(sm.c_recw[j].w), mn_rec_guard(sm.c_recw[j].x), sm.c_newmp[j]);
+      const uint4 rw = sm.c_recw[j];
+      if (k == MN_K_RESTORE) {  // cc:563-565: the consumed entry was the record's only expected one
+        const float nmp = sm.c_newmp[j];
+        const uint32_t g = mn_store_priority(sm, nmp, mn_u2f(rw.w), MN_G_NONE, false, sm.c_lo[j], sm.c_hi[j], rec);
+        mn_store_rec(im, rec, make_uint4(mn_rec_with_guard(rw.x, g), rw.y, rw.z, mn_f2u(nmp)));  // (no other accepted member touches it)
       } else if (k == MN_K_MERGE) {
         mn_commit_merge_object(im, sm, A, j);
-      } else if (k == MN_K_REQUEUE) {
-        float4 v = sm.c_val[j];
-        v.z = mn_store_priority(sm, v.w, -1.0f, sm.c_lh[j].x, sm.c_lh[j].y, rec);
-        MN_REC_B(im, rec) = v;
+      } else if (k == MN_K_REQUEUE) {  // the guard is consumed: the exact entry takes its place
+        const uint32_t g = mn_store_priority(sm, mn_u2f(rw.w), mn_u2f(rw.w), MN_G_NONE, false, sm.c_lh[j].x, sm.c_lh[j].y, rec);
+        MN_REC(im, rec).x = mn_rec_with_guard(rw.x, g);
       } else if (k == MN_K_UNGUARD) {
-        float4 v = sm.c_val[j];
-        v.z = -1.0f;
-        MN_REC_B(im, rec) = v;
+        MN_REC(im, rec).x = mn_rec_with_guard(rw.x, MN_G_NONE);
       }
     }
     MN_FOR(i, ncand * A.C) {

@@ -185,9 +185,9 @@ class BatchSegmenter:
         return s.as_dict()
 
     def total_logprob(self, image):
-        """(class term, object sameness term, record differentness term, total) of the last run's
-        segmentation of ``image`` -- the reference's printed-only ComputeTotalLogprob
-        (segment.cc:272-287), evaluated on the GPU from the maintained sufficient statistics."""
+        """(class term, sameness term, differentness term, total) of the last run's segmentation of
+        ``image`` -- the number the reference only prints (segment.cc:314-350, ComputeTotalLogprobFromScratch),
+        evaluated on the GPU in float64 from the maps and the final label mask."""
         out = (ctypes.c_double * 4)()
         st = _lib.lib().mn_plan_image_logprob(self._plan, int(image), out)
         if st != 0:

@@ -265,11 +265,11 @@ def canonical_result(mask, object_class):
     return cm, ncls
 
 
-def total_logprob_from_scratch(mask, object_class, class_pred, adj_pred, offset_list,
-                               object_merge_factor):
-    """float64 evaluation of segment.cc:314-350 restricted to what the output mask determines:
-    class term over instance pixels + omf * (same-term inside instances + different-term across),
-    with all class-0 (label 0) pixels treated as one region whose class is 0."""
+def total_logprob_terms_from_scratch(mask, object_class, class_pred, adj_pred, offset_list):
+    """float64 evaluation of segment.cc:314-350 restricted to what the output mask determines: (class term over
+    all pixels -- the class of the pixel's instance, class 0 for background --, same-term over the in-image
+    (pixel, offset) pairs inside one label, different-term over the pairs across two); all class-0 (label 0)
+    pixels are one region."""
     cp = np.asarray(class_pred, dtype=np.float32).clip(EPS, 1.0 - EPS).astype(np.float64)
     ap = np.asarray(adj_pred, dtype=np.float32).clip(EPS, 1.0 - EPS).astype(np.float64)
     m = np.asarray(mask)
@@ -293,7 +293,14 @@ def total_logprob_from_scratch(mask, object_class, class_pred, adj_pred, offset_
         same = a == b
         tot_same += np.log(s[same]).sum()
         tot_diff += np.log(1.0 - s[~same]).sum()
-    return float(tot_class + (tot_diff + tot_same) * object_merge_factor)
+    return float(tot_class), float(tot_same), float(tot_diff)
+
+
+def total_logprob_from_scratch(mask, object_class, class_pred, adj_pred, offset_list,
+                               object_merge_factor):
+    """class term + omf * (same-term + different-term) of total_logprob_terms_from_scratch."""
+    tc, ts, td = total_logprob_terms_from_scratch(mask, object_class, class_pred, adj_pred, offset_list)
+    return float(tc + (td + ts) * object_merge_factor)
 
 
 # ---- the step after the path (SURVEY 8f): checkers for mergenet_b200/csrc/mn_post.cuh ------------

@@ -32,7 +32,7 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   im.parent = zalloc<int>(N);
   im.pix_cap = 2 * (3 * N + 2048);
   im.pix_pool = zalloc<int>(im.pix_cap);
-  im.rec = zalloc<uint4>(2 * E);
+  im.rec = zalloc<uint4>(E);
   // EMUL_HASH_PERMILLE: slots per 1000 records (default 1600); a tight table exercises the overflow area
   const long long permille = getenv("EMUL_HASH_PERMILLE") ? atoll(getenv("EMUL_HASH_PERMILLE")) : 1600;
   im.hash_nbuckets = (uint32_t)(E * permille / 1000 / 8 + 64);
@@ -97,17 +97,16 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
         float diff = (float)log(1.0 - (double)s), same = logf(s), oml = same - diff;
         float mp = mn_priority(oml, omf, mlb, C, 1, im.cls[lo], im.clp + (size_t)lo * C, 1, im.cls[hi],
                                im.clp + (size_t)hi * C, nullptr);
-        MN_REC_LH(im, r) = make_int2(lo, hi);
+        const uint32_t g = mp >= 0.0f ? MN_G_EXACT : MN_G_NONE;
+        mn_store_rec(im, (int)r, make_uint4(mn_rec_pack_x(lo, MN_HS_NONE, g), (uint32_t)hi, mn_f2u(oml), mn_f2u(mp)));
         int hslot = mn_hash_insert(im, lo, hi, (int)r);
-        MN_REC_A(im, r) = make_uint4((uint32_t)lo, (uint32_t)hi, (uint32_t)hslot, mn_f2u(diff));
-        MN_REC_B(im, r) = make_float4(oml, same, mp >= 0.0f ? mp : -1.0f, mp);
+        MN_REC(im, r).x = mn_rec_pack_x(lo, mn_hs_of_slot(mn_hash_pos(im.hash_nbuckets, lo, hi), hslot), g);
         if (mp >= 0.0f) {
           uint32_t ord = (mn_tie_u(lo, hi) << 4) | (uint32_t)rank_of_k[k];
           key = ((uint64_t)(~mn_f2u(mp == 0.0f ? 0.0f : mp)) << MN_ORD_BITS) | ord;
         }
       } else {
-        MN_REC_A(im, r) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
-        MN_REC_B(im, r) = make_float4(0, 0, -1.0f, -1.0f);
+        mn_store_rec(im, (int)r, make_uint4(MN_REC_DEAD, 0u, 0u, mn_f2u(-1.0f)));
       }
       im.init_keys[r] = key;
     }
@@ -136,8 +135,8 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   }
   int status = im.ctl->status;
   if (getenv("EMUL_DEBUG")) {
-    for (size_t r = 0; r < E; r++) if (MN_REC_LH(im, r).x >= 0 && MN_REC_B(im, r).w >= 0.0f)
-      fprintf(stderr, "LEFTOVER rec %zu lo %d hi %d mp %.9g (bits %08x) root %d\n", r, MN_REC_LH(im, r).x, MN_REC_LH(im, r).y, MN_REC_B(im, r).w, mn_f2u(MN_REC_B(im, r).w), mn_root_of(MN_REC_B(im, r).w));
+    for (size_t r = 0; r < E; r++) if (mn_rec_key(im, (int)r).x >= 0 && mn_u2f(MN_REC(im, r).w) >= 0.0f)
+      fprintf(stderr, "LEFTOVER rec %zu lo %d hi %d mp %.9g (bits %08x) guard %u root %d\n", r, mn_rec_key(im, (int)r).x, mn_rec_key(im, (int)r).y, mn_u2f(MN_REC(im, r).w), MN_REC(im, r).w, mn_rec_guard(MN_REC(im, r).x), mn_root_of(mn_u2f(MN_REC(im, r).w)));
     fprintf(stderr, "status %d fail_line %d hash_ovf_n %d peak_entries %d peak_chunks %d (E %zu) tn_bump %d qc_bump %d pix_bump %d\n", im.ctl->status, im.ctl->fail_line, im.ctl->hash_ovf_n, im.ctl->peak_entries, im.ctl->peak_chunks, E, im.ctl->tn_bump, im.ctl->qc_bump, im.ctl->pix_bump);
     fprintf(stderr, "tree_entries %d static_cursor %d n_init %d nins %d nhot %d cold_empty %d\n", im.ctl->tree_entries, im.ctl->static_cursor, im.ctl->n_init, sm->nins, sm->nhot, sm->cold_empty);
   }
