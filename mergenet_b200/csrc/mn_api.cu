@@ -580,6 +580,8 @@ static int run_front(mn_plan* p, int b0, int B, const float* d_class, float* d_a
       size_t tb = p->cub_temp_bytes;
       MN_CUDA_OK(cub::DeviceRadixSort::SortKeys(p->d_cub_temp, tb, (const uint64_t*)p->d_keys_scratch,
                                                 p->h_imgs[b].init_keys, (int)p->E, 0, 32 + MN_ORD_BITS, s));
+      // (library kernels of one 60-bit sort: histogram + exclusive sum + 8 onesweep passes, profiles/r01_launches_*.csv)
+      p->timings.other_launches += 2 + (32 + MN_ORD_BITS + 7) / 8;
     }
   }
   if (record_events) MN_CUDA_OK(cudaEventRecord(p->ev[3], s));
@@ -624,6 +626,7 @@ static int run_back(mn_plan* p, int B, const float* d_class, const float* d_adj,
     for (int b = 0; b < B; b++) {
       size_t tb = p->cub_temp_bytes;
       MN_CUDA_OK(cub::DeviceScan::ExclusiveSum(p->d_cub_temp, tb, (const int*)p->h_imgs[b].cls, p->h_imgs[b].pix_pool, N, s));
+      p->timings.other_launches += 2;  // (scan init + scan)
     }
     MN_CUDA_OK(cudaMemsetAsync(d_object_class, 0xFF, (size_t)B * N * 4, s));
     mn_label_write_kernel<<<g, 256, 0, s>>>(p->d_imgs, B, N, d_mask, d_object_class, d_ninst);

@@ -108,3 +108,41 @@ def test_oracle_matches_reference_on_saturated_maps(oracle_mod):
             ref = oracle_mod.ref_run_segmentation(cp, sp, C, offs, *opts)
             ora = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)[:2]
         assert cases.same_result(oracle_mod, ref, ora), name
+
+
+def _quantized_case(h, w, seed, C=3, K=6):
+    """Block-quantized maps (levels 0.2 / 0.5 / 0.8 on 4x4 blocks): thousands of EXACTLY equal priorities whose pop
+    order decides which of several equally good merges happens first."""
+    from mergenet_b200 import synth
+    rng = np.random.default_rng(seed)
+    lv = np.array([0.2, 0.5, 0.8], np.float32)
+    up = lambda a: np.kron(a, np.ones((4, 4), np.float32))[:h, :w]  # noqa: E731
+    cp = np.stack([up(lv[rng.integers(0, 3, ((h + 3) // 4, (w + 3) // 4))]) for _ in range(C)])
+    sp = np.stack([up(lv[rng.integers(0, 3, ((h + 3) // 4, (w + 3) // 4))]) for _ in range(K)])
+    return synth.clip_probs(cp), synth.clip_probs(sp), C, synth.generate_offsets(40, K)
+
+
+def test_tie_dependent_inputs_known_limitation(oracle_mod):
+    """KNOWN LIMITATION, kept visible: among EQUAL priorities the reference pops in the order its libstdc++ binary
+    heap happens to hold them (PriorityCompare compares the priority only, segment.h:270-275; the push order comes
+    from unordered_map iteration, cc:650-652) -- a function of the whole push/pop history that no parallel
+    scheduler can replay.  Oracle and CUDA path use one fixed total order instead (mn_common.h: mn_tie).  On inputs
+    whose partition does not depend on the tie order (every fixture: soft maps, saturated oracle-mode maps,
+    constant maps) results are identical to the reference; on block-quantized maps they are not, and this test
+    records that instead of hiding it: the oracle is deterministic, produces a partition of comparable total
+    log-prob, and differs from the reference's."""
+    if not oracle_mod.have_reference():
+        pytest.skip("reference .so absent")
+    differ = 0
+    for h, w, seed in [(17, 23, 0), (24, 32, 1), (24, 32, 2)]:
+        cp, sp, C, offs = _quantized_case(h, w, seed)
+        ref = oracle_mod.ref_run_segmentation(cp, sp, C, offs, *cases.PLAIN_OPTS)
+        ora = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *cases.PLAIN_OPTS)[:2]
+        again = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *cases.PLAIN_OPTS)[:2]
+        assert cases.same_result(oracle_mod, ora, again)
+        lr = oracle_mod.total_logprob_from_scratch(ref[0], ref[1], cp, sp, offs, 1.0)
+        lo = oracle_mod.total_logprob_from_scratch(ora[0], ora[1], cp, sp, offs, 1.0)
+        assert abs(lr - lo) <= 0.05 * abs(lr), (lr, lo)  # two greedy runs of the same objective
+        differ += 0 if cases.same_result(oracle_mod, ref, ora) else 1
+    if differ == 0:
+        pytest.fail("tie-dependent inputs now equal the reference: update README / DESIGN (limitation lifted)")
