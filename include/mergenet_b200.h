@@ -172,6 +172,18 @@ int mn_resize_masks_nearest_device(const int* d_in, int batch, int height, int w
 int mn_resize_masks_nearest_host(const int* h_in, int batch, int height, int width, int* h_out,
                                  int out_height, int out_width);
 /*
+ * cv2.resize(maps, (out_width, out_height)) -- INTER_LINEAR, float32 -- for `planes` map planes
+ * (egs/cityscape/local/segment.py:116-123 resizes the class and offset maps to the segmentation size before the
+ * segmenter runs).  Planar layout [planes][H][W] -> [planes][out_height][out_width] (the reference moves the channel
+ * axis last for cv2 and back: the arithmetic per channel is the same).  Bit-identical to OpenCV 4.13's generic
+ * path, which images of 2 or >= 5 channels take (the class / offset maps have 9..81 / 10..16); OpenCV's 1-, 3- and
+ * 4-channel paths round differently and are not claimed.
+ */
+int mn_resize_maps_bilinear_device(const float* d_in, long long planes, int height, int width, float* d_out,
+                                   int out_height, int out_width, void* stream);
+int mn_resize_maps_bilinear_host(const float* h_in, long long planes, int height, int width, float* h_out,
+                                 int out_height, int out_width);
+/*
  * COCO run-length encoding of every instance of ONE int32 label mask [H][W] with labels 0..n_instances
  * (egs/cityscape/local/segment.py:165-186: for i in 1..n: maskUtils.encode(asfortranarray(mask == i))):
  * column-major runs (pycocotools rleEncode), written as the compressed ASCII `counts` string
@@ -183,7 +195,7 @@ int mn_resize_masks_nearest_host(const int* h_in, int batch, int height, int wid
 int mn_mask_to_coco_rle_host(const int* h_mask, int height, int width, int n_instances,
                              unsigned char* counts, long long counts_capacity, long long* offsets);
 
-/* device time (CUDA events, ms) of the last mn_resize_masks_nearest_host / mn_mask_to_coco_rle_host call */
+/* device time (CUDA events, ms) of the last mn_resize_masks_nearest_host / mn_resize_maps_bilinear_host / mn_mask_to_coco_rle_host call */
 float mn_post_last_ms(void);
 
 /* ---- test hooks (parity tests call these through the same library) --------------------------- */

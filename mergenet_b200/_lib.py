@@ -20,7 +20,7 @@ EXPORTS = ["c_run_segmentation", "mn_shutdown", "mn_last_error", "mn_status_stri
            "mn_workspace_bytes_per_image", "mn_plan_create", "mn_plan_destroy",
            "mn_segment_batch_device", "mn_segment_batch_host", "mn_modeb_segment_host", "mn_plan_image_stats",
            "mn_plan_timings", "mn_plan_image_logprob", "mn_debug_edge_dump", "mn_debug_libm", "mn_debug_edge_bench",
-           "mn_resize_masks_nearest_device", "mn_resize_masks_nearest_host", "mn_mask_to_coco_rle_host", "mn_post_last_ms"]
+           "mn_resize_masks_nearest_device", "mn_resize_masks_nearest_host", "mn_resize_maps_bilinear_device", "mn_resize_maps_bilinear_host", "mn_mask_to_coco_rle_host", "mn_post_last_ms"]
 
 
 class MergeNetError(RuntimeError):
@@ -135,6 +135,10 @@ def lib():
     L.mn_resize_masks_nearest_device.argtypes = [_V, ctypes.c_int, ctypes.c_int, ctypes.c_int, _V, ctypes.c_int, ctypes.c_int, _V]
     L.mn_resize_masks_nearest_host.restype = ctypes.c_int
     L.mn_resize_masks_nearest_host.argtypes = [_V, ctypes.c_int, ctypes.c_int, ctypes.c_int, _V, ctypes.c_int, ctypes.c_int]
+    L.mn_resize_maps_bilinear_device.restype = ctypes.c_int
+    L.mn_resize_maps_bilinear_device.argtypes = [_V, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, _V, ctypes.c_int, ctypes.c_int, _V]
+    L.mn_resize_maps_bilinear_host.restype = ctypes.c_int
+    L.mn_resize_maps_bilinear_host.argtypes = [_V, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, _V, ctypes.c_int, ctypes.c_int]
     L.mn_mask_to_coco_rle_host.restype = ctypes.c_int
     L.mn_mask_to_coco_rle_host.argtypes = [_V, ctypes.c_int, ctypes.c_int, ctypes.c_int, _V, ctypes.c_longlong, _V]
     L.mn_post_last_ms.restype = ctypes.c_float

@@ -156,43 +156,66 @@ __device__ __forceinline__ float mn_logprob_input(float v, int input) {
   if (input & (MN_INPUT_LOGITS | MN_INPUT_CLIP)) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
   return v;
 }
-// log(a) + log(b) = log(a * b): a thread multiplies its probabilities in float64 (each factor >= 2^-24 after the clip,
-// 2^-126 by the contract of unclipped inputs; 1.0 - (double)s is exact) and takes one log per MN_LP_FMAX factors, so
-// the pass is bound by its loads, not by the fp64 pipe.  The result equals the sum of the logs to float64 rounding.
-struct MnLogAcc {
-  double prod, sum; int n, fmax;
-  __device__ __forceinline__ void init(int fm) { prod = 1.0; sum = 0.0; n = 0; fmax = fm; }
-  __device__ __forceinline__ void mul(double f) {
-    if (n >= fmax) { sum += log(prod); prod = 1.0; n = 0; }
-    prod *= f; n++;
+// log(a) + log(b) = log(a * b): a thread keeps each of its three sums as a PRODUCT in float64, split into a mantissa in
+// [1, 2^k) and an integer exponent (a probability's own exponent field is peeled off with integer ops before the
+// multiply, so the product can neither underflow nor depend on how small the inputs are), and takes ONE log per sum at
+// the end: the pass is bound by its loads, not by the fp64 pipe.  Equals the sum of the logs to float64 rounding
+// (1.0 - (double)s is exact).  Values outside (0, 1) -- an unclipped caller -- take libm's log directly, with its
+// special values.
+struct MnProdAcc {
+  double m; int e; double slow;
+  __device__ __forceinline__ void init() { m = 1.0; e = 0; slow = 0.0; }
+  // f: a positive normal double; on: whether this sum takes the factor
+  __device__ __forceinline__ void mul(double f, bool on) {
+    const int hi = __double2hiint(f);
+    const double mant = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(f));
+    m = __dmul_rn(m, on ? mant : 1.0);
+    e += on ? (hi >> 20) - 1023 : 0;
   }
-  __device__ __forceinline__ double total() { return sum + log(prod); }
+  __device__ __forceinline__ void renorm() {  // (mantissa product back into [1, 2): call at least every ~900 factors)
+    const int hi = __double2hiint(m);
+    e += (hi >> 20) - 1023;
+    m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(m));
+  }
+  __device__ __forceinline__ double total() const { return log(m) + (double)e * 0x1.62e42fefa39efp-1 + slow; }
 };
 __global__ void __launch_bounds__(256) mn_partition_logprob_kernel(MnLogprobParams P) {
   __shared__ double red[3][8];
   const int N = P.N, W = P.W, H = P.H, K = P.K;
-  // factors one product may take before it could leave the double range: 2^-24 each when clipped (40 * 24 = 960 bits)
-  const int fmax = (P.input & (MN_INPUT_LOGITS | MN_INPUT_CLIP)) ? 40 : 8;
   for (int b = blockIdx.y; b < P.nimg; b += gridDim.y) {
     const int* mask = P.d_mask + (size_t)b * N;
     const int* ocls = P.d_object_class + (size_t)b * N;
     const float* cp = P.d_class + (size_t)b * P.C * N;
     const float* ap = P.d_adj + (size_t)b * K * N;
-    MnLogAcc ac, as, ad;
-    ac.init(fmax); as.init(fmax); ad.init(fmax);
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+    MnProdAcc ac, as, ad;
+    ac.init(); as.init(); ad.init();
+    int it = 0;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x, it++) {
       const int row = p / W, col = p - row * W;
       const int lab = mask[p];
       int cls = lab > 0 ? ocls[lab - 1] : 0;
       cls = cls < 0 ? 0 : (cls >= P.C ? P.C - 1 : cls);  // (only a failed image can hold anything else)
-      ac.mul((double)mn_logprob_input(cp[(size_t)cls * N + p], P.input));
+      {
+        const float v = mn_logprob_input(cp[(size_t)cls * N + p], P.input);
+        const uint32_t vb = __float_as_uint(v);
+        if (vb - 0x00800000u < 0x7f000000u) ac.mul(mn_f32bits_to_f64(vb), true);  // positive normal float
+        else ac.slow += log((double)v);
+      }
 #pragma unroll 5
       for (int k = 0; k < K; k++) {
         const int r2 = row + P.off_r[k], c2 = col + P.off_c[k];
         if (r2 < 0 || r2 >= H || c2 < 0 || c2 >= W) continue;
-        const double s = (double)mn_logprob_input(ap[(size_t)k * N + p], P.input);
-        if (mask[r2 * W + c2] == lab) as.mul(s); else ad.mul(1.0 - s);
+        const float sv = mn_logprob_input(ap[(size_t)k * N + p], P.input);
+        const bool same = mask[r2 * W + c2] == lab;
+        const uint32_t sb = __float_as_uint(sv);
+        if (sb - 0x00800000u < 0x3f000000u) {  // a positive normal float below 1: s and 1 - s are normal doubles
+          const double sd = mn_f32bits_to_f64(sb);
+          const double f = same ? sd : __dadd_rn(1.0, -sd);
+          as.mul(f, same); ad.mul(f, !same);
+        } else if (same) as.slow += log((double)sv);
+        else ad.slow += log(1.0 - (double)sv);
       }
+      if ((it & 31) == 31) { ac.renorm(); as.renorm(); ad.renorm(); }  // (<= 32 * 17 factors below 2 in between)
     }
     double tc = ac.total(), ts = as.total(), td = ad.total();
     for (int o = 16; o > 0; o >>= 1) {
@@ -336,7 +359,7 @@ static int choose_edge_tile(int C, int K, int* smem_bytes) {
   size_t budget = (size_t)(226 * 1024) / MN_EDGE_CTAS_PER_SM - 4096;
   int tp = (int)(budget / per_px);
   tp = std::min(tp, MN_EDGE_THREADS / 2);
-  tp = tp / 4 * 4;
+  tp = tp >= 32 ? tp / 32 * 32 : tp / 4 * 4;  // (multiples of 32 pixels: the 2-D tensor-map boxes land 128-byte aligned)
   if (tp >= 128) tp = tp / 128 * 128;
   if (tp < 4) tp = 4;
   *smem_bytes = (int)(128 + per_px * tp + 16 * sizeof(MnLogfTab) + 128 * sizeof(MnLog1mTab) + 64);
@@ -500,6 +523,31 @@ extern "C" int mn_plan_create(mn_plan** out, int max_batch, int H, int W, int C,
   return MN_STATUS_OK;
 }
 
+// 2-D tensor map over a [planes][N] fp32 array, box = `box_rows` planes x `tp` pixels (dense rows in shared memory);
+// the encoder comes from the driver at run time (cudaGetDriverEntryPoint: the library does not link libcuda)
+typedef CUresult (*mn_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static mn_encode_tiled_fn mn_tensor_map_encoder() {
+  static mn_encode_tiled_fn fn = []() -> mn_encode_tiled_fn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return (mn_encode_tiled_fn)f;
+  }();
+  return fn;
+}
+static bool make_plane_map(CUtensorMap* m, const float* base, size_t planes, size_t n, int box_rows, int tp) {
+  mn_encode_tiled_fn enc = mn_tensor_map_encoder();
+  if (!enc || box_rows > 256 || tp > 256 || planes >= (1ull << 32)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)planes};
+  const cuuint64_t strides[1] = {(cuuint64_t)n * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)tp, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // the edge pass for images [0, B): the warp-pipeline kernel when it applies, else the tile kernel
 static int launch_edge(mn_plan* p, int b0, int B, const float* d_class, float* d_adj, int clip, float sdb, cudaStream_t s) {
   const int N = p->N, C = p->C, K = p->K;
@@ -513,6 +561,13 @@ static int launch_edge(mn_plan* p, int b0, int B, const float* d_class, float* d
   P.clip = ((clip & MN_INPUT_CLIP) || P.logits) ? 1 : 0;  // (sigmoid saturates to 0 / 1 in fp32: logits are always clipped)
   P.sdb = sdb;
   P.only_if = nullptr;
+  P.use_tmap = 0;
+  CUtensorMap tmc, tma;
+  memset(&tmc, 0, sizeof(tmc)); memset(&tma, 0, sizeof(tma));
+  const bool no_tmap = getenv("MN_EDGE_NO_TMAP") != nullptr;  // (A/B hook: the 1-D bulk-copy producer)
+  if (P.use_tma && !no_tmap && p->edge_tp % 32 == 0 && make_plane_map(&tmc, d_class, (size_t)B * C, N, C, p->edge_tp) &&
+      make_plane_map(&tma, d_adj, (size_t)B * K, N, K, p->edge_tp))
+    P.use_tmap = 1;
   const bool warp_pipeline = p->edge2_ncons > 0 && P.use_tma && sdb == 0.0f;
   // the drop-in symbol takes whatever floats the caller hands in (the reference computes libm's special values
   // for them): check the domain of the fast kernel's log recipes and let the general kernel redo the batch if needed
@@ -544,12 +599,12 @@ static int launch_edge(mn_plan* p, int b0, int B, const float* d_class, float* d
       Q.only_if = p->d_domain_flag;
       const long long qt = (long long)B * Q.tiles_per_image;
       int qgrid = (int)std::min<long long>(qt, (long long)p->num_sms * MN_EDGE_CTAS_PER_SM);
-      mn_edge_pass_kernel<<<qgrid, MN_EDGE_THREADS, p->edge_smem, s>>>(Q);
+      mn_edge_pass_kernel<<<qgrid, MN_EDGE_THREADS, p->edge_smem, s>>>(Q, tmc, tma);
       p->timings.edge_launches++;
     }
   } else {
     int grid = (int)std::min<long long>(tiles, (long long)p->num_sms * MN_EDGE_CTAS_PER_SM);
-    mn_edge_pass_kernel<<<grid, MN_EDGE_THREADS, p->edge_smem, s>>>(P);
+    mn_edge_pass_kernel<<<grid, MN_EDGE_THREADS, p->edge_smem, s>>>(P, tmc, tma);
   }
   p->timings.edge_launches++;
   return MN_STATUS_OK;
@@ -895,6 +950,35 @@ extern "C" int mn_resize_masks_nearest_host(const int* h_in, int B, int H, int W
   cudaError_t e = cudaMemcpyAsync(di, h_in, nin, cudaMemcpyHostToDevice, st);
   cudaEventRecord(ps.e0, st);
   if (e == cudaSuccess) e = mn_resize_nearest_launch(di, B, H, W, dout, OH, OW, st);
+  cudaEventRecord(ps.e1, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, dout, nout, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) cudaEventElapsedTime(&g_post_ms, ps.e0, ps.e1);
+  if (e != cudaSuccess) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  return MN_STATUS_OK;
+}
+
+extern "C" int mn_resize_maps_bilinear_device(const float* d_in, long long planes, int H, int W, float* d_out, int OH, int OW, void* stream) {
+  g_last_error = MN_STATUS_OK;
+  if (!d_in || !d_out || planes <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0) { g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  MN_CUDA_OK(mn_resize_bilinear_launch(d_in, planes, H, W, d_out, OH, OW, (cudaStream_t)stream));
+  return MN_STATUS_OK;
+}
+extern "C" int mn_resize_maps_bilinear_host(const float* h_in, long long planes, int H, int W, float* h_out, int OH, int OW) {
+  g_last_error = MN_STATUS_OK;
+  if (!h_in || !h_out || planes <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0) { g_last_error = MN_STATUS_BAD_ARG; return MN_STATUS_BAD_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  const size_t nin = (size_t)planes * H * W * 4, nout = (size_t)planes * OH * OW * 4;
+  PostScratch& ps = g_post;
+  if (!ps.ensure(nin, nout, 0)) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }
+  float* di = (float*)ps.buf[0]; float* dout = (float*)ps.buf[1];
+  cudaStream_t st = ps.stream;
+  cudaError_t e = cudaMemcpyAsync(di, h_in, nin, cudaMemcpyHostToDevice, st);
+  cudaEventRecord(ps.e0, st);
+  if (e == cudaSuccess) e = mn_resize_bilinear_launch(di, planes, H, W, dout, OH, OW, st);
   cudaEventRecord(ps.e1, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, dout, nout, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);

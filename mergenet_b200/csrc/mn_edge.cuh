@@ -18,6 +18,7 @@
 //   the (lo,hi)->record hash insert, the per-pixel live-record bit masks, and the 64-bit sort key
 //   of the initial queue entry (sentinel when mp < 0 or the slot does not exist, cc:225-227).
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only: the encoder is fetched from the driver at run time, no -lcuda)
 #include <cuda_runtime.h>
 
 #include "mn_common.h"
@@ -56,6 +57,15 @@ __device__ __forceinline__ void mn_tma_load_1d(void* smem_dst, const void* gsrc,
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
           mn_smem_u32(smem_dst)),
       "l"(gsrc), "r"(bytes), "r"(mn_smem_u32(bar))
+      : "memory");
+}
+// 2-D tiled TMA load: one box (inner extent x rows) of a [rows][inner] tensor described by a tensor map; rows and
+// columns beyond the tensor arrive as zeros and still count towards the barrier's transaction bytes
+__device__ __forceinline__ void mn_tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c_inner, int c_row, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          mn_smem_u32(smem_dst)),
+      "l"(tmap), "r"(c_inner), "r"(c_row), "r"(mn_smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void mn_tma_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
@@ -198,6 +208,8 @@ struct MnEdgeParams {
   int TP;                   // pixels per tile (multiple of 4)
   int tiles_per_image;
   int use_tma;              // N % 4 == 0 and 16-byte aligned bases
+  int use_tmap;             // tile kernel: the input planes of a tile arrive as TWO 2-D tensor-map boxes (class planes x
+                            // pixels, offset planes x pixels) instead of C + K 1-D bulk copies (needs use_tma, TP % 32 == 0)
   int clip;                 // apply the wrapper's clip to [2^-23, 1-2^-23] (c_segment.pyx:53-55)
   int logits;               // inputs are the network's logits: sigmoid first (inference_utils.py:43-44,95-96), then clip
   float sdb;
@@ -233,7 +245,8 @@ __global__ void __launch_bounds__(256) mn_domain_check_kernel(const float* a, si
 // at a barrier or on its TMA loads the other computes
 #define MN_EDGE_THREADS 512
 #define MN_EDGE_CTAS_PER_SM 2
-__global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_pass_kernel(MnEdgeParams P) {
+__global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_pass_kernel(MnEdgeParams P, const __grid_constant__ CUtensorMap tm_class,
+                                                                                            const __grid_constant__ CUtensorMap tm_adj) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (P.only_if && *P.only_if == 0) return;
   const int C = P.C, K = P.K, TP = P.TP, NPL = C + K;
@@ -267,6 +280,12 @@ __global__ void __launch_bounds__(MN_EDGE_THREADS, MN_EDGE_CTAS_PER_SM) mn_edge_
     float* dst = stage ? in1 : in0;
     const float* cbase = P.class_pred + ((size_t)b * C) * P.N + start;
     const float* abase = P.adj_pred + ((size_t)b * K) * P.N + start;
+    if (P.use_tmap) {  // two boxes: [C planes][TP pixels] and [K planes][TP pixels] (the tail of a last tile: zeros)
+      mn_mbar_expect_tx(&bars[stage], (uint32_t)(NPL * TP * 4));
+      mn_tma_load_2d(dst, &tm_class, start, b * C, &bars[stage]);
+      mn_tma_load_2d(dst + (size_t)C * TP, &tm_adj, start, b * K, &bars[stage]);
+      return;
+    }
     mn_mbar_expect_tx(&bars[stage], (uint32_t)(NPL * tl * 4));
     for (int pl = 0; pl < C; pl++)
       mn_tma_load_1d(dst + (size_t)pl * TP, cbase + (size_t)pl * P.N, tl * 4, &bars[stage]);

@@ -1,4 +1,6 @@
 // mn_post.cuh -- the step after the merge path, on the device:
+//   * bilinear resize of the class / sameness maps to the segmentation size
+//     (egs/cityscape/local/segment.py:116-123: cv2.resize(maps, seg_size), INTER_LINEAR);
 //   * nearest-neighbour resize of the instance masks back to the image size
 //     (egs/cityscape/local/segment.py:147-149: cv2.resize(mask, (w, h), interpolation=cv2.INTER_NEAREST));
 //   * COCO run-length encoding of every instance of a label mask
@@ -41,6 +43,52 @@ static cudaError_t mn_resize_nearest_launch(const int* d_in, int B, int H, int W
     if (OH > 65535) return cudaErrorInvalidValue;
     dim3 g((unsigned)((OW + 255) / 256 < 64 ? (OW + 255) / 256 : 64), (unsigned)OH, (unsigned)nb);
     mn_resize_nearest_kernel<<<g, 256, 0, s>>>(d_in + (size_t)b0 * H * W, d_out + (size_t)b0 * OH * OW, H, W, OH, OW, ifx, ify);
+  }
+  return cudaGetLastError();
+}
+
+// ---- bilinear resize of the probability maps ---------------------------------------------------------
+// cv2.resize(maps, (out_w, out_h)) with the default INTER_LINEAR on float32 maps of 2 or >= 5 channels
+// (egs/cityscape/local/segment.py:116-123 resizes the C- and K-channel maps to the segmentation size), restated from
+// OpenCV's resize.cpp: per destination column  fx = (float)((dx + 0.5) * (src_w / (double)dst_w) - 0.5), sx = floor(fx),
+// fx -= sx (float), and (fx, sx) = (0, 0) left of the image, (0, src_w - 1) at or beyond its last column; per
+// destination row the same WITHOUT that clamp of the weight -- the two source rows are clipped to the image instead;
+// value = (S[sy0][sx] * (1 - fx) + S[sy0][sx + 1] * fx) * (1 - fy) + (S[sy1][sx] * (1 - fx) + S[sy1][sx + 1] * fx) * fy,
+// every product and sum rounded to float on its own (no FMA: the generic many-channel path of the OpenCV in this image
+// evaluates it that way; its 1-, 3- and 4-channel paths round differently and are not claimed).  Bit-identical to cv2
+// 4.13 on the test matrix (tests/test_post.py).  Planar layout: d_in [planes][H][W] -> d_out [planes][OH][OW].
+__global__ void __launch_bounds__(256) mn_resize_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
+                                                                 int OH, int OW, double scale_x, double scale_y) {
+  const int y = blockIdx.y;
+  const size_t pl = blockIdx.z;
+  float fy = (float)(((double)y + 0.5) * scale_y - 0.5);
+  const int sy = (int)floorf(fy);
+  fy = __fsub_rn(fy, (float)sy);
+  const int y0 = min(max(sy, 0), H - 1), y1 = min(max(sy + 1, 0), H - 1);
+  const float b0 = __fsub_rn(1.0f, fy), b1 = fy;
+  const float* r0 = in + (pl * H + y0) * W;
+  const float* r1 = in + (pl * H + y1) * W;
+  float* orow = out + (pl * OH + y) * OW;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < OW; x += gridDim.x * blockDim.x) {
+    float fx = (float)(((double)x + 0.5) * scale_x - 0.5);
+    int sx = (int)floorf(fx);
+    fx = __fsub_rn(fx, (float)sx);
+    if (sx < 0) { fx = 0.0f; sx = 0; }
+    if (sx >= W - 1) { fx = 0.0f; sx = W - 1; }
+    const int x1 = min(sx + 1, W - 1);
+    const float a0 = __fsub_rn(1.0f, fx), a1 = fx;
+    const float h0 = __fadd_rn(__fmul_rn(r0[sx], a0), __fmul_rn(r0[x1], a1));
+    const float h1 = __fadd_rn(__fmul_rn(r1[sx], a0), __fmul_rn(r1[x1], a1));
+    orow[x] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+  }
+}
+static cudaError_t mn_resize_bilinear_launch(const float* d_in, long long planes, int H, int W, float* d_out, int OH, int OW, cudaStream_t s) {
+  if (OH > 65535) return cudaErrorInvalidValue;
+  const double sx = (double)W / (double)OW, sy = (double)H / (double)OH;
+  for (long long p0 = 0; p0 < planes; p0 += 65535) {
+    const int np = (int)(planes - p0 < 65535 ? planes - p0 : 65535);
+    dim3 g((unsigned)((OW + 255) / 256 < 64 ? (OW + 255) / 256 : 64), (unsigned)OH, (unsigned)np);
+    mn_resize_bilinear_kernel<<<g, 256, 0, s>>>(d_in + (size_t)p0 * H * W, d_out + (size_t)p0 * OH * OW, H, W, OH, OW, sx, sy);
   }
   return cudaGetLastError();
 }

@@ -2,6 +2,7 @@
 their COCO run-length encoding -- what `egs/cityscape/local/segment.py:147-149,165-186` and
 `egs/coco/local/segment.py:190-204` do with cv2 and pycocotools on the host.
 
+    resize_maps_bilinear(maps, out_h, out_w)           cv2.resize(maps, (out_w, out_h)) of the class / offset maps
     resize_masks_nearest(masks, out_h, out_w)          cv2.resize(mask, (out_w, out_h), INTER_NEAREST)
     coco_rle_counts(mask, n_instances)                 [maskUtils.encode(asfortranarray(mask == i))["counts"]]
     convert_to_coco_result(mask, object_class, image_id, catIds)   the reference function, same dicts
@@ -34,6 +35,22 @@ def resize_masks_nearest(masks, out_h, out_w):
     _check(_lib.lib().mn_resize_masks_nearest_host(m.ctypes.data, B, H, W, out.ctypes.data, int(out_h), int(out_w)),
            "mn_resize_masks_nearest_host")
     return out[0] if single else out
+
+
+def resize_maps_bilinear(maps, out_h, out_w):
+    """maps: float32 [C, H, W] (or [B, C, H, W]) on the host.  Returns cv2.resize(channel-last maps, (out_w, out_h))
+    moved back to channel-first, i.e. what egs/cityscape/local/segment.py:116-123 feeds the segmenter (bit-identical
+    to OpenCV 4.13's generic float path, which maps of 2 or >= 5 channels take)."""
+    m = np.ascontiguousarray(maps, dtype=np.float32)
+    if m.ndim not in (3, 4):
+        raise ValueError("maps must be [C, H, W] or [B, C, H, W]")
+    _lib.require_device()
+    H, W = m.shape[-2:]
+    planes = int(np.prod(m.shape[:-2]))
+    out = np.empty(m.shape[:-2] + (int(out_h), int(out_w)), np.float32)
+    _check(_lib.lib().mn_resize_maps_bilinear_host(m.ctypes.data, planes, H, W, out.ctypes.data, int(out_h), int(out_w)),
+           "mn_resize_maps_bilinear_host")
+    return out
 
 
 def coco_rle_counts(mask, n_instances):

@@ -304,6 +304,38 @@ def total_logprob_from_scratch(mask, object_class, class_pred, adj_pred, offset_
 
 
 # ---- the step after the path: checkers for mergenet_b200/csrc/mn_post.cuh ------------
+def oracle_resize_bilinear(maps, out_h, out_w):
+    """cv2.resize(maps, (out_w, out_h)) (INTER_LINEAR, float32, generic many-channel path) restated in numpy for
+    planar maps [..., H, W]: OpenCV resize.cpp computes per destination index f = (float)((d + 0.5) * scale - 0.5),
+    s = floor(f), f -= s in float; columns clamp (f, s) to (0, 0) / (0, W - 1) outside the image, rows keep the
+    weight and clip the two source rows; horizontal then vertical pass, every product and sum rounded to float."""
+    import math
+    m = np.ascontiguousarray(maps, dtype=np.float32)
+    H, W = m.shape[-2:]
+
+    def coef(n_src, n_dst, clamp):
+        scale = n_src / n_dst
+        i0 = np.zeros(n_dst, np.int64); i1 = np.zeros(n_dst, np.int64); w1 = np.zeros(n_dst, np.float32)
+        for d in range(n_dst):
+            f = np.float32((d + 0.5) * scale - 0.5)
+            s = math.floor(f)
+            f = np.float32(f - np.float32(s))
+            if clamp:
+                if s < 0:
+                    f = np.float32(0); s = 0
+                if s >= n_src - 1:
+                    f = np.float32(0); s = n_src - 1
+            i0[d] = min(max(s, 0), n_src - 1); i1[d] = min(max(s + 1, 0), n_src - 1); w1[d] = f
+        return i0, i1, w1
+
+    y0, y1, yb = coef(H, int(out_h), False)
+    x0, x1, xa = coef(W, int(out_w), True)
+    one = np.float32(1)
+    rows = m[..., :, x0] * (one - xa) + m[..., :, x1] * xa
+    out = rows[..., y0, :] * (one - yb)[:, None] + rows[..., y1, :] * yb[:, None]
+    return out.astype(np.float32)
+
+
 def oracle_resize_nearest(mask, out_h, out_w):
     """cv2.resize(mask, (out_w, out_h), interpolation=cv2.INTER_NEAREST), restated (resizeNN)."""
     L = oracle_lib()

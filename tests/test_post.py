@@ -91,3 +91,40 @@ def test_gpu_post_pass_on_a_segmentation_full_size_round_trip(oracle_mod, lib_mo
     strings = [r["segmentation"]["counts"] for r in res]
     assert np.array_equal(oracle_mod.oracle_coco_rle_decode(strings, 1024, 2048), big)
     assert [r["category_id"] for r in res] == [100 + c for c in ocls[:n]]
+
+
+BILINEAR_SIZES = [(33, 47, 100, 64), (31, 47, 93, 47), (64, 64, 17, 23), (5, 7, 50, 70), (50, 70, 5, 7), (1, 9, 4, 30),
+                  (9, 1, 30, 4), (40, 80, 80, 160)]
+
+
+def test_oracle_resize_bilinear_equals_cv2(oracle_mod):
+    """egs/cityscape/local/segment.py:116-123: the restatement against this image's cv2 itself, BIT FOR BIT, for the
+    channel counts the class / offset maps have (OpenCV's generic float path: 2 or >= 5 channels; its 1-, 3- and
+    4-channel paths round differently and are not claimed).  Tolerance: none (float bits equal)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for cn in (2, 5, 9, 10, 16, 81):
+        for (h, w, oh, ow) in BILINEAR_SIZES:
+            src = rng.random((cn, h, w)).astype(np.float32)
+            want = np.moveaxis(cv2.resize(np.moveaxis(src, 0, -1), (ow, oh)).reshape(oh, ow, cn), -1, 0)
+            got = oracle_mod.oracle_resize_bilinear(src, oh, ow)
+            assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(want).view(np.uint32)), (cn, h, w, oh, ow)
+
+
+@pytest.mark.gpu
+def test_gpu_resize_bilinear_equals_oracle_and_cv2(oracle_mod, lib_mod):
+    from mergenet_b200 import post
+    rng = np.random.default_rng(2)
+    for cn, (h, w, oh, ow) in [(9, s) for s in BILINEAR_SIZES] + [(10, (128, 256, 256, 512)), (81, (40, 40, 64, 64)),
+                                                                    (16, (64, 64, 40, 40))]:
+        src = rng.random((cn, h, w)).astype(np.float32)
+        got = post.resize_maps_bilinear(src, oh, ow)
+        assert np.array_equal(got.view(np.uint32), oracle_mod.oracle_resize_bilinear(src, oh, ow).view(np.uint32)), (cn, h, w, oh, ow)
+    try:
+        import cv2
+    except ImportError:
+        return
+    src = rng.random((10, 512, 1024)).astype(np.float32)  # the Cityscapes recipe: maps at half size -> 1024 x 2048
+    want = np.moveaxis(cv2.resize(np.moveaxis(src, 0, -1), (2048, 1024)), -1, 0)
+    got = post.resize_maps_bilinear(src, 1024, 2048)
+    assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(want).view(np.uint32))
