@@ -148,38 +148,35 @@ __global__ void mn_label_write_kernel(const MnImage* imgs, int nimg, int N, int*
 struct MnLogprobParams {
   const float* d_class; const float* d_adj; const int* d_mask; const int* d_object_class;
   double* partial;  // [nimg][gridDim.x][3]
-  int nimg, H, W, C, K, N, input;  // input: MN_INPUT_* flags of the run (the values the edge pass saw)
-  int off_r[MN_MAX_K], off_c[MN_MAX_K];
+  int nimg, H, W, C, K, N;
+  int maxr, maxc;   // largest |row offset| / |column offset|: pixels farther than that from every border take no bounds test
+  int off_r[MN_MAX_K], off_c[MN_MAX_K], delta[MN_MAX_K];
 };
-__device__ __forceinline__ float mn_logprob_input(float v, int input) {
-  if (input & MN_INPUT_LOGITS) v = mn_sigmoid_f32(v);
-  if (input & (MN_INPUT_LOGITS | MN_INPUT_CLIP)) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
+// MODE: the MN_INPUT_* transform the run applied while reading the maps (0: values as given)
+template <int MODE>
+__device__ __forceinline__ float mn_logprob_input(float v) {
+  if (MODE & MN_INPUT_LOGITS) v = mn_sigmoid_f32(v);
+  if (MODE & (MN_INPUT_LOGITS | MN_INPUT_CLIP)) v = fminf(fmaxf(v, 1.1920929e-07f), 0.99999988f);
   return v;
 }
-// log(a) + log(b) = log(a * b): a thread keeps each of its three sums as a PRODUCT in float64, split into a mantissa in
-// [1, 2^k) and an integer exponent (a probability's own exponent field is peeled off with integer ops before the
-// multiply, so the product can neither underflow nor depend on how small the inputs are), and takes ONE log per sum at
-// the end: the pass is bound by its loads, not by the fp64 pipe.  Equals the sum of the logs to float64 rounding
-// (1.0 - (double)s is exact).  Values outside (0, 1) -- an unclipped caller -- take libm's log directly, with its
-// special values.
+// log(a) + log(b) = log(a * b): a thread keeps its sums as PRODUCTS in float64 -- mantissa in the double, the exponent
+// peeled off into an integer every few pixels (a factor is >= 2^-24, so 34 of them cannot leave the double range) --
+// and takes one log per sum at the end: the pass is bound by its loads and instruction issue, not by the fp64 pipe.
+// Equals the sum of the logs to float64 rounding (the widening of s and 1.0 - (double)s are exact).  Factors outside
+// [2^-24, 1) -- an unclipped caller -- take libm's log directly, with its special values.
 struct MnProdAcc {
-  double m; int e; double slow;
-  __device__ __forceinline__ void init() { m = 1.0; e = 0; slow = 0.0; }
-  // f: a positive normal double; on: whether this sum takes the factor
-  __device__ __forceinline__ void mul(double f, bool on) {
-    const int hi = __double2hiint(f);
-    const double mant = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(f));
-    m = __dmul_rn(m, on ? mant : 1.0);
-    e += on ? (hi >> 20) - 1023 : 0;
-  }
-  __device__ __forceinline__ void renorm() {  // (mantissa product back into [1, 2): call at least every ~900 factors)
+  double m; int e;
+  __device__ __forceinline__ void init() { m = 1.0; e = 0; }
+  __device__ __forceinline__ void renorm() {  // mantissa back into [1, 2)
     const int hi = __double2hiint(m);
     e += (hi >> 20) - 1023;
     m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(m));
   }
-  __device__ __forceinline__ double total() const { return log(m) + (double)e * 0x1.62e42fefa39efp-1 + slow; }
+  __device__ __forceinline__ double total() const { return log(m) + (double)e * 0x1.62e42fefa39efp-1; }
 };
-__global__ void __launch_bounds__(256) mn_partition_logprob_kernel(MnLogprobParams P) {
+#define MN_LP_FAST(bits) ((bits) - 0x33800000u < 0x3f800000u - 0x33800000u)  // a float in [2^-24, 1)
+template <int MODE>
+__global__ void __launch_bounds__(256, 3) mn_partition_logprob_kernel(MnLogprobParams P) {
   __shared__ double red[3][8];
   const int N = P.N, W = P.W, H = P.H, K = P.K;
   for (int b = blockIdx.y; b < P.nimg; b += gridDim.y) {
@@ -187,37 +184,70 @@ __global__ void __launch_bounds__(256) mn_partition_logprob_kernel(MnLogprobPara
     const int* ocls = P.d_object_class + (size_t)b * N;
     const float* cp = P.d_class + (size_t)b * P.C * N;
     const float* ap = P.d_adj + (size_t)b * K * N;
-    MnProdAcc ac, as, ad;
-    ac.init(); as.init(); ad.init();
+    MnProdAcc ac, aall, asame;  // class factors; every pair's factor (s inside an instance, 1 - s across); the inside ones
+    ac.init(); aall.init(); asame.init();
+    double slow_c = 0.0, slow_s = 0.0, slow_d = 0.0;  // logs taken one by one (out-of-domain factors)
     int it = 0;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x, it++) {
       const int row = p / W, col = p - row * W;
       const int lab = mask[p];
       int cls = lab > 0 ? ocls[lab - 1] : 0;
       cls = cls < 0 ? 0 : (cls >= P.C ? P.C - 1 : cls);  // (only a failed image can hold anything else)
+      const float cv = mn_logprob_input<MODE>(cp[(size_t)cls * N + p]);
+      float sv[MN_MAX_K]; int lq[MN_MAX_K];
+      const bool interior = row >= P.maxr && row < H - P.maxr && col >= P.maxc && col < W - P.maxc;
+      uint32_t ok = 0;  // bit k: the pair (p, k) exists
+      if (interior) {   // every load of the pixel issued before the first use
+#pragma unroll
+        for (int k = 0; k < MN_MAX_K; k++)
+          if (k < K) { sv[k] = ap[(size_t)k * N + p]; lq[k] = mask[p + P.delta[k]]; }
+        ok = (1u << K) - 1u;
+      } else {
+#pragma unroll
+        for (int k = 0; k < MN_MAX_K; k++) {
+          if (k < K) {
+            const int r2 = row + P.off_r[k], c2 = col + P.off_c[k];
+            const bool in = r2 >= 0 && r2 < H && c2 >= 0 && c2 < W;
+            sv[k] = in ? ap[(size_t)k * N + p] : 0.5f;
+            lq[k] = in ? mask[r2 * W + c2] : -1;
+            ok |= in ? (1u << k) : 0u;
+          }
+        }
+      }
       {
-        const float v = mn_logprob_input(cp[(size_t)cls * N + p], P.input);
-        const uint32_t vb = __float_as_uint(v);
-        if (vb - 0x00800000u < 0x7f000000u) ac.mul(mn_f32bits_to_f64(vb), true);  // positive normal float
-        else ac.slow += log((double)v);
+        const uint32_t vb = __float_as_uint(cv);
+        if (vb - 0x00800000u < 0x7f000000u) ac.m = __dmul_rn(ac.m, mn_f32bits_to_f64(vb));  // positive normal float
+        else slow_c += log((double)cv);
       }
-#pragma unroll 5
-      for (int k = 0; k < K; k++) {
-        const int r2 = row + P.off_r[k], c2 = col + P.off_c[k];
-        if (r2 < 0 || r2 >= H || c2 < 0 || c2 >= W) continue;
-        const float sv = mn_logprob_input(ap[(size_t)k * N + p], P.input);
-        const bool same = mask[r2 * W + c2] == lab;
-        const uint32_t sb = __float_as_uint(sv);
-        if (sb - 0x00800000u < 0x3f000000u) {  // a positive normal float below 1: s and 1 - s are normal doubles
-          const double sd = mn_f32bits_to_f64(sb);
-          const double f = same ? sd : __dadd_rn(1.0, -sd);
-          as.mul(f, same); ad.mul(f, !same);
-        } else if (same) as.slow += log((double)sv);
-        else ad.slow += log(1.0 - (double)sv);
+      bool fast = true;
+#pragma unroll
+      for (int k = 0; k < MN_MAX_K; k++)
+        if (k < K) { sv[k] = mn_logprob_input<MODE>(sv[k]); fast = fast && MN_LP_FAST(__float_as_uint(sv[k])); }
+      if (fast) {
+#pragma unroll
+        for (int k = 0; k < MN_MAX_K; k++) {
+          if (k < K) {
+            const bool on = (ok >> k) & 1u, same = lq[k] == lab;
+            const double sd = mn_f32bits_to_f64(__float_as_uint(sv[k]));
+            const double f = on ? (same ? sd : __dadd_rn(1.0, -sd)) : 1.0;
+            aall.m = __dmul_rn(aall.m, f);
+            asame.m = __dmul_rn(asame.m, same ? f : 1.0);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < MN_MAX_K; k++) {  // (static indices: sv / lq stay in registers)
+          if (k < K && ((ok >> k) & 1u)) {
+            const bool same = lq[k] == lab;
+            const double l = log(same ? (double)sv[k] : 1.0 - (double)sv[k]);
+            slow_s += same ? l : 0.0; slow_d += same ? 0.0 : l;
+          }
+        }
       }
-      if ((it & 31) == 31) { ac.renorm(); as.renorm(); ad.renorm(); }  // (<= 32 * 17 factors below 2 in between)
+      if (it & 1) { aall.renorm(); asame.renorm(); }  // (at most 2 * 16 factors >= 2^-24 since the last one)
+      if ((it & 7) == 7) ac.renorm();                 // (8 class factors >= 2^-126)
     }
-    double tc = ac.total(), ts = as.total(), td = ad.total();
+    double tc = ac.total() + slow_c, ts = asame.total() + slow_s, td = (aall.total() - asame.total()) + slow_d;
     for (int o = 16; o > 0; o >>= 1) {
       tc += __shfl_xor_sync(0xffffffffu, tc, o); ts += __shfl_xor_sync(0xffffffffu, ts, o); td += __shfl_xor_sync(0xffffffffu, td, o);
     }
@@ -692,11 +722,17 @@ static int run_back(mn_plan* p, int B, const float* d_class, const float* d_adj,
   {
     MnLogprobParams L;
     L.d_class = d_class; L.d_adj = d_adj; L.d_mask = d_mask; L.d_object_class = d_object_class; L.partial = p->d_logprob_partial;
-    L.nimg = B; L.H = p->H; L.W = p->W; L.C = p->C; L.K = p->K; L.N = N; L.input = clip & (MN_INPUT_CLIP | MN_INPUT_LOGITS);
-    for (int k = 0; k < p->K; k++) { L.off_r[k] = p->offsets[2 * k]; L.off_c[k] = p->offsets[2 * k + 1]; }
+    L.nimg = B; L.H = p->H; L.W = p->W; L.C = p->C; L.K = p->K; L.N = N; L.maxr = 0; L.maxc = 0;
+    for (int k = 0; k < p->K; k++) {
+      L.off_r[k] = p->offsets[2 * k]; L.off_c[k] = p->offsets[2 * k + 1]; L.delta[k] = L.off_r[k] * p->W + L.off_c[k];
+      L.maxr = std::max(L.maxr, std::abs(L.off_r[k])); L.maxc = std::max(L.maxc, std::abs(L.off_c[k]));
+    }
     const int gx = std::max(1, std::min(MN_LOGPROB_BLOCKS, (N + 1023) / 1024));
     dim3 g((unsigned)gx, (unsigned)std::min(B, 65535));
-    mn_partition_logprob_kernel<<<g, 256, 0, s>>>(L);
+    const int mode = clip & (MN_INPUT_CLIP | MN_INPUT_LOGITS);
+    if (mode & MN_INPUT_LOGITS) mn_partition_logprob_kernel<MN_INPUT_LOGITS><<<g, 256, 0, s>>>(L);
+    else if (mode & MN_INPUT_CLIP) mn_partition_logprob_kernel<MN_INPUT_CLIP><<<g, 256, 0, s>>>(L);
+    else mn_partition_logprob_kernel<0><<<g, 256, 0, s>>>(L);
     mn_partition_logprob_fold_kernel<<<B, 96, 0, s>>>(p->d_logprob_partial, B, gx, p->d_logprob);
     p->timings.other_launches += 2;
     p->last_omf = omf;

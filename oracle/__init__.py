@@ -9,7 +9,7 @@ Two checkers live here:
   ``oracle/_ref/libsegment_ref.so`` (``make -C oracle ref``), driven through ctypes with the same
   glue as ``/root/reference/utils/csegment/c_segment.pyx:53-84``.
 * ``oracle_run_segmentation`` -- the plain-C restatement ``mergenet_oracle.c`` (``liboracle.so``),
-  deterministic tie-break (mp desc, lo asc, hi asc), with counters and an optional merge log.
+  deterministic tie-break (mp desc, then the (u, D) scatter rule of mn_common.h: mn_tie), with counters and an optional merge log.
 
 Parity pin: the reference has no golden vectors for this path; the restatement is pinned against
 the compiled reference itself (tests/test_oracle_vs_reference.py) and against fixtures generated
