@@ -1,7 +1,7 @@
-"""quick perf probe (dev tool): python tools_probe.py H W B [soft]"""
+"""quick perf probe (dev tool): python tools/probe.py H W B [soft]"""
 import sys, time, json
 import numpy as np
-sys.path.insert(0, '.')
+import os; sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 from mergenet_b200 import BatchSegmenter, SegmenterOptions, synth
 h, w, B = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 soft = (sys.argv[4] != 'oracle') if len(sys.argv) > 4 else True
