@@ -175,17 +175,19 @@ struct MnProdAcc {
   __device__ __forceinline__ double total() const { return log(m) + (double)e * 0x1.62e42fefa39efp-1; }
 };
 #define MN_LP_FAST(bits) ((bits) - 0x33800000u < 0x3f800000u - 0x33800000u)  // a float in [2^-24, 1)
-template <int MODE>
+// KT: the number of offsets when it is one of the usual ones (fully unrolled, no predicates), 0 = any K <= MN_MAX_K
+template <int MODE, int KT>
 __global__ void __launch_bounds__(256, 3) mn_partition_logprob_kernel(MnLogprobParams P) {
   __shared__ double red[3][8];
-  const int N = P.N, W = P.W, H = P.H, K = P.K;
+  const int N = P.N, W = P.W, H = P.H, K = KT ? KT : P.K;
+  constexpr int KU = KT ? KT : MN_MAX_K;
   for (int b = blockIdx.y; b < P.nimg; b += gridDim.y) {
     const int* mask = P.d_mask + (size_t)b * N;
     const int* ocls = P.d_object_class + (size_t)b * N;
     const float* cp = P.d_class + (size_t)b * P.C * N;
     const float* ap = P.d_adj + (size_t)b * K * N;
-    MnProdAcc ac, aall, asame;  // class factors; every pair's factor (s inside an instance, 1 - s across); the inside ones
-    ac.init(); aall.init(); asame.init();
+    MnProdAcc ac, as, ad;  // class factors; s of the pairs inside an instance; 1 - s of the pairs across two
+    ac.init(); as.init(); ad.init();
     double slow_c = 0.0, slow_s = 0.0, slow_d = 0.0;  // logs taken one by one (out-of-domain factors)
     int it = 0;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x, it++) {
@@ -194,23 +196,22 @@ __global__ void __launch_bounds__(256, 3) mn_partition_logprob_kernel(MnLogprobP
       int cls = lab > 0 ? ocls[lab - 1] : 0;
       cls = cls < 0 ? 0 : (cls >= P.C ? P.C - 1 : cls);  // (only a failed image can hold anything else)
       const float cv = mn_logprob_input<MODE>(cp[(size_t)cls * N + p]);
-      float sv[MN_MAX_K]; int lq[MN_MAX_K];
+      float sv[KU]; int lq[KU];
       const bool interior = row >= P.maxr && row < H - P.maxr && col >= P.maxc && col < W - P.maxc;
-      uint32_t ok = 0;  // bit k: the pair (p, k) exists
+      uint32_t missing = 0;  // bit k: the pair (p, k) leaves the image
       if (interior) {   // every load of the pixel issued before the first use
 #pragma unroll
-        for (int k = 0; k < MN_MAX_K; k++)
-          if (k < K) { sv[k] = ap[(size_t)k * N + p]; lq[k] = mask[p + P.delta[k]]; }
-        ok = (1u << K) - 1u;
-      } else {
+        for (int k = 0; k < KU; k++)
+          if (KT || k < K) { sv[k] = ap[(size_t)k * N + p]; lq[k] = mask[p + P.delta[k]]; }
+      } else {          // border band: pairs that leave the image do not exist
 #pragma unroll
-        for (int k = 0; k < MN_MAX_K; k++) {
-          if (k < K) {
+        for (int k = 0; k < KU; k++) {
+          if (KT || k < K) {
             const int r2 = row + P.off_r[k], c2 = col + P.off_c[k];
             const bool in = r2 >= 0 && r2 < H && c2 >= 0 && c2 < W;
             sv[k] = in ? ap[(size_t)k * N + p] : 0.5f;
-            lq[k] = in ? mask[r2 * W + c2] : -1;
-            ok |= in ? (1u << k) : 0u;
+            lq[k] = in ? mask[r2 * W + c2] : lab;
+            missing |= in ? 0u : (1u << k);
           }
         }
       }
@@ -219,35 +220,36 @@ __global__ void __launch_bounds__(256, 3) mn_partition_logprob_kernel(MnLogprobP
         if (vb - 0x00800000u < 0x7f000000u) ac.m = __dmul_rn(ac.m, mn_f32bits_to_f64(vb));  // positive normal float
         else slow_c += log((double)cv);
       }
-      bool fast = true;
+      bool fast = missing == 0;  // (a border pixel with a missing pair takes the one-by-one path)
 #pragma unroll
-      for (int k = 0; k < MN_MAX_K; k++)
-        if (k < K) { sv[k] = mn_logprob_input<MODE>(sv[k]); fast = fast && MN_LP_FAST(__float_as_uint(sv[k])); }
+      for (int k = 0; k < KU; k++)
+        if (KT || k < K) {
+          sv[k] = mn_logprob_input<MODE>(sv[k]);
+          if (MODE == 0) fast = fast && MN_LP_FAST(__float_as_uint(sv[k]));  // (clipped values are in the domain)
+        }
       if (fast) {
 #pragma unroll
-        for (int k = 0; k < MN_MAX_K; k++) {
-          if (k < K) {
-            const bool on = (ok >> k) & 1u, same = lq[k] == lab;
+        for (int k = 0; k < KU; k++) {
+          if (KT || k < K) {
             const double sd = mn_f32bits_to_f64(__float_as_uint(sv[k]));
-            const double f = on ? (same ? sd : __dadd_rn(1.0, -sd)) : 1.0;
-            aall.m = __dmul_rn(aall.m, f);
-            asame.m = __dmul_rn(asame.m, same ? f : 1.0);
+            if (lq[k] == lab) as.m = __dmul_rn(as.m, sd);
+            else ad.m = __dmul_rn(ad.m, __dadd_rn(1.0, -sd));
           }
         }
       } else {
 #pragma unroll
-        for (int k = 0; k < MN_MAX_K; k++) {  // (static indices: sv / lq stay in registers)
-          if (k < K && ((ok >> k) & 1u)) {
+        for (int k = 0; k < KU; k++) {  // (static indices: sv / lq stay in registers)
+          if ((KT || k < K) && !((missing >> k) & 1u)) {
             const bool same = lq[k] == lab;
             const double l = log(same ? (double)sv[k] : 1.0 - (double)sv[k]);
             slow_s += same ? l : 0.0; slow_d += same ? 0.0 : l;
           }
         }
       }
-      if (it & 1) { aall.renorm(); asame.renorm(); }  // (at most 2 * 16 factors >= 2^-24 since the last one)
-      if ((it & 7) == 7) ac.renorm();                 // (8 class factors >= 2^-126)
+      if (it & 1) { as.renorm(); ad.renorm(); }   // (at most 2 * 16 factors >= 2^-24 since the last one)
+      if ((it & 7) == 7) ac.renorm();              // (8 class factors >= 2^-126)
     }
-    double tc = ac.total() + slow_c, ts = asame.total() + slow_s, td = (aall.total() - asame.total()) + slow_d;
+    double tc = ac.total() + slow_c, ts = as.total() + slow_s, td = ad.total() + slow_d;
     for (int o = 16; o > 0; o >>= 1) {
       tc += __shfl_xor_sync(0xffffffffu, tc, o); ts += __shfl_xor_sync(0xffffffffu, ts, o); td += __shfl_xor_sync(0xffffffffu, td, o);
     }
@@ -260,6 +262,12 @@ __global__ void __launch_bounds__(256, 3) mn_partition_logprob_kernel(MnLogprobP
     }
     __syncthreads();
   }
+}
+template <int MODE>
+static void mn_launch_partition_logprob(const MnLogprobParams& L, dim3 g, cudaStream_t s) {
+  if (L.K == 10) mn_partition_logprob_kernel<MODE, 10><<<g, 256, 0, s>>>(L);
+  else if (L.K == 16) mn_partition_logprob_kernel<MODE, 16><<<g, 256, 0, s>>>(L);
+  else mn_partition_logprob_kernel<MODE, 0><<<g, 256, 0, s>>>(L);
 }
 // one warp per image and term: the block partials in index order (fixed summation tree)
 __global__ void mn_partition_logprob_fold_kernel(const double* partial, int nimg, int nblk, double* out /* [nimg][4] */) {
@@ -730,9 +738,9 @@ static int run_back(mn_plan* p, int B, const float* d_class, const float* d_adj,
     const int gx = std::max(1, std::min(MN_LOGPROB_BLOCKS, (N + 1023) / 1024));
     dim3 g((unsigned)gx, (unsigned)std::min(B, 65535));
     const int mode = clip & (MN_INPUT_CLIP | MN_INPUT_LOGITS);
-    if (mode & MN_INPUT_LOGITS) mn_partition_logprob_kernel<MN_INPUT_LOGITS><<<g, 256, 0, s>>>(L);
-    else if (mode & MN_INPUT_CLIP) mn_partition_logprob_kernel<MN_INPUT_CLIP><<<g, 256, 0, s>>>(L);
-    else mn_partition_logprob_kernel<0><<<g, 256, 0, s>>>(L);
+    if (mode & MN_INPUT_LOGITS) mn_launch_partition_logprob<MN_INPUT_LOGITS>(L, g, s);
+    else if (mode & MN_INPUT_CLIP) mn_launch_partition_logprob<MN_INPUT_CLIP>(L, g, s);
+    else mn_launch_partition_logprob<0>(L, g, s);
     mn_partition_logprob_fold_kernel<<<B, 96, 0, s>>>(p->d_logprob_partial, B, gx, p->d_logprob);
     p->timings.other_launches += 2;
     p->last_omf = omf;
