@@ -1139,7 +1139,9 @@ extern "C" int mn_debug_edge_dump(int H, int W, int C, int K, const int* offset_
                                   float* h_adj, float sdb, float omf, float mlb, float* clp, int* cls,
                                   float* same, float* diff, float* oml, float* mp, int* lo, int* hi) {
   mn_plan* p = nullptr;
-  int rc = mn_plan_create(&p, 1, H, W, C, K, offset_list, 0);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }  // the caller's current device
+  int rc = mn_plan_create(&p, 1, H, W, C, K, offset_list, dev);
   if (rc) return rc;
   auto done = [&](int code) { mn_plan_destroy(p); g_last_error = code; return code; };
   if (ensure_staging(p, 1)) return done(MN_STATUS_CUDA);
@@ -1181,7 +1183,9 @@ __global__ void mn_fill_probs_kernel(float* p, size_t n, uint32_t seed) {
 extern "C" int mn_debug_edge_bench(int H, int W, int C, int K, const int* offset_list, int B, int iters, int clip,
                                    float* ms_per_launch) {
   mn_plan* p = nullptr;
-  int rc = mn_plan_create(&p, B, H, W, C, K, offset_list, 0);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }  // the caller's current device
+  int rc = mn_plan_create(&p, B, H, W, C, K, offset_list, dev);
   if (rc) return rc;
   auto done = [&](int code) { mn_plan_destroy(p); g_last_error = code; return code; };
   const size_t N = p->N;
