@@ -174,10 +174,13 @@ struct MnProdAcc {
   }
   __device__ __forceinline__ double total() const { return log(m) + (double)e * 0x1.62e42fefa39efp-1; }
 };
+#ifndef MN_LP_BLOCKS
+#define MN_LP_BLOCKS 4  // resident blocks per SM the register budget is set for (measured: 0.50 ms vs 0.57 ms at 3, 16 images; fetching label and class one pixel ahead and dropping the division: 0.64 ms, not kept)
+#endif
 #define MN_LP_FAST(bits) ((bits) - 0x33800000u < 0x3f800000u - 0x33800000u)  // a float in [2^-24, 1)
 // KT: the number of offsets when it is one of the usual ones (fully unrolled, no predicates), 0 = any K <= MN_MAX_K
 template <int MODE, int KT>
-__global__ void __launch_bounds__(256, 3) mn_partition_logprob_kernel(MnLogprobParams P) {
+__global__ void __launch_bounds__(256, MN_LP_BLOCKS) mn_partition_logprob_kernel(MnLogprobParams P) {
   __shared__ double red[3][8];
   const int N = P.N, W = P.W, H = P.H, K = KT ? KT : P.K;
   constexpr int KU = KT ? KT : MN_MAX_K;
@@ -215,17 +218,13 @@ __global__ void __launch_bounds__(256, 3) mn_partition_logprob_kernel(MnLogprobP
           }
         }
       }
-      {
-        const uint32_t vb = __float_as_uint(cv);
-        if (vb - 0x00800000u < 0x7f000000u) ac.m = __dmul_rn(ac.m, mn_f32bits_to_f64(vb));  // positive normal float
-        else slow_c += log((double)cv);
-      }
-      bool fast = missing == 0;  // (a border pixel with a missing pair takes the one-by-one path)
+      bool fast = true;
 #pragma unroll
       for (int k = 0; k < KU; k++)
         if (KT || k < K) {
           sv[k] = mn_logprob_input<MODE>(sv[k]);
-          if (MODE == 0) fast = fast && MN_LP_FAST(__float_as_uint(sv[k]));  // (clipped values are in the domain)
+          if (!interior && ((missing >> k) & 1u)) sv[k] = 1.0f;  // no pair: the factor 1 on the "inside" product (lq = lab)
+          else if (MODE == 0) fast = fast && MN_LP_FAST(__float_as_uint(sv[k]));  // (clipped values are in the domain)
         }
       if (fast) {
 #pragma unroll
@@ -245,6 +244,11 @@ __global__ void __launch_bounds__(256, 3) mn_partition_logprob_kernel(MnLogprobP
             slow_s += same ? l : 0.0; slow_d += same ? 0.0 : l;
           }
         }
+      }
+      {  // the class factor last: its load hangs on two earlier ones (label -> class of the label -> that plane)
+        const uint32_t vb = __float_as_uint(cv);
+        if (vb - 0x00800000u < 0x7f000000u) ac.m = __dmul_rn(ac.m, mn_f32bits_to_f64(vb));  // positive normal float
+        else slow_c += log((double)cv);
       }
       if (it & 1) { as.renorm(); ad.renorm(); }   // (at most 2 * 16 factors >= 2^-24 since the last one)
       if ((it & 7) == 7) ac.renorm();              // (8 class factors >= 2^-126)
