@@ -66,7 +66,7 @@
 #endif
 #define MN_OVF 128        // records in the hash overflow area (cached in shared memory)
 #ifndef MN_REFILL_TARGET
-#define MN_REFILL_TARGET 384      // stop loading tree leaves once this many entries are staged
+#define MN_REFILL_TARGET 256      // stop loading tree leaves once this many entries are staged (A/B at 1024x2048, merge ms: 64: 11212, 128: 10986, 192: 10950, 256: 10925-10983, 384: 11128, 640: 11618, 832: 12042)
 #endif
 #ifndef MN_REFILL_STATIC_MIN
 #define MN_REFILL_STATIC_MIN 128  // sort-buffer slots always left for initial entries

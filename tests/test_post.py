@@ -128,3 +128,34 @@ def test_gpu_resize_bilinear_equals_oracle_and_cv2(oracle_mod, lib_mod):
     want = np.moveaxis(cv2.resize(np.moveaxis(src, 0, -1), (2048, 1024)), -1, 0)
     got = post.resize_maps_bilinear(src, 1024, 2048)
     assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(want).view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_driver_loop_body_end_to_end(oracle_mod, lib_mod):
+    """The body of egs/cityscape/local/segment.py:112-186 with every step on the GPU -- maps resized to the
+    segmentation size (cv2.resize, :116-123), c_segment.run_segmentation (:138-143), mask back at the image size
+    (INTER_NEAREST, :147-149), COCO results (:165-186) -- against the same chain built from the checkers
+    (cv2 / the oracle restatements): identical masks after canonical relabel, identical classes, identical RLE."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    import cases
+    from mergenet_b200 import c_segment, post, synth
+    cp, sp, C, offs = cases.cityscapes_like(48, 96, 31, True, rmax=20)   # network output at half size
+    seg_h, seg_w, img_h, img_w = 96, 192, 150, 300
+    cls_r = synth.clip_probs(post.resize_maps_bilinear(cp, seg_h, seg_w))
+    adj_r = synth.clip_probs(post.resize_maps_bilinear(sp, seg_h, seg_w))
+    mask, ocls = c_segment.run_segmentation(cls_r, adj_r, C, offs, *cases.RECIPE_OPTS)
+    big = post.resize_masks_nearest(mask, img_h, img_w)
+    res = post.convert_to_coco_result(big, ocls, 7, list(range(100, 100 + C)))
+    # the checkers' chain
+    cls_o = synth.clip_probs(oracle_mod.oracle_resize_bilinear(cp, seg_h, seg_w))
+    adj_o = synth.clip_probs(oracle_mod.oracle_resize_bilinear(sp, seg_h, seg_w))
+    assert np.array_equal(cls_r.view(np.uint32), cls_o.view(np.uint32)) and np.array_equal(adj_r.view(np.uint32), adj_o.view(np.uint32))
+    m0, c0, _ = oracle_mod.oracle_run_segmentation(cls_o, adj_o, C, offs, *cases.RECIPE_OPTS)
+    assert cases.same_result(oracle_mod, (m0, c0), (mask, ocls))
+    assert np.array_equal(big, oracle_mod.oracle_resize_nearest(mask, img_h, img_w))
+    want = oracle_mod.oracle_coco_rle(big, len(ocls))
+    assert len(res) == len(ocls) and len(ocls) > 0
+    for i, r in enumerate(res):
+        assert r["segmentation"]["counts"] == want[i] and r["segmentation"]["size"] == [img_h, img_w]
+        assert r["category_id"] == 100 + ocls[i] and r["image_id"] == 7
