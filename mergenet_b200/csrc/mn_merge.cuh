@@ -72,7 +72,9 @@
 #define MN_REFILL_STATIC_MIN 128  // sort-buffer slots always left for initial entries
 #endif
 #define MN_NEG_INF (-3.0e38f)
+#ifndef MN_RANK_MAX
 #define MN_RANK_MAX 256  // up to this many entries are ordered by brute-force ranking (no barriers)
+#endif
 // cycle accounting buckets (thread 0, clock64)
 #define MN_NCYC 16
 #define MN_CY_CONFLICT 0 // footprints into the conflict table + conflict check
