@@ -160,6 +160,26 @@ int mn_modeb_segment_host(const float* h_log_class, const float* h_log_same, con
                           double merge_logprob_bias, double prune_threshold, long long* h_mask, int* h_object_class,
                           int* n_instances, long long* stats4);
 
+/* ---- tie-exact replay: the reference's C++ segmenter INCLUDING its order among equal priorities ---------------- */
+/*
+ * c_run_segmentation above reproduces the reference (segment.cc:539-727) wherever the merge order is decided by the
+ * priorities, and uses a fixed rule of its own among EXACTLY equal priorities; the reference's order there is an
+ * artefact of libstdc++ -- PriorityCompare sees the priority only (segment.h:270-275), so std::push_heap /
+ * std::pop_heap decide, fed in std::unordered_map iteration order (segment.cc:650-652).  On inputs whose partition
+ * depends on that order (e.g. block-quantized maps) this entry gives the reference's own result: the same edge pass,
+ * then ONE GPU thread that replays the loop with GCC 13 libstdc++'s heap and hash-table orders restated literally
+ * (mn_exact.cuh, mn_stl_order.h), including the `objects` map whose iteration order numbers the labels
+ * (segment.cc:503-515).  h_mask [H][W] and h_object_class [H*W] therefore equal the reference's RAW output arrays
+ * (not only up to relabelling).  Sequential by nature: seconds at 256 x 512, for validation and small / medium
+ * images, not the hot path.  Arguments as c_run_segmentation (host buffers; h_adj rewritten in place when
+ * same_different_bias != 0), with height before width and the batch entries' `clip` flags.
+ * stats4 (optional): queue pops, merges, queue pushes, bucket-arena collections.
+ */
+int mn_exact_segment_host(const float* h_class, int num_classes, float* h_adj, int num_offsets, int height, int width,
+                          const int* offset_list, int clip, float same_different_bias, float object_merge_factor,
+                          float merge_logprob_bias, int* h_mask, int* h_object_class, int* n_instances,
+                          long long* stats4);
+
 /* ---- the step after the path: masks back at the image size, COCO run-length encoding ---- */
 /*
  * cv2.resize(mask, (out_width, out_height), interpolation=cv2.INTER_NEAREST) for `batch` int32 masks on

@@ -12,13 +12,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MN_LIB_PATH selects another BUILD of this same library (e.g. the -DMN_PHASE_CYCLES profiling build)
 LIB_PATH = os.environ.get("MN_LIB_PATH") or os.path.join(_HERE, "libmergenet_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["mn_api.cu", "mn_edge.cuh", "mn_merge.cuh", "mn_modeb.cuh", "mn_post.cuh", "mn_layout.h", "mn_common.h", "mn_log1m_tab.h"]
+SOURCES = ["mn_api.cu", "mn_edge.cuh", "mn_merge.cuh", "mn_modeb.cuh", "mn_exact.cuh", "mn_stl_order.h", "mn_stl_primes.h", "mn_post.cuh", "mn_layout.h", "mn_common.h", "mn_log1m_tab.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-fmad=false"]
 
 EXPORTS = ["c_run_segmentation", "mn_shutdown", "mn_last_error", "mn_status_string", "mn_device_count",
            "mn_workspace_bytes_per_image", "mn_plan_create", "mn_plan_destroy",
-           "mn_segment_batch_device", "mn_segment_batch_host", "mn_modeb_segment_host", "mn_plan_image_stats",
+           "mn_segment_batch_device", "mn_segment_batch_host", "mn_modeb_segment_host", "mn_exact_segment_host", "mn_plan_image_stats",
            "mn_plan_timings", "mn_plan_image_logprob", "mn_debug_edge_dump", "mn_debug_libm", "mn_debug_edge_bench",
            "mn_resize_masks_nearest_device", "mn_resize_masks_nearest_host", "mn_resize_maps_bilinear_device", "mn_resize_maps_bilinear_host", "mn_mask_to_coco_rle_host", "mn_post_last_ms"]
 
@@ -120,6 +120,9 @@ def lib():
     L.mn_modeb_segment_host.restype = ctypes.c_int
     L.mn_modeb_segment_host.argtypes = [_V, _V, _V, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _I,
                                         ctypes.c_double, ctypes.c_double, ctypes.c_double, _V, _V, _V, _V]
+    L.mn_exact_segment_host.restype = ctypes.c_int
+    L.mn_exact_segment_host.argtypes = [_F, ctypes.c_int, _F, ctypes.c_int, ctypes.c_int, ctypes.c_int, _I, ctypes.c_int,
+                                        ctypes.c_float, ctypes.c_float, ctypes.c_float, _I, _I, _I, _V]
     L.mn_plan_image_stats.restype = ctypes.c_int
     L.mn_plan_image_stats.argtypes = [_V, ctypes.c_int, ctypes.POINTER(ImageStats)]
     L.mn_plan_image_logprob.restype = ctypes.c_int

@@ -24,6 +24,8 @@
 #include "mn_layout.h"
 #include "mn_merge.cuh"
 #include "mn_modeb.cuh"
+#include "mn_exact.cuh"
+#include "mn_stl_primes.h"
 
 // ------------------------------------------------------------------------------------------------
 static thread_local int g_last_error = MN_STATUS_OK;
@@ -1134,6 +1136,96 @@ extern "C" int mn_modeb_segment_host(const float* h_logc, const float* h_lsame, 
   if (status == 1) return done(MN_STATUS_Q_POOL);
   if (status == 2) return done(MN_STATUS_HASH_FULL);
   if (status == 3) return done(MN_STATUS_NO_BACKGROUND);
+  return done(MN_STATUS_OK);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tie-exact replay of the reference's C++ segmenter (mn_exact.cuh): the edge pass of the hot path, then ONE thread
+// that replays segment.cc:539-727 with libstdc++'s heap and hash-table orders
+__global__ void mn_exact_kernel(MnExact m) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) mnx_run(m);
+}
+
+extern "C" int mn_exact_segment_host(const float* h_class, int C, float* h_adj, int K, int H, int W, const int* offset_list,
+                                     int clip, float sdb, float omf, float mlb, int* h_mask, int* h_object_class,
+                                     int* n_instances, long long* stats4) {
+  g_last_error = MN_STATUS_OK;
+  if (!h_class || !h_adj || !offset_list || !h_mask || !h_object_class || !n_instances) {
+    g_last_error = MN_STATUS_BAD_ARG;
+    return MN_STATUS_BAD_ARG;
+  }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { g_last_error = MN_STATUS_CUDA; return MN_STATUS_CUDA; }  // the caller's current device
+  mn_plan* p = nullptr;
+  int rc = mn_plan_create(&p, 1, H, W, C, K, offset_list, dev);  // (checks the shape; its workspace receives the edge pass)
+  if (rc) return rc;
+  unsigned char* d = nullptr;
+  auto done = [&](int code) { if (d) cudaFree(d); mn_plan_destroy(p); g_last_error = code; return code; };
+  if (ensure_staging(p, 1)) return done(MN_STATUS_CUDA);
+  const size_t N = p->N, E = (size_t)p->E;
+  cudaStream_t s = p->stream;
+  MnExact m;
+  memset(&m, 0, sizeof(m));
+  m.C = C; m.K = K; m.H = H; m.W = W; m.N = (int)N; m.E = (long long)E; m.omf = omf; m.mlb = mlb;
+  for (int k = 0; k < K; k++) { m.off_r[k] = offset_list[2 * k]; m.off_c[k] = offset_list[2 * k + 1]; }
+  m.heap.cap = (long long)(8 * E + 1024);  // (the reference's own queue holds 3.2 E entries over a whole 1024 x 2048 run)
+  m.arena.half = (long long)(32 * N + 5 * E + 4096);
+  if (const char* w = getenv("MN_EXACT_ARENA_WORDS")) {  // (test hook: a small half-space, so that the collection runs on the device too)
+    const long long v = atoll(w);
+    if (v > 0 && v < m.arena.half) m.arena.half = v;
+  }
+  m.arena.ntabs = (int)N + 1;
+  // one allocation, carved up (256-byte aligned pieces)
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) / 256 * 256; return at; };
+  const size_t a_npix = take(N * 4), a_cls = take(N * 4), a_pnext = take(N * 4), a_ptail = take(N * 4),
+               a_tab = take((N + 1) * sizeof(MnStlTab)), a_onext = take(N * 4), a_o1 = take(E * 4), a_o2 = take(E * 4),
+               a_oml = take(E * 4), a_mp = take(E * 4), a_merged = take(E * 4), a_ndn = take(2 * E * 4),
+               a_ndk = take(2 * E * 8), a_qk = take((size_t)m.heap.cap * 4), a_qr = take((size_t)m.heap.cap * 4),
+               a_bk = take((size_t)m.arena.half * 2 * 4), a_primes = take(MN_STL_NPRIMES * 4), a_mask = take(N * 4),
+               a_ocls = take(N * 4), a_scalars = take(256);
+  if (cudaMalloc(&d, o) != cudaSuccess) { d = nullptr; return done(MN_STATUS_CUDA); }
+  m.npix = (int*)(d + a_npix); m.cls = (int*)(d + a_cls); m.pix_next = (int*)(d + a_pnext); m.pix_tail = (int*)(d + a_ptail);
+  m.tab = (MnStlTab*)(d + a_tab); m.ob_next = (int*)(d + a_onext);
+  m.r_o1 = (int*)(d + a_o1); m.r_o2 = (int*)(d + a_o2); m.r_oml = (float*)(d + a_oml); m.r_mp = (float*)(d + a_mp);
+  m.r_merged = (int*)(d + a_merged); m.nd_next = (int*)(d + a_ndn); m.nd_key = (unsigned long long*)(d + a_ndk);
+  m.heap.key = (float*)(d + a_qk); m.heap.rec = (int*)(d + a_qr); m.heap.n = 0;
+  m.arena.bk = (int*)(d + a_bk); m.arena.tabs = m.tab; m.arena.primes = (const unsigned*)(d + a_primes);
+  m.out_mask = (int*)(d + a_mask); m.out_cls = (int*)(d + a_ocls);
+  // scalars: stats[8] | bump | base | out_n | status | overflow
+  long long* sc = (long long*)(d + a_scalars);
+  m.stats = sc; m.arena.collections = sc + 3; m.arena.bump = sc + 8; m.arena.base = sc + 9;
+  m.out_n = (int*)(sc + 10); m.status = (int*)(sc + 11); m.arena.overflow = (int*)(sc + 12);
+  static const unsigned primes[MN_STL_NPRIMES] = {MN_STL_PRIMES};
+  cudaError_t e = cudaMemcpyAsync(p->d_in_class, h_class, (size_t)C * N * 4, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_in_adj, h_adj, (size_t)K * N * 4, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync((void*)m.arena.primes, primes, sizeof(primes), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(sc, 0, 256, s);
+  if (e != cudaSuccess) return done(MN_STATUS_CUDA);
+  // edge pass (+ the record init of the hot path, unused here) exactly as the drop-in symbol runs it
+  // (like the drop-in symbol, any floats are accepted: out-of-domain maps take the kernel with libm's special values)
+  rc = run_front(p, 0, 1, p->d_in_class, p->d_in_adj, clip | MN_INPUT_CHECK_DOMAIN, sdb, omf, mlb, s, false);
+  if (rc) return done(rc);
+  const MnImage& im = p->h_imgs[0];
+  m.clp = im.clp; m.rec_same = im.rec_same; m.rec_diff = im.rec_diff;
+  mn_exact_kernel<<<1, 32, 0, s>>>(m);
+  int status = 0, n = 0;
+  long long st[8] = {0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(st, sc, 64, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&n, m.out_n, 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&status, m.status, 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_mask, m.out_mask, N * 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_object_class, m.out_cls, N * 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && sdb != 0.0f)  // the reference rewrites the caller's buffer (segment.cc:187-191)
+    e = cudaMemcpyAsync(h_adj, p->d_in_adj, (size_t)K * N * 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return done(MN_STATUS_CUDA);
+  *n_instances = n;
+  if (stats4) for (int i = 0; i < 4; i++) stats4[i] = st[i];
+  if (status == 1) return done(MN_STATUS_Q_POOL);
+  if (status == 2) return done(MN_STATUS_PL_POOL);
+  if (status == 3) return done(MN_STATUS_INTERNAL);
+  if (status == 4) return done(MN_STATUS_BAD_ARG);
   return done(MN_STATUS_OK);
 }
 

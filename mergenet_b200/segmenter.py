@@ -11,6 +11,8 @@
   (mn_modeb.cuh): the small-image mode the pure-Python reference is, not the hot path.
 * ``mode="csegment"`` ("Mode A"): the semantics of the reference's C++ port, which the Cityscapes recipe
   calls (egs/cityscape/local/segment.py:138-143) -- the hot path of this library.
+* ``mode="csegment-exact"``: Mode A including the reference's order among exactly equal priorities and its label
+  numbering (``c_segment.run_segmentation_exact``; sequential, for validation and small / medium images).
 
 ``BatchSegmenter`` is the additive batched interface (device tensors in, device tensors out).
 """
@@ -28,8 +30,8 @@ SegmenterOptions = namedtuple('SegmenterOptions',
 class ObjectSegmenter:
     def __init__(self, nnet_class_probs, nnet_sameness_probs, num_classes, offsets, opts=None,
                  mode="segmenter"):
-        if mode not in ("segmenter", "csegment"):
-            raise ValueError("mode must be 'segmenter' (utils/segmenter.py semantics) or 'csegment'")
+        if mode not in ("segmenter", "csegment", "csegment-exact"):
+            raise ValueError("mode must be 'segmenter' (utils/segmenter.py semantics), 'csegment' or 'csegment-exact'")
         self.mode = mode
         self.opts = opts
         if self.opts is None:
@@ -66,11 +68,12 @@ class ObjectSegmenter:
         """(mask [H,W], object_class list) -- segmenter.py:432-483.  mode "segmenter": int64 mask, labels in
         ascending surviving object id, after prune(prune_threshold) (the reference always prunes at 200.0);
         raises UnboundLocalError where the reference does.  mode "csegment": the C++ port's result (int32)."""
-        if self.mode == "csegment":
-            return c_segment.run_segmentation(self.class_probs, self.sameness_probs, self.num_classes,
-                                              [tuple(o) for o in self.offsets],
-                                              self.opts.same_different_bias, self.opts.object_merge_factor,
-                                              self.opts.merge_logprob_bias)
+        if self.mode != "segmenter":
+            run = c_segment.run_segmentation if self.mode == "csegment" else c_segment.run_segmentation_exact
+            return run(self.class_probs, self.sameness_probs, self.num_classes,
+                       [tuple(o) for o in self.offsets],
+                       self.opts.same_different_bias, self.opts.object_merge_factor,
+                       self.opts.merge_logprob_bias)
         _lib.require_device()
         return self._run_modeb(_lib.lib().mn_modeb_segment_host, prune_threshold)
 

@@ -35,6 +35,36 @@ def smooth(h, w, seed):
     return cp, sp, 9, offs
 
 
+def quantized(h, w, seed, C=3, K=6):
+    """Block-quantized maps (levels 0.2 / 0.5 / 0.8 on 4x4 blocks): thousands of EXACTLY equal priorities whose pop
+    order decides which of several equally good merges happens first -- the inputs on which the reference's result
+    depends on libstdc++'s heap / hash-table orders."""
+    rng = np.random.default_rng(seed)
+    lv = np.array([0.2, 0.5, 0.8], np.float32)
+    up = lambda a: np.kron(a, np.ones((4, 4), np.float32))[:h, :w]  # noqa: E731
+    cp = np.stack([up(lv[rng.integers(0, 3, ((h + 3) // 4, (w + 3) // 4))]) for _ in range(C)])
+    sp = np.stack([up(lv[rng.integers(0, 3, ((h + 3) // 4, (w + 3) // 4))]) for _ in range(K)])
+    return synth.clip_probs(cp), synth.clip_probs(sp), C, synth.generate_offsets(40, K)
+
+
+def tie_exact_cases():
+    """(name, class_pred, adj_pred, C, offsets, opts) -- the fixtures of tests/golden/exact (raw reference outputs)."""
+    out = []
+    out.append(("quant_17x23", ) + quantized(17, 23, 0) + (PLAIN_OPTS,))
+    out.append(("quant_24x32_a", ) + quantized(24, 32, 1) + (PLAIN_OPTS,))
+    out.append(("quant_24x32_b", ) + quantized(24, 32, 2) + (RECIPE_OPTS,))
+    out.append(("quant_32x32_C4_K16", ) + quantized(32, 32, 3, C=4, K=16) + (PLAIN_OPTS,))
+    out.append(("quant_sdb_20x28", ) + quantized(20, 28, 4) + ((0.5, 1.0, 0.03),))
+    out.append(("quant_omf_40x56", ) + quantized(40, 56, 5, C=5, K=10) + (QUARTER_OPTS,))
+    out.append(("quant_96x128", ) + quantized(96, 128, 6, C=5, K=10) + (PLAIN_OPTS,))
+    out.append(("city_oracle_48x64", ) + cityscapes_like(48, 64, 1, False) + (RECIPE_OPTS,))
+    out.append(("smooth_40x56", ) + smooth(40, 56, 3) + (QUARTER_OPTS,))
+    out.append(("coco_soft_44x52", ) + coco_like(44, 52, 5, True) + (RECIPE_OPTS,))
+    out.append(("tiny_1x7", ) + cityscapes_like(1, 7, 6, True, n_shapes=1, rmax=3) + (RECIPE_OPTS,))
+    out.append(("one_pixel", ) + quantized(1, 1, 7) + (PLAIN_OPTS,))
+    return out
+
+
 def small_cases():
     """(name, class_pred, adj_pred, C, offsets) -- the parity matrix."""
     out = []

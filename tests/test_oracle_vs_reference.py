@@ -111,15 +111,7 @@ def test_oracle_matches_reference_on_saturated_maps(oracle_mod):
 
 
 def _quantized_case(h, w, seed, C=3, K=6):
-    """Block-quantized maps (levels 0.2 / 0.5 / 0.8 on 4x4 blocks): thousands of EXACTLY equal priorities whose pop
-    order decides which of several equally good merges happens first."""
-    from mergenet_b200 import synth
-    rng = np.random.default_rng(seed)
-    lv = np.array([0.2, 0.5, 0.8], np.float32)
-    up = lambda a: np.kron(a, np.ones((4, 4), np.float32))[:h, :w]  # noqa: E731
-    cp = np.stack([up(lv[rng.integers(0, 3, ((h + 3) // 4, (w + 3) // 4))]) for _ in range(C)])
-    sp = np.stack([up(lv[rng.integers(0, 3, ((h + 3) // 4, (w + 3) // 4))]) for _ in range(K)])
-    return synth.clip_probs(cp), synth.clip_probs(sp), C, synth.generate_offsets(40, K)
+    return cases.quantized(h, w, seed, C, K)
 
 
 def test_tie_dependent_inputs_known_limitation(oracle_mod):
