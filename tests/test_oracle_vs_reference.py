@@ -115,14 +115,15 @@ def _quantized_case(h, w, seed, C=3, K=6):
 
 
 def test_tie_dependent_inputs_known_limitation(oracle_mod):
-    """KNOWN LIMITATION, kept visible: among EQUAL priorities the reference pops in the order its libstdc++ binary
-    heap happens to hold them (PriorityCompare compares the priority only, segment.h:270-275; the push order comes
-    from unordered_map iteration, cc:650-652) -- a function of the whole push/pop history that no parallel
-    scheduler can replay.  Oracle and CUDA path use one fixed total order instead (mn_common.h: mn_tie).  On inputs
+    """The HOT PATH's tie rule, kept visible: among EQUAL priorities the reference pops in the order its libstdc++
+    binary heap happens to hold them (PriorityCompare compares the priority only, segment.h:270-275; the push order
+    comes from unordered_map iteration, cc:650-652) -- a function of the whole push/pop history that no parallel
+    scheduler can replay.  Oracle and hot path use one fixed total order instead (mn_common.h: mn_tie).  On inputs
     whose partition does not depend on the tie order (every fixture: soft maps, saturated oracle-mode maps,
     constant maps) results are identical to the reference; on block-quantized maps they are not, and this test
     records that instead of hiding it: the oracle is deterministic, produces a partition of comparable total
-    log-prob, and differs from the reference's."""
+    log-prob, and differs from the reference's.  (The reference's own result on such inputs is what the tie-exact
+    replay returns: tests/test_exact_tie_order.py.)"""
     if not oracle_mod.have_reference():
         pytest.skip("reference .so absent")
     differ = 0
