@@ -1,0 +1,127 @@
+"""Long seeded soak (manual; the CPU suite runs the short version, tests/test_random_sweep.py): for every random case
+
+  * soft / noisy / smooth maps: unmodified reference == oracle == scheduler host build (canonical relabel), and the
+    tie-exact replay's host build == the reference's RAW arrays;
+  * quantized maps (2-4 levels on blocks: thousands of exactly equal priorities): tie-exact replay == reference RAW,
+    oracle == scheduler host build (both use the fixed tie rule).
+
+usage: python tests/manual/soak_sweep.py <seed> <n_cases> [max_h max_w] [emul .so]   (needs oracle/_ref, i.e. the build container)
+"""
+import ctypes
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+sys.path.insert(0, os.path.join(HERE, ".."))
+sys.path.insert(0, os.path.join(HERE, "..", "golden"))
+import cases  # noqa: E402
+import oracle  # noqa: E402
+import make_golden_exact  # noqa: E402
+from mergenet_b200 import synth  # noqa: E402
+from test_emul_scheduler import run_emul, NAMES  # noqa: E402,F401
+from test_random_sweep import _same  # noqa: E402
+
+
+def load_emul(path):
+    lib = ctypes.CDLL(path)
+    F = ctypes.POINTER(ctypes.c_float); I = ctypes.POINTER(ctypes.c_int); LL = ctypes.POINTER(ctypes.c_longlong)
+    lib.emul_run_segmentation.argtypes = [F, ctypes.c_int, F, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          I, I, I, ctypes.c_float, ctypes.c_float, ctypes.c_float, LL]
+    return lib
+
+
+def load_exact():
+    lib = ctypes.CDLL(os.path.join(HERE, "..", "emul", "libemul_exact.so"))
+    F, I = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)
+    lib.emul_exact_segment.restype = ctypes.c_int
+    lib.emul_exact_segment.argtypes = [F, ctypes.c_int, F, ctypes.c_int, ctypes.c_int, ctypes.c_int, I, ctypes.c_float,
+                                       ctypes.c_float, ctypes.c_float, I, I, I, ctypes.POINTER(ctypes.c_longlong),
+                                       ctypes.c_longlong]
+    return lib
+
+
+def run_exact(lib, cp, sp, C, offs, opts):
+    cp_, ap_, off, mask, ocls = oracle._glue(cp, sp, offs)
+    n = ctypes.c_int(0)
+    rc = lib.emul_exact_segment(oracle._fp(cp_), cp_.shape[0], oracle._fp(ap_), ap_.shape[0], ap_.shape[2], ap_.shape[1],
+                                oracle._ip(off), opts[0], opts[1], opts[2], oracle._ip(mask), oracle._ip(ocls),
+                                ctypes.byref(n), None, 0)
+    return rc, mask, ocls
+
+
+def random_case(rng, max_h, max_w):
+    h, w = int(rng.integers(1, max_h + 1)), int(rng.integers(1, max_w + 1))
+    C = int(rng.integers(1, 12))
+    K = int(rng.integers(1, 13))
+    offs = []
+    while len(offs) < K:
+        o = (int(rng.integers(-9, 10)), int(rng.integers(-9, 10)))
+        if o == (0, 0) or o in offs or (-o[0], -o[1]) in offs:
+            continue
+        offs.append(o)
+    kind = int(rng.integers(0, 5))
+    quant = False
+    if kind == 0:
+        cp, sp = synth.smooth_random_maps(h, w, C, K, int(rng.integers(0, 1 << 30)))
+    elif kind == 1:
+        cp = synth.clip_probs(rng.random((C, h, w)).astype(np.float32))
+        sp = synth.clip_probs(rng.random((K, h, w)).astype(np.float32))
+    elif kind == 2:
+        m, cl = synth.gt_instance_mask(h, w, max(1, h * w // 150), 6, max(2, C), int(rng.integers(0, 1 << 30)))
+        C = max(2, C)
+        cp, sp = synth.soft_maps(m, cl, C, offs, int(rng.integers(0, 1 << 30)))
+    else:  # quantized: nl levels on bs x bs blocks
+        quant = True
+        nl = int(rng.integers(2, 5)); bs = int(rng.integers(1, 6))
+        lv = np.sort(rng.random(nl).astype(np.float32) * 0.9 + 0.05)
+        up = lambda a: np.kron(a, np.ones((bs, bs), np.float32))[:h, :w]  # noqa: E731
+        g = lambda: up(lv[rng.integers(0, nl, ((h + bs - 1) // bs, (w + bs - 1) // bs))])  # noqa: E731
+        cp = synth.clip_probs(np.stack([g() for _ in range(C)]))
+        sp = synth.clip_probs(np.stack([g() for _ in range(K)]))
+    omf = float(rng.choice([1.0, 0.25, 0.1, 2.0]))
+    mlb = float(rng.choice([0.0, 0.03, -0.05, 0.2]))
+    sdb = float(rng.choice([0.0, 0.0, 0.0, 0.5, -0.7]))
+    return cp, sp, C, offs, (sdb, omf, mlb), quant
+
+
+def main():
+    seed, n = int(sys.argv[1]), int(sys.argv[2])
+    max_h = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+    max_w = int(sys.argv[4]) if len(sys.argv) > 4 else 80
+    emul = load_emul(sys.argv[5] if len(sys.argv) > 5 else os.path.join(HERE, "..", "emul", "libemul.so"))
+    exact = load_exact()
+    rng = np.random.default_rng(seed)
+    t0 = time.time()
+    nq = 0
+    for i in range(n):
+        cp, sp, C, offs, opts, quant = random_case(rng, max_h, max_w)
+        tag = (seed, i, cp.shape, sp.shape, offs, opts, quant)
+        rmask, rocls, _ = make_golden_exact.reference_raw(cp, sp, C, offs, opts)
+        rc, xm, xo = run_exact(exact, cp, sp, C, offs, opts)
+        if rc != 0 or not np.array_equal(xm, rmask) or not np.array_equal(xo, rocls):
+            print("MISMATCH exact vs reference", rc, tag, flush=True)
+            return 1
+        m0, c0, st0 = oracle.oracle_run_segmentation(cp, sp, C, offs, *opts)
+        if opts[0] == 0.0:  # (the scheduler's host build starts after the edge pass, which owns the same_different_bias rewrite)
+            rc, m1, c1, st = run_emul(emul, oracle, cp, sp, C, offs, opts)
+            if rc != 0 or st["merges"] != st0["merges"] or not _same(oracle, (m0, c0), (m1, c1)):
+                print("MISMATCH oracle vs scheduler", rc, tag, flush=True)
+                return 1
+        if not quant:
+            if not _same(oracle, (rmask, oracle._trim(rocls)), (m0, c0)):
+                print("MISMATCH reference vs oracle", tag, flush=True)
+                return 1
+        else:
+            nq += 1
+        if i % 200 == 199:
+            print("seed %d: %d cases ok (%d quantized), %.0f s" % (seed, i + 1, nq, time.time() - t0), flush=True)
+    print("seed %d: all %d cases ok (%d quantized), %.0f s" % (seed, n, nq, time.time() - t0), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
