@@ -1725,7 +1725,8 @@ MN_D void mn_pass_accept(const MnImage& im, MnSm& sm, int ncand, int npr) {
 // arrays never exceed 2 N ints (capacity < 2 * npix, and the pixels of all objects add up to N).  When a
 // round's arrays do not fit the active half, the live arrays are copied, packed, to the other half: one
 // scan over the objects (MN_GCL per step, one per thread), small arrays copied by their thread, large
-// ones by the whole block.  Costs ~1 ms and happens a handful of times per image.
+// ones by the whole block.  Costs ~1 ms and happens a handful of times per image.  A half holds 4 N ints: the packed
+// live arrays (<= 2 N) plus the new survivor arrays of one round (<= 2 N: its merges touch disjoint objects).
 MN_D void mn_pix_gc(const MnImage& im, MnSm& sm, const MnMergeArgs& A) {
   MN_SYNC();
   const int half = im.pix_cap / 2;

@@ -30,7 +30,7 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   im.cls = zalloc<int>(N);
   im.obj = zalloc<uint4>(N);
   im.parent = zalloc<int>(N);
-  im.pix_cap = 2 * (3 * N + 2048);
+  im.pix_cap = 2 * (4 * N + 2048);  // as ws_layout() of the library
   im.pix_pool = zalloc<int>(im.pix_cap);
   im.rec = zalloc<uint4>(E);
   // EMUL_HASH_PERMILLE: slots per 1000 records (default 1600); a tight table exercises the overflow area
@@ -39,7 +39,7 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   im.hash = zalloc<uint32_t>((size_t)im.hash_nbuckets * 8);
   im.hash_ovf_cap = 4096;
   im.hash_ovf = zalloc<uint32_t>(im.hash_ovf_cap);
-  im.qc_low_n = (int)(E * 8 / ((size_t)MN_QCH * 16));
+  im.qc_low_n = (int)((E * 8 + (size_t)MN_QCH * 16 - 1) / ((size_t)MN_QCH * 16));  // as ws_layout() of the library: rounded up
   im.qc_cap = im.qc_low_n + (int)(E * 9 / 20 / MN_QCH) + 4 * MN_NROOTS + 4096;
   im.q_ent = zalloc<uint4>((size_t)im.qc_cap * MN_QCH + 2 * MN_QCH);
   im.init_keys = (uint64_t*)im.q_ent;  // one arena, as in the library
