@@ -65,6 +65,31 @@ def tie_exact_cases():
     return out
 
 
+def layout_regression_cases():
+    """(name, class_pred, adj_pred, C, offsets, opts): inputs that broke the workspace layout until the end of round 2
+    (found by tests/manual/soak_sweep.py; see tests/test_emul_scheduler.py for what each one hit)."""
+    out = []
+    # (1) own queue chunks on top of the last E % 128 initial keys: one small offset, every priority >= 0, E > 1024
+    for (h, w, offs, seed) in [(31, 53, [(0, 1)], 1), (40, 47, [(0, 1)], 2), (30, 34, [(1, 0), (0, 1)], 3)]:
+        rng = np.random.default_rng(seed)
+        cp = rng.random((3, h, w)).astype(np.float32) * 0.2 + 0.1
+        cp[1] += 0.5                                                      # one dominant class: class deltas are 0
+        sp = rng.random((len(offs), h, w)).astype(np.float32) * 0.45 + 0.52  # "same" everywhere: every priority > 0
+        out.append(("keys_tail_%dx%d" % (h, w), synth.clip_probs(cp), synth.clip_probs(sp), 3, offs, (0.0, 1.0, 0.2)))
+    # (2) pixel pool: two blobs of 2^k + few pixels each that merge last (capacities 2^(k+1) + 2^(k+1) -> 2^(k+2))
+    h, w = 2, 2 * 1030
+    offs = [(0, 1), (1, 0), (1, 1)]
+    cp = np.full((2, h, w), 0.5, np.float32)
+    cp[1] = 0.6
+    sp = np.full((3, h, w), 0.9, np.float32)
+    rng = np.random.default_rng(5)
+    sp += (rng.random(sp.shape).astype(np.float32) - 0.5) * 0.05   # no ties
+    for k, (dr, dc) in enumerate(offs):                            # pairs across the middle are "different"
+        sp[k, :, 1030 - dc:1030] = 0.2
+    out.append(("two_halves_2x2060", synth.clip_probs(cp), synth.clip_probs(sp), 2, offs, (0.0, 1.0, 0.5)))
+    return out
+
+
 def small_cases():
     """(name, class_pred, adj_pred, C, offsets) -- the parity matrix."""
     out = []

@@ -147,7 +147,10 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
                        c->cuts_capacity, (long long)c->qc_bump, (long long)c->pix_gcs, (long long)c->tn_bump};
     memcpy(stats, v, sizeof(v));
   }
-  // (leaks on purpose: short-lived test process helper)
+  // (the long sweep, tests/manual/soak_sweep.py, calls this tens of thousands of times per process)
+  free(im.clp); free(im.cls); free(im.obj); free(im.parent); free(im.pix_pool); free(im.rec); free(im.hash);
+  free(im.hash_ovf); free(im.q_ent); free(im.qc_next); free(im.qc_free); free(im.tn); free(im.tn_dir); free(im.ctl);
+  free(sm); free(c_clp);
   return status;
 }
 

@@ -141,23 +141,11 @@ def test_pixel_pool_holds_two_huge_objects_merging(emul, oracle_mod):
 
 def test_pixel_pool_two_equal_halves_worst_case(emul, oracle_mod):
     """The constructed worst case: two blobs of 2^k + few pixels each (strong sameness inside, weak across) that merge
-    last under a large merge_logprob_bias."""
-    from mergenet_b200 import synth
-    h, w = 2, 2 * 1030  # two 2 x 1030 halves: 2060 pixels each (capacity 4096), merged 4120 (capacity 8192); N = 4120
-    offs = [(0, 1), (1, 0), (1, 1)]
-    cp = np.full((2, h, w), 0.5, np.float32)
-    cp[1] = 0.6
-    sp = np.full((3, h, w), 0.9, np.float32)
-    rng = np.random.default_rng(5)
-    sp += (rng.random(sp.shape).astype(np.float32) - 0.5) * 0.05   # no ties
-    for k, (dr, dc) in enumerate(offs):  # pairs across the middle are "different"
-        lo = 1030 - dc
-        sp[k, :, lo:1030] = 0.2
-    cp, sp = synth.clip_probs(cp), synth.clip_probs(sp)
-    opts = (0.0, 1.0, 0.5)  # the bias merges the two halves in the end anyway
-    m0, c0, st0 = oracle_mod.oracle_run_segmentation(cp, sp, 2, offs, *opts)
+    last under a large merge_logprob_bias (cases.layout_regression_cases)."""
+    name, cp, sp, C, offs, opts = [c for c in cases.layout_regression_cases() if c[0].startswith("two_halves")][0]
+    m0, c0, st0 = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)
     assert st0["final_objects"] == 1 and st0["max_abs_npix"] >= 1900, st0
-    rc, m1, c1, st = run_emul(emul, oracle_mod, cp, sp, 2, offs, opts)
+    rc, m1, c1, st = run_emul(emul, oracle_mod, cp, sp, C, offs, opts)
     assert rc == 0, rc
     assert st["merges"] == st0["merges"] and cases.same_result(oracle_mod, (m0, c0), (m1, c1))
 
@@ -169,20 +157,15 @@ def test_own_queue_chunks_start_behind_the_last_initial_key(emul, oracle_mod):
     merge_logprob_bias (every record starts with a priority >= 0) and more than 1024 records they are real entries:
     the first chunk written destroyed them and a later refill decoded garbage record ids (a crash on the host build, an
     illegal address on the GPU).  Chunks now start at ceil(8 E / 1024)."""
-    from mergenet_b200 import synth
-    for (h, w, offs, seed) in [(31, 53, [(0, 1)], 1), (40, 47, [(0, 1)], 2), (30, 34, [(1, 0), (0, 1)], 3)]:
-        K = len(offs)
+    todo = [c for c in cases.layout_regression_cases() if c[0].startswith("keys_tail")]
+    assert len(todo) == 3
+    for name, cp, sp, C, offs, opts in todo:
+        K, (h, w) = len(offs), cp.shape[1:]
         E = h * w * K
         oob = sum((h * w) - (h - abs(dr)) * (w - abs(dc)) for dr, dc in offs)
         assert E > 1024 and E % 128 > oob, (E, E % 128, oob)  # real keys in the last partial kilobyte of the key array
-        rng = np.random.default_rng(seed)
-        cp = rng.random((3, h, w)).astype(np.float32) * 0.2 + 0.1
-        cp[1] += 0.5                                                      # one dominant class: class deltas are 0
-        sp = rng.random((K, h, w)).astype(np.float32) * 0.45 + 0.52       # "same" everywhere: every priority > 0
-        cp, sp = synth.clip_probs(cp), synth.clip_probs(sp)
-        opts = (0.0, 1.0, 0.2)
-        m0, c0, st0 = oracle_mod.oracle_run_segmentation(cp, sp, 3, offs, *opts)
+        m0, c0, st0 = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)
         assert st0["init_pushes"] == st0["init_records"]  # no dormant record: no sentinel among the valid slots
-        rc, m1, c1, st = run_emul(emul, oracle_mod, cp, sp, 3, offs, opts)
-        assert rc == 0, (h, w, rc)
-        assert st["merges"] == st0["merges"] and cases.same_result(oracle_mod, (m0, c0), (m1, c1)), (h, w)
+        rc, m1, c1, st = run_emul(emul, oracle_mod, cp, sp, C, offs, opts)
+        assert rc == 0, (name, rc)
+        assert st["merges"] == st0["merges"] and cases.same_result(oracle_mod, (m0, c0), (m1, c1)), name

@@ -406,3 +406,14 @@ def test_saturated_maps_take_libm_special_values(oracle_mod, lib_mod):
             assert L.mn_last_error() == 0
             c1 = oracle_mod._trim(oc)
         assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), name
+
+
+def test_workspace_layout_regressions(oracle_mod, lib_mod):
+    """Inputs that broke the workspace layout until the end of round 2 (cases.layout_regression_cases): the
+    scheduler's own queue chunks overlaid the last E % 128 initial keys; a pixel-pool half of 3 N ints was too small
+    for two objects of just over 2^k pixels merging.  Through the drop-in C ABI on the real kernels."""
+    from mergenet_b200 import c_segment
+    for name, cp, sp, C, offs, opts in cases.layout_regression_cases():
+        m0, c0, _ = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)
+        m1, c1 = c_segment.run_segmentation(cp, sp, C, offs, *opts)
+        assert cases.same_result(oracle_mod, (m0, c0), (m1, c1)), name
