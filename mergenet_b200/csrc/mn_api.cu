@@ -364,26 +364,9 @@ static WsLayout ws_layout(int H, int W, int C, int K) {
   const size_t N = (size_t)H * W, E = N * K;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
-  // two halves.  After a collection the live arrays take at most 2 N ints (capacity = pow2 >= npix < 2 npix), and the new
-  // survivor arrays of ONE round at most 2 N more (its merges touch disjoint objects): 4 N ints per half always fit.
-  // (3 N did not: two objects of just over 2^k pixels each -- capacities 2^(k+1) -- merging into one of capacity
-  // 2^(k+2) need 4 x their pixel count; found by tests/manual/soak_sweep.py on a 59 x 75 image that collapses to
-  // one object, regression test in tests/test_emul_scheduler.py)
-  L.pix_cap = (int)(2 * (4 * N + 2048));
-  // One arena holds, in turn, the edge pass outputs rec_same | rec_diff (8 E bytes, dead after record
-  // init), the sorted initial keys (8 E bytes, written by the sort), and the queue chunks: the consumed
-  // prefix of the keys is recycled as chunks (qc_low_n of them), and qc_cap - qc_low_n extra chunks
-  // cover the early demand (measured: 0.30 E entries at 256x512).
-  // (rounded UP: the first chunk of the scheduler's own starts behind the LAST key.  Rounded down -- until the end of
-  // round 2 -- it overlaid the final E % 128 keys, which are sentinels of dormant / out-of-image slots on every usual
-  // shape (and E % 128 = 0 on all BASELINE shapes), but real entries when nearly every record starts with a priority
-  // >= 0 and few slots leave the image: one offset (0, 1) with a large merge_logprob_bias; found by
-  // tests/manual/soak_sweep.py, regression test in tests/test_emul_scheduler.py)
-  L.qc_low_n = (int)((E * 8 + (size_t)MN_QCH * 16 - 1) / ((size_t)MN_QCH * 16));
-  L.qc_cap = L.qc_low_n + (int)(E * 9 / 20 / MN_QCH + 4 * MN_NROOTS + 4096);
-  L.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)std::max<size_t>(4096, E / 512);  // measured: < E / 1700 splits
-  L.hash_nbuckets = (uint32_t)(E * 18 / 10 / 8 + 64);
-  L.hash_ovf_cap = 16384;
+  const MnCaps caps = mn_workspace_caps(N, E);  // (mn_layout.h: shared with the scheduler's host build)
+  L.pix_cap = caps.pix_cap; L.qc_low_n = caps.qc_low_n; L.qc_cap = caps.qc_cap; L.tn_cap = caps.tn_cap;
+  L.hash_nbuckets = caps.hash_nbuckets; L.hash_ovf_cap = caps.hash_ovf_cap;
   L.clp = take(N * C * 4);
   L.cls = take(N * 4);
   L.obj = take(N * 16);

@@ -149,6 +149,38 @@ struct MnImage {
   MnCtl* ctl;
 };
 
+// ---- capacities of the per-image pools (one definition for the library, mn_api.cu: ws_layout, and for the host build
+// of the scheduler that the CPU suite and the long seeded sweep run, tests/emul: a pool that is too small must show up
+// there, not on a user's image) ---------------------------------------------------------------------
+struct MnCaps {
+  int pix_cap, qc_low_n, qc_cap, tn_cap;
+  uint32_t hash_nbuckets, hash_ovf_cap;
+};
+MN_HD MnCaps mn_workspace_caps(size_t N, size_t E) {
+  MnCaps c;
+  // Pixel pool, two halves.  After a collection the live arrays take at most 2 N ints (capacity = pow2 >= npix < 2 npix),
+  // and the new survivor arrays of ONE round at most 2 N more (its merges touch disjoint objects): 4 N ints per half
+  // always fit.  (3 N did not: two objects of just over 2^k pixels each -- capacities 2^(k+1) -- merging into one of
+  // capacity 2^(k+2) need 4 x their pixel count; found by tests/manual/soak_sweep.py on a 59 x 75 image that collapses
+  // to one object, regression tests in tests/test_emul_scheduler.py and tests/test_gpu_parity.py)
+  c.pix_cap = (int)(2 * (4 * N + 2048));
+  // One arena holds, in turn, the edge pass outputs rec_same | rec_diff (8 E bytes, dead after record init), the sorted
+  // initial keys (8 E bytes, written by the sort), and the queue chunks: the consumed prefix of the keys is recycled as
+  // chunks (qc_low_n of them), and qc_cap - qc_low_n extra chunks cover the early demand (measured: 0.30 E entries at
+  // 256x512).  qc_low_n is rounded UP: the first chunk of the scheduler's own starts behind the LAST key.
+  // (Rounded down -- until the end of round 2 -- it overlaid the final E % 128 keys, which are sentinels of dormant /
+  // out-of-image slots on every usual shape (and E % 128 = 0 on all BASELINE shapes), but real entries when nearly every
+  // record starts with a priority >= 0 and few slots leave the image: one offset (0, 1) with a large
+  // merge_logprob_bias; found by tests/manual/soak_sweep.py, same regression tests)
+  c.qc_low_n = (int)((E * 8 + (size_t)MN_QCH * 16 - 1) / ((size_t)MN_QCH * 16));
+  c.qc_cap = c.qc_low_n + (int)(E * 9 / 20 / MN_QCH + 4 * MN_NROOTS + 4096);
+  const size_t splits = E / 512 > 4096 ? E / 512 : 4096;  // measured: < E / 1700 splits
+  c.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)splits;
+  c.hash_nbuckets = (uint32_t)(E * 18 / 10 / 8 + 64);
+  c.hash_ovf_cap = 16384;
+  return c;
+}
+
 // ---- the 16-byte record --------------------------------------------------------------------------
 // Guard state of a record = what is queued for it (the queue is lazy, see mn_merge.cuh):
 //   NONE   no entry is expected (fresh, or its guard was consumed);

@@ -30,22 +30,28 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   im.cls = zalloc<int>(N);
   im.obj = zalloc<uint4>(N);
   im.parent = zalloc<int>(N);
-  im.pix_cap = 2 * (4 * N + 2048);  // as ws_layout() of the library
+  // pool capacities: the library's own (mn_layout.h: mn_workspace_caps), so that a pool that is too small fails here.
+  // Two deliberate exceptions: EMUL_HASH_PERMILLE (slots per 1000 records; a tight table exercises the overflow area),
+  // and the stress builds with small tree leaves (-DMN_LEAFCAP < 512), which split far more often than the product.
+  const MnCaps caps = mn_workspace_caps((size_t)N, E);
+  im.pix_cap = caps.pix_cap;
   im.pix_pool = zalloc<int>(im.pix_cap);
   im.rec = zalloc<uint4>(E);
-  // EMUL_HASH_PERMILLE: slots per 1000 records (default 1600); a tight table exercises the overflow area
-  const long long permille = getenv("EMUL_HASH_PERMILLE") ? atoll(getenv("EMUL_HASH_PERMILLE")) : 1600;
-  im.hash_nbuckets = (uint32_t)(E * permille / 1000 / 8 + 64);
+  im.hash_nbuckets = caps.hash_nbuckets;
+  if (getenv("EMUL_HASH_PERMILLE")) im.hash_nbuckets = (uint32_t)(E * atoll(getenv("EMUL_HASH_PERMILLE")) / 1000 / 8 + 64);
   im.hash = zalloc<uint32_t>((size_t)im.hash_nbuckets * 8);
-  im.hash_ovf_cap = 4096;
+  im.hash_ovf_cap = caps.hash_ovf_cap;
   im.hash_ovf = zalloc<uint32_t>(im.hash_ovf_cap);
-  im.qc_low_n = (int)((E * 8 + (size_t)MN_QCH * 16 - 1) / ((size_t)MN_QCH * 16));  // as ws_layout() of the library: rounded up
-  im.qc_cap = im.qc_low_n + (int)(E * 9 / 20 / MN_QCH) + 4 * MN_NROOTS + 4096;
+  im.qc_low_n = caps.qc_low_n;
+  im.qc_cap = caps.qc_cap;
   im.q_ent = zalloc<uint4>((size_t)im.qc_cap * MN_QCH + 2 * MN_QCH);
   im.init_keys = (uint64_t*)im.q_ent;  // one arena, as in the library
   im.qc_next = zalloc<int>(im.qc_cap);
   im.qc_free = zalloc<int>(im.qc_cap);
+  im.tn_cap = caps.tn_cap;
+#if MN_LEAFCAP < 512
   im.tn_cap = MN_NROOTS + MN_TREE_FANOUT * (int)(16384 + E / 128);
+#endif
   im.tn = zalloc<int4>(im.tn_cap);
   im.tn_dir = zalloc<int>((size_t)im.tn_cap * 8);
   im.ctl = zalloc<MnCtl>(1);
