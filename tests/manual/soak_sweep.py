@@ -6,7 +6,7 @@
   * quantized maps (2-4 levels on blocks: thousands of exactly equal priorities): tie-exact replay == reference RAW,
     oracle == scheduler host build (both use the fixed tie rule).
 
-usage: python tests/manual/soak_sweep.py <seed> <n_cases> [max_h max_w] [emul .so]   (needs oracle/_ref, i.e. the build container)
+usage: python tests/manual/soak_sweep.py <seed> <n_cases> [max_h max_w] [emul .so | -] [wide]   (needs oracle/_ref, i.e. the build container)
 """
 import ctypes
 import os
@@ -54,13 +54,15 @@ def run_exact(lib, cp, sp, C, offs, opts):
     return rc, mask, ocls
 
 
-def random_case(rng, max_h, max_w):
+def random_case(rng, max_h, max_w, wide=False):
+    """wide: up to 16 offsets reaching 25 pixels, up to 40 classes (the COCO-shaped end of the range)"""
     h, w = int(rng.integers(1, max_h + 1)), int(rng.integers(1, max_w + 1))
-    C = int(rng.integers(1, 12))
-    K = int(rng.integers(1, 13))
+    C = int(rng.integers(1, 41 if wide else 12))
+    K = int(rng.integers(1, 17 if wide else 13))
+    reach = 25 if wide else 9
     offs = []
     while len(offs) < K:
-        o = (int(rng.integers(-9, 10)), int(rng.integers(-9, 10)))
+        o = (int(rng.integers(-reach, reach + 1)), int(rng.integers(-reach, reach + 1)))
         if o == (0, 0) or o in offs or (-o[0], -o[1]) in offs:
             continue
         offs.append(o)
@@ -93,14 +95,15 @@ def main():
     seed, n = int(sys.argv[1]), int(sys.argv[2])
     max_h = int(sys.argv[3]) if len(sys.argv) > 3 else 64
     max_w = int(sys.argv[4]) if len(sys.argv) > 4 else 80
-    emul = load_emul(sys.argv[5] if len(sys.argv) > 5 else os.path.join(HERE, "..", "emul", "libemul.so"))
+    emul = load_emul(sys.argv[5] if len(sys.argv) > 5 and sys.argv[5] != "-" else os.path.join(HERE, "..", "emul", "libemul.so"))
+    wide = len(sys.argv) > 6 and sys.argv[6] == "wide"
     exact = load_exact()
     rng = np.random.default_rng(seed)
     t0 = time.time()
     nq = 0
     nt = 0
     for i in range(n):
-        cp, sp, C, offs, opts, quant = random_case(rng, max_h, max_w)
+        cp, sp, C, offs, opts, quant = random_case(rng, max_h, max_w, wide)
         tag = (seed, i, cp.shape, sp.shape, offs, opts, quant)
         rmask, rocls, _ = make_golden_exact.reference_raw(cp, sp, C, offs, opts)
         rc, xm, xo = run_exact(exact, cp, sp, C, offs, opts)

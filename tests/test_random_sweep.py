@@ -74,3 +74,22 @@ def test_random_sweep_cuda_path_equals_oracle(oracle_mod, lib_mod):
         m0, c0, _ = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)
         m1, c1 = c_segment.run_segmentation(cp, sp, C, offs, *opts)
         assert _same(oracle_mod, (m0, c0), (m1, c1)), (i, cp.shape, sp.shape, offs, opts)
+
+
+@pytest.mark.gpu
+def test_random_sweep_wide_cuda_path_equals_oracle(oracle_mod, lib_mod):
+    """The generator of the long seeded sweep (tests/manual/soak_sweep.py) through the drop-in C ABI: up to 16 offsets
+    reaching 25 pixels, up to 40 classes, quantized maps (thousands of exact ties: oracle and CUDA path share the fixed
+    tie rule, so they must agree there too), same_different_bias != 0 (the in-place rewrite of the edge pass), shapes
+    whose record count is not a multiple of anything."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "manual"))
+    from soak_sweep import random_case
+    from mergenet_b200 import c_segment
+    for seed, wide, n in [(20261101, True, 50), (20261102, False, 50)]:
+        rng = np.random.default_rng(seed)
+        for i in range(n):
+            cp, sp, C, offs, opts, quant = random_case(rng, 64, 80, wide)
+            m0, c0, _ = oracle_mod.oracle_run_segmentation(cp, sp, C, offs, *opts)
+            m1, c1 = c_segment.run_segmentation(cp, sp.copy(), C, offs, *opts)
+            assert _same(oracle_mod, (m0, c0), (m1, c1)), (seed, i, cp.shape, sp.shape, offs, opts, quant)
