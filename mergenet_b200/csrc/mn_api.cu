@@ -1194,6 +1194,8 @@ extern "C" int mn_exact_segment_host(const float* h_class, int C, float* h_adj, 
   if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_in_adj, h_adj, (size_t)K * N * 4, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = cudaMemcpyAsync((void*)m.arena.primes, primes, sizeof(primes), cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = cudaMemsetAsync(sc, 0, 256, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(m.out_mask, 0, N * 4, s);     // a failed run leaves (0, -1), like the drop-in symbol
+  if (e == cudaSuccess) e = cudaMemsetAsync(m.out_cls, 0xFF, N * 4, s);
   if (e != cudaSuccess) return done(MN_STATUS_CUDA);
   // edge pass (+ the record init of the hot path, unused here) exactly as the drop-in symbol runs it
   // (like the drop-in symbol, any floats are accepted: out-of-domain maps take the kernel with libm's special values)
