@@ -149,6 +149,17 @@ def test_exact_replay_on_host_equals_live_reference(emul_exact):
             fixed = oracle.oracle_run_segmentation(cp, sp, C, offs, *opts)[:2]
             differ += 0 if cases.same_result(oracle, (rmask, oracle._trim(rocls)), fixed) else 1
     assert differ >= 3  # these inputs do depend on the tie order: the fixed rule gives another partition
+    # ... and the generator of the long seeded sweep (tests/manual/soak_sweep.py): quantized / noisy / smooth / soft
+    # maps, 1-16 offsets, same_different_bias
+    sys.path.insert(0, os.path.join(HERE, "manual"))
+    from soak_sweep import random_case
+    for seed, wide, n in [(20261105, False, 150), (20261106, True, 100)]:
+        rng = np.random.default_rng(seed)
+        for i in range(n):
+            cp, sp, C, offs, opts, quant = random_case(rng, 48, 56, wide)
+            rmask, rocls, _ = make_golden_exact.reference_raw(cp, sp, C, offs, opts)
+            rc, mask, ocls, st = emul_exact(cp, sp, C, offs, opts)
+            assert rc == 0 and np.array_equal(mask, rmask) and np.array_equal(ocls, rocls), (seed, i, cp.shape, sp.shape, offs, opts, quant)
 
 
 @pytest.mark.gpu
