@@ -49,6 +49,9 @@ enum {
  * (the reference's own c_segment.pyx) cannot see a status -- one line naming the status goes to stderr.
  * Nothing is printed on success (the reference's progress lines, segment.cc:540-569, are not reproduced).
  * Shape limits: those of mn_plan_create below.
+ * With MN_TIE_ORDER=reference in the environment the call runs the tie-exact replay (mn_exact_segment_host below)
+ * instead of the hot path: the reference's RAW arrays also on inputs whose partition depends on the order among
+ * exactly equal priorities, at sequential speed -- a switch for callers that bind this symbol directly.
  */
 void c_run_segmentation(float* class_pred, int class_dim, float* adj_pred, int offset_dim,
                         int img_width, int img_height, int num_classes, int* offset_list,

@@ -944,6 +944,24 @@ extern "C" void c_run_segmentation(float* class_pred, int class_dim, float* adj_
     fail(MN_STATUS_BAD_ARG);
     return;
   }
+  // MN_TIE_ORDER=reference in the environment: the tie-exact replay (mn_exact_segment_host) instead of the hot path, for
+  // callers that link this symbol directly (the reference's own c_segment.pyx) and need the reference's RAW arrays also on
+  // inputs whose partition depends on the order among exactly equal priorities.  Sequential; anything else: the hot path.
+  if (const char* tie = getenv("MN_TIE_ORDER")) {
+    if (strcmp(tie, "reference") == 0) {
+      int ninst_exact = 0;
+      const int rc = mn_exact_segment_host(class_pred, num_classes, adj_pred, offset_dim, img_height, img_width, offset_list,
+                                           0, sdb, omf, mlb, output, object_class, &ninst_exact, nullptr);
+      if (rc != MN_STATUS_OK) {
+        if (N > 0) {
+          memset(output, 0, sizeof(int) * (size_t)N);
+          memset(object_class, 0xFF, sizeof(int) * (size_t)N);
+        }
+        fail(rc);
+      }
+      return;
+    }
+  }
   int device = 0;
   if (cudaGetDevice(&device) != cudaSuccess) { fail(MN_STATUS_CUDA); return; }  // the caller's current device
   PlanCache& c = g_cache;

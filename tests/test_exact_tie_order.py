@@ -214,3 +214,23 @@ def test_exact_gpu_bucket_arena_collection():
             os.environ.pop("MN_EXACT_ARENA_WORDS", None)
         else:
             os.environ["MN_EXACT_ARENA_WORDS"] = old
+
+
+@pytest.mark.gpu
+def test_drop_in_symbol_with_reference_tie_order(monkeypatch):
+    """MN_TIE_ORDER=reference: the drop-in symbol itself (what the reference's own Cython binding links) runs the
+    tie-exact replay -- raw arrays of the reference on a tie-dependent fixture; without the variable, the hot path."""
+    import oracle
+    from mergenet_b200 import c_segment
+    g, offs, opts = _load([f for f in FIXTURES if f.endswith("quant_24x32_a.npz")][0])
+    assert int(g["tie_dependent"]) == 1
+    ref_list = [int(v) for v in g["ref_object_class"][0, :int(g["ref_mask"].max())]]
+    monkeypatch.setenv("MN_TIE_ORDER", "reference")
+    mask, ocls = c_segment.run_segmentation(g["class_pred"], g["adj_pred"].copy(), int(g["num_classes"]), offs, *opts)
+    assert np.array_equal(mask, g["ref_mask"]) and [int(c) for c in ocls] == ref_list
+    monkeypatch.delenv("MN_TIE_ORDER")
+    mask2, ocls2 = c_segment.run_segmentation(g["class_pred"], g["adj_pred"].copy(), int(g["num_classes"]), offs, *opts)
+    assert not cases.same_result(oracle, (mask, list(ocls)), (mask2, list(ocls2)))  # the fixed tie rule: another partition
+    monkeypatch.setenv("MN_TIE_ORDER", "fixed")  # anything but "reference": the hot path
+    mask3, ocls3 = c_segment.run_segmentation(g["class_pred"], g["adj_pred"].copy(), int(g["num_classes"]), offs, *opts)
+    assert np.array_equal(mask3, mask2)
