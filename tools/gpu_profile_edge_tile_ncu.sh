@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, session 3i: GPU suite, bench line, Mode B wall time, ncu capture of the tile edge kernel (tensor-map loads) on cfg4
+# profiling recipe (round 2): GPU suite, bench line, Mode B wall time, ncu capture of the tile edge kernel (tensor-map loads) on cfg4
 tag=${1:-s3i}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc $?"; tail -3 gpurun_out/${tag}_pytest.log

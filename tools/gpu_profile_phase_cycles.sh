@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, session 2: fresh per-phase cycle buckets (profiling build made on the box) + ncu source-level capture of the
+# profiling recipe (round 2): fresh per-phase cycle buckets (profiling build made on the box) + ncu source-level capture of the
 # merge kernel on one 256x512 image, exported to CSV on the box
 tag=${1:-s2}
 mkdir -p gpurun_out /tmp/mn_prof

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, session 3b: GPU suite, bench line, ncu launch list of the bench command, ncu captures of the partition
+# profiling recipe (round 2): GPU suite, bench line, ncu launch list of the bench command, ncu captures of the partition
 # statistics pass (full) and of the merge kernel on the whole GPU (148 CTAs, 512x1024 images: the workspace of 148
 # full-size images cannot be saved and restored between ncu's replay passes)
 tag=${1:-s3b}
