@@ -177,6 +177,10 @@ int mn_modeb_segment_host(const float* h_log_class, const float* h_log_same, con
  * images, not the hot path.  Arguments as c_run_segmentation (host buffers; h_adj rewritten in place when
  * same_different_bias != 0), with height before width and the batch entries' `clip` flags.
  * stats4 (optional): queue pops, merges, queue pushes, bucket-arena collections.
+ * Failures are loud and leave (0, -1) in the outputs: MN_STATUS_Q_POOL (more than 8 E queue entries alive at once),
+ * MN_STATUS_PL_POOL (the live bucket arrays exceed 5 E + 32 N words), MN_STATUS_BAD_ARG (shape limits; an offset list
+ * that names one pixel pair twice, which the reference leaves undefined), MN_STATUS_INTERNAL (an adjacency list the
+ * reference itself would exit(1) on, segment.cc:664-673).
  */
 int mn_exact_segment_host(const float* h_class, int num_classes, float* h_adj, int num_offsets, int height, int width,
                           const int* offset_list, int clip, float same_different_bias, float object_merge_factor,
