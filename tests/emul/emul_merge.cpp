@@ -160,6 +160,14 @@ extern "C" int emul_run_segmentation(const float* class_pred, int class_dim, con
   return status;
 }
 
+// The pool capacities of the library (mn_layout.h: mn_workspace_caps) for a shape, so that the CPU suite can check their
+// invariants directly: {pix_cap, qc_low_n, qc_cap, tn_cap, hash_nbuckets, hash_ovf_cap, MN_QCH}.
+extern "C" void emul_workspace_caps(long long N, long long E, long long* out7) {
+  const MnCaps c = mn_workspace_caps((size_t)N, (size_t)E);
+  out7[0] = c.pix_cap; out7[1] = c.qc_low_n; out7[2] = c.qc_cap; out7[3] = c.tn_cap;
+  out7[4] = c.hash_nbuckets; out7[5] = c.hash_ovf_cap; out7[6] = MN_QCH;
+}
+
 // The accept pass compares 64-bit pop keys instead of full (mp, tie) orders: whenever entry a pops
 // before entry b, key(a) >= key(b) must hold (equal keys are treated as "pops first": the safe side).
 // Returns the number of violations over n random pairs (many of them tied on mp, close in lo/hi).

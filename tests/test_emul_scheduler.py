@@ -169,3 +169,25 @@ def test_own_queue_chunks_start_behind_the_last_initial_key(emul, oracle_mod):
         rc, m1, c1, st = run_emul(emul, oracle_mod, cp, sp, C, offs, opts)
         assert rc == 0, (name, rc)
         assert st["merges"] == st0["merges"] and cases.same_result(oracle_mod, (m0, c0), (m1, c1)), name
+
+
+def test_workspace_capacity_invariants(emul):
+    """mn_workspace_caps (one definition for the library and this host build): the scheduler's own queue chunks start
+    behind the last initial key for EVERY record count, a pixel-pool half holds 4 N ints, and the shapes at the limits
+    of mn_plan_create do not overflow the int fields."""
+    emul.emul_workspace_caps.restype = None
+    emul.emul_workspace_caps.argtypes = [ctypes.c_longlong, ctypes.c_longlong, ctypes.POINTER(ctypes.c_longlong)]
+    rng = np.random.default_rng(3)
+    shapes = [(1, 1), (1643, 1643), (4425, 4425 * 11), (2 ** 21, 10 * 2 ** 21), (2 ** 24 - 1, 2 ** 25), (2 ** 24 - 1, 2 ** 24 - 1)]
+    shapes += [(int(n), int(n) * int(k)) for n, k in zip(rng.integers(1, 2 ** 21, 2000), rng.integers(1, 17, 2000))]
+    for N, E in shapes:
+        if E > 2 ** 25:
+            continue
+        out = (ctypes.c_longlong * 7)()
+        emul.emul_workspace_caps(N, E, out)
+        pix_cap, qc_low_n, qc_cap, tn_cap, nb, ovf, qch = list(out)
+        chunk_bytes = qch * 16
+        assert qc_low_n * chunk_bytes >= 8 * E > (qc_low_n - 1) * chunk_bytes, (N, E)   # ceil(8 E / chunk bytes)
+        assert qc_cap > qc_low_n and (qc_cap - qc_low_n) * qch >= 0.45 * E, (N, E)
+        assert pix_cap // 2 >= 4 * N + 2048 and pix_cap < 2 ** 31, (N, E)
+        assert tn_cap >= 8 * max(4096, E // 512) and nb * 8 >= 1.8 * E and ovf >= 128, (N, E)
