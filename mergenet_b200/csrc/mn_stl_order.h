@@ -33,11 +33,16 @@ struct MnStlTab {          // one std::unordered_map<size_t, T*>
   long long boff;          // where the bucket array lives in the arena (nbkt > 1)
 };
 
-struct MnStlArena {        // bucket arrays of every table: two half-spaces, bump allocated in the current one.  A table
-  int* bk;                 // abandons its array when it grows and when its object dies; when the current half is full
-  long long half;          // the live arrays (tables with nbkt > 1) are copied to the other half (bucket words hold
-  long long* bump;         // node ids, not addresses, so they move freely).  The live arrays never exceed
-  long long* base;         // ~2.3 x (2 records per pixel pair) + 13 per object words: a half of 5 E + 32 N always fits.
+// Bucket arrays of every table: two half-spaces, bump allocated in the current one.  A table abandons its array when it
+// grows and when its owner dies; when the current half is full the live arrays (tables with nbkt > 1) are copied, packed,
+// to the other half -- bucket words hold node ids, not addresses, so they move freely.  The live arrays stay below
+// ~2.3 x (2 nodes per record) + 13 per object words (measured peak: ~3 words per record slot); a half of 5 E + 32 N
+// words always fits.
+struct MnStlArena {
+  int* bk;                 // 2 * half words
+  long long half;
+  long long* bump;         // next free word
+  long long* base;         // start of the current half (0 or half)
   MnStlTab* tabs;          // every table that may own an array, for the collection
   int ntabs;
   const unsigned* primes;  // MN_STL_PRIMES
