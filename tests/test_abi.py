@@ -53,6 +53,19 @@ def test_wrapper_argument_errors_match_cython(lib_mod):
         c_segment.run_segmentation(a, a, 2, None, 0, 1, 0)
 
 
+def test_exact_wrapper_keeps_the_same_argument_checks(lib_mod):
+    from mergenet_b200 import c_segment, segmenter
+    a = np.zeros((2, 4, 4), np.float32)
+    with pytest.raises(TypeError):
+        c_segment.run_segmentation_exact(None, a, 2, [(0, 1)], 0, 1, 0)
+    with pytest.raises(ValueError):
+        c_segment.run_segmentation_exact(a, a.astype(np.float64), 2, [(0, 1)], 0, 1, 0)
+    with pytest.raises(TypeError):
+        c_segment.run_segmentation_exact(a, a, 2, ((0, 1),), 0, 1, 0)
+    with pytest.raises(ValueError):
+        segmenter.ObjectSegmenter(a, a, 2, [(0, 1), (1, 0)], mode="exact")
+
+
 def test_no_cpu_fallback(lib_mod):
     """Without a device the product path must fail loudly, never compute."""
     L = lib_mod.lib()
