@@ -89,3 +89,28 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "liboracle" not in text and "libsegment_ref" not in text, f
+
+
+def test_tie_order_switch_without_a_device_fails_loudly(lib_mod, monkeypatch, capfd):
+    """MN_TIE_ORDER=reference routes the drop-in symbol to the tie-exact replay; without a device that route, like the
+    hot path, leaves (0, -1) in the outputs, sets the status and says so on stderr."""
+    import ctypes
+    L = lib_mod.lib()
+    if L.mn_device_count() > 0:
+        pytest.skip("a GPU is present")
+    F, I = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)
+    cp = np.full((2, 4, 5), 0.5, np.float32)
+    sp = np.full((2, 4, 5), 0.5, np.float32)
+    off = np.array([[0, 1], [1, 0]], np.int32)
+    for value in ("reference", "fixed", None):
+        if value is None:
+            monkeypatch.delenv("MN_TIE_ORDER", raising=False)
+        else:
+            monkeypatch.setenv("MN_TIE_ORDER", value)
+        mask = np.full((4, 5), 7, np.int32)
+        ocls = np.full(20, 7, np.int32)
+        L.c_run_segmentation(cp.ctypes.data_as(F), 2, sp.ctypes.data_as(F), 2, 5, 4, 2, off.ctypes.data_as(I),
+                             mask.ctypes.data_as(I), ocls.ctypes.data_as(I), 0.0, 1.0, 0.0)
+        assert L.mn_last_error() == 7, value
+        assert (mask == 0).all() and (ocls == -1).all(), value
+        assert "c_run_segmentation failed" in capfd.readouterr().err, value
